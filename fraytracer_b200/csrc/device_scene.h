@@ -1,0 +1,73 @@
+// device_scene.h -- the compiled scene as it lives in HBM (and as the host compiler emits it).
+//
+// Everything is a handful of flat arrays (structure-of-arrays at the array level, 16-byte records inside
+// so that every access is one vectorised LDG.128 / LDG.64 through the read-only path):
+//
+//   nodes[]   float4   form nodes, variable length records.  A node is addressed by a 32-bit "word":
+//                      bits 31..28 = kind code (FT_K_*), bits 27..0 = index of its first float4.
+//                      record[0] is always the bounding sphere {cx,cy,cz,r} (Types.fs:19-24).
+//       sphere    [0] {C, R}                                  (its distance IS the bound test's value)
+//       capsule   [1] {From, R} [2] {dir, -} [3] {dirInv, -}                       (SdfForm.fs:148-164)
+//       torus     [1] {N, planeD} [2] {Major, Minor, -, -}      (C = bound centre)  (SdfForm.fs:182-194)
+//       triangle  [1] {V1,R} [2] {V2} [3] {V3} [4] {v21} [5] {v32} [6] {v13} [7] {v21'} [8] {v32'}
+//                 [9] {v13'} [10] {nor} [11] {n21} [12] {n32} [13] {n13}             (SdfForm.fs:216-250)
+//       union     [1] {aabbMin, bits(cellBase)} [2] {cellSizeInv, -} [3] bits{cx-1, cy-1, cz-1, cy*cz}
+//                                                                 (SdfBoundary.fs:276-282, SdfForm.fs:22-34)
+//       subtract  [1] bits{word a, word b, -, -}                                    (SdfForm.fs:45-47)
+//       intersect [1] bits{nchild, linkBase, -, -}    links[linkBase+i] = child word (SdfForm.fs:58-64)
+//       smooth    [1] {strength, -1/strength, bits(nchild), bits(linkBase)}         (SdfForm.fs:75-82)
+//   cells[]   float4   {centre.xyz, bits(entryBegin)} per grid cell, x-major like the .NET [,,] array
+//   entries[] uint2    {bits(LowerBound), child word}; each cell's list is sorted ascending by LowerBound
+//                      (SdfBoundary.fs:267-268) and closed by a sentinel {+inf, 0}: the loop
+//                      `if !(min > lb - dtc) break` is exactly equivalent to the reference's full scan
+//                      because the list is sorted and `min` never grows (DESIGN.md "early exit").
+//   entry_child[] int  child position inside the union (for the material arg-min and introspection)
+//   objects[] int4     {kind, form word, a, b}: LEAF a=material b=leaf id | UNION a=objLinkBase b=unused
+//                      | SUBTRACT/INTERSECT a=base object
+//   obj_links[] int    object index of child i of an object union
+//   materials[] float4 {r,g,b,-}
+//   lights[]  float4x2 {bits(kind), v.xyz} {rgb, -}   v = normalize(-direction) or the position
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
+struct int4 { int x, y, z, w; };
+#endif
+
+enum : uint32_t {
+    FT_K_SPHERE = 1,
+    FT_K_CAPSULE = 2,
+    FT_K_TORUS = 3,
+    FT_K_TRIANGLE = 4,
+    FT_K_UNION = 8,
+    FT_K_SUBTRACT = 9,
+    FT_K_INTERSECT = 10,
+    FT_K_SMOOTH = 11,
+};
+#define FT_WORD(kind, off) (((uint32_t)(kind) << 28) | (uint32_t)(off))
+#define FT_WORD_KIND(w) ((w) >> 28)
+#define FT_WORD_OFF(w) ((w)&0x0FFFFFFFu)
+#define FT_IS_PRIMITIVE(w) (((w) >> 31) == 0u)
+
+#define FT_DEV_MAX_LIGHTS 32
+
+struct DevScene {
+    const float4 *nodes;
+    const float4 *cells;
+    const uint2 *entries;
+    const int32_t *entry_child;
+    const uint32_t *links;
+    const int4 *objects;
+    const int32_t *obj_links;
+    const float4 *materials;
+    const float4 *lights;
+    uint32_t root_word;   // form word of scene.Object.Form
+    int32_t root_object;
+    int32_t n_lights;
+    int32_t step_cap;
+    float bg[3];
+};

@@ -1,0 +1,579 @@
+// ft_api.cu -- the C ABI of include/fraytracer_b200.h: scene handles, device memory, streams, stats.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "scene_compiler.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return FT_ERR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation) return FT_ERR_OUT_OF_MEMORY;
+    return FT_ERR_CUDA;
+}
+#define CU(call)                                           \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+cudaError_t upload(const std::vector<T> &v, const T **out, int64_t *bytes) {
+    T *d = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&d, n);
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) {
+        e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return e;
+        }
+    }
+    *out = d;
+    *bytes += (int64_t)n;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+struct ft_scene {
+    int device = 0;
+    int sm_count = 0;
+    ftc::CompiledScene host;
+    DevScene dev{};
+    int64_t device_bytes = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long *d_stats = nullptr, *h_stats = nullptr;
+    // scratch for the host-pointer entry points, grown on demand
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::mutex mu;
+
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= scratch_bytes) return cudaSuccess;
+        if (d_scratch) cudaFree(d_scratch);
+        d_scratch = nullptr;
+        scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&d_scratch, bytes);
+        if (e == cudaSuccess) scratch_bytes = bytes;
+        return e;
+    }
+    void release() {
+        const void *ptrs[] = {dev.nodes, dev.cells, dev.entries, dev.entry_child, dev.links,
+                              dev.objects, dev.obj_links, dev.materials, dev.lights};
+        for (const void *p : ptrs)
+            if (p) cudaFree(const_cast<void *>(p));
+        if (d_stats) cudaFree(d_stats);
+        if (h_stats) cudaFreeHost(h_stats);
+        if (d_scratch) cudaFree(d_scratch);
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+};
+
+namespace {
+
+constexpr size_t kStatWords = (size_t)FT_STAT_SLOTS * FT_STAT_STRIDE;
+
+void sum_stats(const unsigned long long *h, ft_render_stats *st) {
+    unsigned long long hits = 0, shadow = 0, capped = 0, steps = 0, flops = 0;
+    for (int s = 0; s < FT_STAT_SLOTS; s++) {
+        const unsigned long long *p = h + (size_t)s * FT_STAT_STRIDE;
+        hits += p[FT_STAT_HITS];
+        shadow += p[FT_STAT_SHADOW];
+        capped += p[FT_STAT_CAPPED];
+        steps += p[FT_STAT_STEPS];
+        flops += p[FT_STAT_FLOPS];
+    }
+    st->primary_hits = (int64_t)hits;
+    st->shadow_rays = (int64_t)shadow;
+    st->capped_rays = (int64_t)capped;
+    st->march_steps = (int64_t)steps;
+    st->eval_flops = (int64_t)flops;
+}
+
+int check_ray_params(float epsilon, float length) {
+    if (!(epsilon > 0.0f))
+        return fail(FT_ERR_INVALID_ARGUMENT,
+                    "epsilon must be > 0: with epsilon <= 0 the reference's march loop (SdfForm.fs:93-104) need not "
+                    "terminate");
+    if (std::isnan(length)) return fail(FT_ERR_INVALID_ARGUMENT, "length is NaN");
+    return FT_OK;
+}
+
+RenderParams make_params(int width, int height, float eps, float length, int strip_width, int rank, int world) {
+    RenderParams P;
+    P.width = width;
+    P.height = height;
+    P.strip_width = strip_width;
+    P.rank = rank;
+    P.world = world;
+    P.x_offset = 0;
+    const int strips = (width + strip_width - 1) / strip_width;
+    const int spr = (strips + world - 1) / world;
+    P.local_cols = world == 1 ? width : spr * strip_width;
+    P.epsilon = eps;
+    P.length = length;
+    P.max_size = (float)std::max(width, height);  // Image.fs:18
+    return P;
+}
+
+}  // namespace
+
+extern "C" {
+
+FT_API int ft_abi_version(void) { return FT_ABI_VERSION; }
+
+FT_API const char *ft_last_error(void) { return g_last_error.c_str(); }
+
+FT_API int ft_device_count(int *count) {
+    if (!count) return fail(FT_ERR_INVALID_ARGUMENT, "count is null");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return cuda_fail(e, "cudaGetDeviceCount");
+    }
+    return FT_OK;
+}
+
+FT_API float ft_lens_create(float field_of_view) { return ftc::lens_create(field_of_view); }
+
+FT_API int ft_camera_look_at(const float position[3], const float look_at[3], const float up[3], float near_plane_size,
+                             ft_camera *out) {
+    if (!position || !look_at || !up || !out) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    ftc::camera_look_at(position, look_at, up, near_plane_size, out);
+    return FT_OK;
+}
+
+FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out) {
+    if (!out) return fail(FT_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    ft_scene *s = new (std::nothrow) ft_scene();
+    if (!s) return fail(FT_ERR_OUT_OF_MEMORY, "host allocation failed");
+    std::string err;
+    int st;
+    try {
+        st = ftc::compile_scene(desc, &s->host, &err);
+    } catch (const std::bad_alloc &) {
+        delete s;
+        return fail(FT_ERR_OUT_OF_MEMORY, "host allocation failed while compiling the scene");
+    } catch (const std::exception &ex) {
+        delete s;
+        return fail(FT_ERR_INVALID_ARGUMENT, std::string("scene compiler: ") + ex.what());
+    }
+    if (st != FT_OK) {
+        delete s;
+        return fail(st, err);
+    }
+    if (device == FT_DEVICE_NONE) {  // compile-only handle: introspection works, every compute call fails
+        s->device = FT_DEVICE_NONE;
+        *out = s;
+        return FT_OK;
+    }
+    // no CPU fallback: a scene only renders on a device
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        delete s;
+        return fail(FT_ERR_NO_DEVICE, std::string("no CUDA device available (") +
+                                          (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                          "); fraytracer_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) {
+        delete s;
+        return fail(FT_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    }
+    s->device = device;
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete s;
+        return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    }
+    auto bail = [&](cudaError_t ce, const char *what) {
+        int code = cuda_fail(ce, what);
+        s->release();
+        delete s;
+        return code;
+    };
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    s->sm_count = prop.multiProcessorCount;
+    const ftc::CompiledScene &h = s->host;
+    int64_t bytes = 0;
+    if ((e = upload(h.nodes, &s->dev.nodes, &bytes)) != cudaSuccess) return bail(e, "upload nodes");
+    if ((e = upload(h.cells, &s->dev.cells, &bytes)) != cudaSuccess) return bail(e, "upload cells");
+    if ((e = upload(h.entries, &s->dev.entries, &bytes)) != cudaSuccess) return bail(e, "upload entries");
+    if ((e = upload(h.entry_child, &s->dev.entry_child, &bytes)) != cudaSuccess) return bail(e, "upload entry_child");
+    if ((e = upload(h.links, &s->dev.links, &bytes)) != cudaSuccess) return bail(e, "upload links");
+    if ((e = upload(h.objects, &s->dev.objects, &bytes)) != cudaSuccess) return bail(e, "upload objects");
+    if ((e = upload(h.obj_links, &s->dev.obj_links, &bytes)) != cudaSuccess) return bail(e, "upload obj_links");
+    if ((e = upload(h.materials, &s->dev.materials, &bytes)) != cudaSuccess) return bail(e, "upload materials");
+    if ((e = upload(h.lights, &s->dev.lights, &bytes)) != cudaSuccess) return bail(e, "upload lights");
+    s->device_bytes = bytes;
+    s->dev.root_word = h.root_word;
+    s->dev.root_object = h.root_object;
+    s->dev.n_lights = h.n_lights;
+    s->dev.step_cap = 1 << 22;
+    s->dev.bg[0] = h.bg[0];
+    s->dev.bg[1] = h.bg[1];
+    s->dev.bg[2] = h.bg[2];
+    if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (auto &ev : s->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&s->d_stats, kStatWords * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc stats");
+    if ((e = cudaMemset(s->d_stats, 0, kStatWords * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset stats");
+    if ((e = cudaMallocHost(&s->h_stats, kStatWords * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMallocHost stats");
+    *out = s;
+    return FT_OK;
+}
+
+FT_API int ft_scene_destroy(ft_scene *scene) {
+    if (!scene) return FT_OK;
+    if (scene->device != FT_DEVICE_NONE) {
+        DeviceGuard guard(scene->device);
+        if (scene->stream) cudaStreamSynchronize(scene->stream);
+        scene->release();
+    }
+    delete scene;
+    return FT_OK;
+}
+
+FT_API int ft_scene_info_get(const ft_scene *scene, ft_scene_info *out) {
+    if (!scene || !out) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    const ftc::CompiledScene &h = scene->host;
+    out->n_nodes = h.n_nodes;
+    out->n_primitives = h.n_primitives;
+    out->n_grids = (int32_t)h.grids.size();
+    out->max_depth = h.max_depth;
+    out->n_cells = 0;
+    out->n_entries = 0;
+    for (const auto &g : h.grids) {
+        out->n_cells += g.n_cells;
+        out->n_entries += g.n_entries;
+    }
+    out->device_bytes = scene->device_bytes;
+    out->device = scene->device;
+    out->sm_count = scene->sm_count;
+    return FT_OK;
+}
+
+FT_API int ft_scene_set_step_cap(ft_scene *scene, int32_t max_steps) {
+    if (!scene || max_steps < 1) return fail(FT_ERR_INVALID_ARGUMENT, "invalid step cap");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    scene->dev.step_cap = max_steps;
+    return FT_OK;
+}
+
+FT_API int ft_scene_grid_count(const ft_scene *scene, int32_t *count) {
+    if (!scene || !count) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    *count = (int32_t)scene->host.grids.size();
+    return FT_OK;
+}
+
+FT_API int ft_scene_grid_info(const ft_scene *scene, int32_t grid, ft_grid_info *out) {
+    if (!scene || !out || grid < 0 || grid >= (int32_t)scene->host.grids.size())
+        return fail(FT_ERR_INVALID_ARGUMENT, "grid index out of range");
+    const ftc::GridHost &g = scene->host.grids[(size_t)grid];
+    out->node = g.node;
+    for (int k = 0; k < 3; k++) {
+        out->count[k] = g.count[k];
+        out->aabb_min[k] = g.aabb_min[k];
+        out->cell_size[k] = g.cell_size[k];
+        out->cell_size_inv[k] = g.cell_size_inv[k];
+    }
+    out->n_entries = g.n_entries;
+    return FT_OK;
+}
+
+FT_API int ft_scene_grid_read(const ft_scene *scene, int32_t grid, float *cell_centers, int64_t *cell_begin,
+                              float *entry_lower_bound, int32_t *entry_item) {
+    if (!scene || grid < 0 || grid >= (int32_t)scene->host.grids.size())
+        return fail(FT_ERR_INVALID_ARGUMENT, "grid index out of range");
+    const ftc::GridHost &g = scene->host.grids[(size_t)grid];
+    std::vector<float4> cells((size_t)g.n_cells);
+    const size_t n_dev_entries = scene->host.entries.size();
+    std::vector<uint2> entries(n_dev_entries);
+    std::vector<int32_t> child(n_dev_entries);
+    if (scene->device == FT_DEVICE_NONE) {  // compile-only handle: the arrays that would have been uploaded
+        std::copy(scene->host.cells.begin() + g.cell_base, scene->host.cells.begin() + g.cell_base + g.n_cells, cells.begin());
+        entries = scene->host.entries;
+        child = scene->host.entry_child;
+    } else {  // read back what the kernels actually see
+        DeviceGuard guard(scene->device);
+        CU(cudaMemcpy(cells.data(), scene->dev.cells + g.cell_base, sizeof(float4) * (size_t)g.n_cells, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(entries.data(), scene->dev.entries, sizeof(uint2) * n_dev_entries, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(child.data(), scene->dev.entry_child, sizeof(int32_t) * n_dev_entries, cudaMemcpyDeviceToHost));
+    }
+    int64_t off = 0;
+    for (int64_t c = 0; c < g.n_cells; c++) {
+        if (cell_centers) {
+            cell_centers[3 * c] = cells[(size_t)c].x;
+            cell_centers[3 * c + 1] = cells[(size_t)c].y;
+            cell_centers[3 * c + 2] = cells[(size_t)c].z;
+        }
+        if (cell_begin) cell_begin[c] = off;
+        uint32_t b;
+        std::memcpy(&b, &cells[(size_t)c].w, 4);
+        for (size_t i = b; i < n_dev_entries; i++) {
+            float lb;
+            std::memcpy(&lb, &entries[i].x, 4);
+            if (child[i] < 0) break;  // sentinel
+            if (off >= g.n_entries) return fail(FT_ERR_CUDA, "device grid is longer than the compiled grid");
+            if (entry_lower_bound) entry_lower_bound[off] = lb;
+            if (entry_item) entry_item[off] = child[i];
+            off++;
+        }
+    }
+    if (cell_begin) cell_begin[g.n_cells] = off;
+    if (off != g.n_entries) return fail(FT_ERR_CUDA, "device grid does not match the compiled grid");
+    return FT_OK;
+}
+
+FT_API int ft_strip_layout(int32_t width, int32_t height, int32_t strip_width, int32_t world, int32_t *strips_per_rank,
+                           int64_t *floats_per_rank) {
+    if (width <= 0 || height <= 0 || strip_width <= 0 || world <= 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid strip layout");
+    const int strips = (width + strip_width - 1) / strip_width;
+    const int spr = (strips + world - 1) / world;
+    if (strips_per_rank) *strips_per_rank = spr;
+    if (floats_per_rank) *floats_per_rank = (int64_t)(world == 1 ? width : spr * strip_width) * height * 3;
+    return FT_OK;
+}
+
+FT_API int ft_render_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                            float length, uint32_t flags, int32_t strip_width, int32_t rank, int32_t world,
+                            float *d_out_rgb, int32_t *d_out_leaf, void *stream, ft_render_stats *stats) {
+    if (!scene || !camera || !d_out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || rank < 0 || rank >= world)
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size or strip partition");
+    int st = check_ray_params(epsilon, length);
+    if (st != FT_OK) return st;
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool count = (flags & FT_FLAG_COUNTERS) != 0;
+    const RenderParams P = make_params(width, height, epsilon, length, strip_width, rank, world);
+    if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    cudaError_t e = (flags & FT_FLAG_FAST_MATH)
+                        ? ft_fast::launch_render(scene->dev, *camera, P, d_out_rgb, d_out_leaf, scene->d_stats, count, s)
+                        : ft_strict::launch_render(scene->dev, *camera, P, d_out_rgb, d_out_leaf, scene->d_stats, count, s);
+    if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        sum_stats(scene->h_stats, stats);
+        long long owned = 0;
+        for (int xl = 0; xl < P.local_cols; xl++) {
+            const int strip = xl / strip_width;
+            const int x = (strip * world + rank) * strip_width + (xl - strip * strip_width);
+            owned += x < width;
+        }
+        stats->primary_rays = owned * height;
+        stats->launches = 1;
+    }
+    return FT_OK;
+}
+
+FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon, float length,
+                     uint32_t flags, float *out_rgb, int32_t *out_leaf, ft_render_stats *stats) {
+    if (!scene || !camera || !out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (width <= 0 || height <= 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size");
+    int st = check_ray_params(epsilon, length);
+    if (st != FT_OK) return st;
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    const size_t npix = (size_t)width * height;
+    const size_t rgb_bytes = npix * 3 * sizeof(float), leaf_bytes = out_leaf ? npix * sizeof(int32_t) : 0;
+    CU(scene->reserve(rgb_bytes + leaf_bytes));
+    float *d_rgb = (float *)scene->d_scratch;
+    int32_t *d_leaf = out_leaf ? (int32_t *)((char *)scene->d_scratch + rgb_bytes) : nullptr;
+    const bool count = (flags & FT_FLAG_COUNTERS) != 0;
+    const bool fast = (flags & FT_FLAG_FAST_MATH) != 0;
+    cudaStream_t s = scene->stream;
+    CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    CU(cudaEventRecord(scene->ev[0], s));
+    // Column bands: band k+1 renders while band k's pixels travel to the host on the copy stream.
+    const int bands = (npix >= (size_t)1 << 19) ? 8 : 1;
+    const int band_cols = ((width + bands - 1) / bands + 3) & ~3;
+    int launches = 0;
+    for (int x0 = 0; x0 < width; x0 += band_cols) {
+        const int cols = std::min(band_cols, width - x0);
+        RenderParams P = make_params(width, height, epsilon, length, cols, 0, 1);
+        P.local_cols = cols;
+        P.x_offset = x0;
+        float *band_rgb = d_rgb + (size_t)x0 * height * 3;
+        int32_t *band_leaf = d_leaf ? d_leaf + (size_t)x0 * height : nullptr;
+        cudaError_t e = fast ? ft_fast::launch_render(scene->dev, *camera, P, band_rgb, band_leaf, scene->d_stats, count, s)
+                             : ft_strict::launch_render(scene->dev, *camera, P, band_rgb, band_leaf, scene->d_stats, count, s);
+        if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
+        launches++;
+        CU(cudaEventRecord(scene->ev[3], s));
+        CU(cudaStreamWaitEvent(scene->copy_stream, scene->ev[3], 0));
+        CU(cudaMemcpyAsync(out_rgb + (size_t)x0 * height * 3, band_rgb, (size_t)cols * height * 3 * sizeof(float),
+                           cudaMemcpyDeviceToHost, scene->copy_stream));
+        if (out_leaf)
+            CU(cudaMemcpyAsync(out_leaf + (size_t)x0 * height, band_leaf, (size_t)cols * height * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, scene->copy_stream));
+    }
+    CU(cudaEventRecord(scene->ev[1], s));
+    CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(scene->ev[2], scene->copy_stream));
+    CU(cudaStreamWaitEvent(s, scene->ev[2], 0));
+    CU(cudaEventRecord(scene->ev[2], s));
+    CU(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        sum_stats(scene->h_stats, stats);
+        stats->primary_rays = (int64_t)npix;
+        stats->launches = launches;
+        cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
+        cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
+    }
+    return FT_OK;
+}
+
+FT_API int ft_deinterleave_device(const float *d_gathered, int32_t width, int32_t height, int32_t strip_width,
+                                  int32_t world, int32_t channels, float *d_out, void *stream) {
+    if (!d_gathered || !d_out || width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || channels <= 0)
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    cudaError_t e = launch_deinterleave(d_gathered, width, height, strip_width, world, channels, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "deinterleave kernel launch");
+    return FT_OK;
+}
+
+FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_t flags, float *out_rgb, int32_t *out_leaf,
+                         int32_t *out_steps, uint32_t *out_shadow, ft_render_stats *stats) {
+    if (!scene || n < 0 || (n > 0 && !rays)) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n == 0) return FT_OK;
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    const size_t N = (size_t)n;
+    const size_t ray_bytes = N * sizeof(ft_ray), rgb_bytes = N * 12, i_bytes = N * 4;
+    CU(scene->reserve(ray_bytes + rgb_bytes + 3 * i_bytes));
+    char *base = (char *)scene->d_scratch;
+    float4 *d_rays = (float4 *)base;
+    float *d_rgb = (float *)(base + ray_bytes);
+    int32_t *d_leaf = (int32_t *)(base + ray_bytes + rgb_bytes);
+    int32_t *d_steps = d_leaf + N;
+    uint32_t *d_shadow = (uint32_t *)(d_steps + N);
+    cudaStream_t s = scene->stream;
+    const bool count = (flags & FT_FLAG_COUNTERS) != 0;
+    CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    CU(cudaEventRecord(scene->ev[0], s));
+    CU(cudaMemcpyAsync(d_rays, rays, ray_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(scene->ev[3], s));
+    cudaError_t e = (flags & FT_FLAG_FAST_MATH)
+                        ? ft_fast::launch_trace_rays(scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, scene->d_stats, count, s)
+                        : ft_strict::launch_trace_rays(scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, scene->d_stats, count, s);
+    if (e != cudaSuccess) return cuda_fail(e, "trace_rays kernel launch");
+    CU(cudaEventRecord(scene->ev[1], s));
+    if (out_rgb) CU(cudaMemcpyAsync(out_rgb, d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, s));
+    if (out_leaf) CU(cudaMemcpyAsync(out_leaf, d_leaf, i_bytes, cudaMemcpyDeviceToHost, s));
+    if (out_steps) CU(cudaMemcpyAsync(out_steps, d_steps, i_bytes, cudaMemcpyDeviceToHost, s));
+    if (out_shadow) CU(cudaMemcpyAsync(out_shadow, d_shadow, i_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(scene->ev[2], s));
+    CU(cudaStreamSynchronize(s));
+    if (stats) {
+        sum_stats(scene->h_stats, stats);
+        stats->primary_rays = n;
+        stats->launches = 1;
+        cudaEventElapsedTime(&stats->kernel_ms, scene->ev[3], scene->ev[1]);
+        cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
+    }
+    return FT_OK;
+}
+
+FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint32_t flags, float *out_distance) {
+    if (!scene || n < 0 || (n > 0 && (!positions || !out_distance))) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return FT_OK;
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    const size_t N = (size_t)n;
+    CU(scene->reserve(N * 16));
+    float *d_pts = (float *)scene->d_scratch;
+    float *d_out = d_pts + 3 * N;
+    cudaStream_t s = scene->stream;
+    CU(cudaMemcpyAsync(d_pts, positions, N * 12, cudaMemcpyHostToDevice, s));
+    cudaError_t e = (flags & FT_FLAG_FAST_MATH) ? ft_fast::launch_distance(scene->dev, d_pts, n, d_out, s)
+                                                : ft_strict::launch_distance(scene->dev, d_pts, n, d_out, s);
+    if (e != cudaSuccess) return cuda_fail(e, "distance kernel launch");
+    CU(cudaMemcpyAsync(out_distance, d_out, N * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return FT_OK;
+}
+
+FT_API int ft_host_register(void *ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return FT_OK;
+}
+FT_API int ft_host_unregister(void *ptr) {
+    if (!ptr) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaHostUnregister(ptr));
+    return FT_OK;
+}
+FT_API int ft_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    CU(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable));
+    return FT_OK;
+}
+FT_API int ft_host_free(void *ptr) {
+    if (!ptr) return FT_OK;
+    CU(cudaFreeHost(ptr));
+    return FT_OK;
+}
+
+FT_API int ft_measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate) {
+    cudaError_t e = measure_fp32_peak(device, tflops_fma, sm_mhz_estimate);
+    if (e != cudaSuccess) return cuda_fail(e, "measure_fp32_peak");
+    return FT_OK;
+}
+
+}  // extern "C"

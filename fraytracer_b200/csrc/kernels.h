@@ -1,0 +1,40 @@
+// kernels.h -- launcher declarations shared by ft_api.cu and the two kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/fraytracer_b200.h"
+#include "device_scene.h"
+
+#define FT_STAT_SLOTS 64   // power of two
+#define FT_STAT_STRIDE 16  // unsigned long long per slot (128 B apart)
+#define FT_STAT_HITS 0
+#define FT_STAT_SHADOW 1
+#define FT_STAT_CAPPED 2
+#define FT_STAT_STEPS 3
+#define FT_STAT_FLOPS 4
+
+struct RenderParams {
+    int width, height;   // image X, Y
+    int local_cols;      // columns of this rank's compact buffer
+    int strip_width, rank, world;
+    int x_offset;        // image column of compact column 0 (band rendering)
+    float epsilon, length, max_size;
+};
+
+#define FT_DECLARE_LAUNCHERS(NS)                                                                                      \
+    namespace NS {                                                                                                    \
+    cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb,         \
+                              int *out_leaf, unsigned long long *stats, bool count, cudaStream_t stream);             \
+    cudaError_t launch_trace_rays(const DevScene &S, const float4 *rays, long long n, float *out_rgb, int *out_leaf,  \
+                                  int *out_steps, unsigned *out_shadow, unsigned long long *stats, bool count,        \
+                                  cudaStream_t stream);                                                               \
+    cudaError_t launch_distance(const DevScene &S, const float *pts, long long n, float *out, cudaStream_t stream);   \
+    }
+
+FT_DECLARE_LAUNCHERS(ft_strict)
+FT_DECLARE_LAUNCHERS(ft_fast)
+
+// util_kernels.cu
+cudaError_t launch_deinterleave(const float *gathered, int width, int height, int strip_width, int world, int channels,
+                                float *out, cudaStream_t stream);
+cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate);

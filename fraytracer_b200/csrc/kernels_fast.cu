@@ -1,0 +1,4 @@
+// Contracted build of the hot-path kernels (-fmad=true): FT_FLAG_FAST_MATH.  Not bit-identical to the
+// reference; parity for this build is tolerance-based.
+#define FT_NS ft_fast
+#include "kernels_impl.cuh"

@@ -1,0 +1,52 @@
+// scene_compiler.h -- host scene compiler: flat ft_scene_desc -> device-ready arrays.
+// Mirrors the *constructors* of the reference (SdfForm.fs, SdfObject.fs, SdfLight.fs,
+// SdfBoundary.buildSpatialLookup) so that the compiled data equals what the F# closures capture.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/fraytracer_b200.h"
+#include "device_scene.h"
+
+namespace ftc {
+
+struct GridHost {
+    int32_t node;         // compiled node index of the union
+    int32_t count[3];
+    float aabb_min[3], cell_size[3], cell_size_inv[3];
+    int64_t cell_base;    // first cell in CompiledScene::cells
+    int64_t n_cells;
+    int64_t n_entries;    // without sentinels
+    // per-cell views for introspection (without sentinels)
+    std::vector<int64_t> begin;        // n_cells+1, into lb/item below
+    std::vector<float> lower_bound;
+    std::vector<int32_t> item;
+};
+
+struct CompiledScene {
+    std::vector<float4> nodes;
+    std::vector<float4> cells;
+    std::vector<uint2> entries;
+    std::vector<int32_t> entry_child;
+    std::vector<uint32_t> links;
+    std::vector<int4> objects;
+    std::vector<int32_t> obj_links;
+    std::vector<float4> materials;
+    std::vector<float4> lights;
+    std::vector<GridHost> grids;
+    uint32_t root_word = 0;
+    int32_t root_object = 0;
+    int32_t n_lights = 0;
+    float bg[3] = {0, 0, 0};
+    int32_t n_nodes = 0, n_primitives = 0, max_depth = 0;
+};
+
+// Returns FT_OK or an FT_ERR_* code with a message in `err`.
+int compile_scene(const ft_scene_desc *desc, CompiledScene *out, std::string *err);
+
+// Lens.create / Camera.lookAt (Camera.fs:10-14, 33-42)
+float lens_create(float field_of_view);
+void camera_look_at(const float position[3], const float look_at[3], const float up[3], float nps, ft_camera *out);
+
+}  // namespace ftc

@@ -1,0 +1,121 @@
+"""Synthetic scenes of BASELINE.json's configs, generated exactly like the reference's
+console program does (src/FrayTracer.Console/Program.fs:14-93): same System.Random stream,
+same draw order, same float32 arithmetic.
+
+config 1  default_scene()           Program.fs verbatim: 1000 tori, intersect sphere 3.5, subtract sphere 2.5
+config 2  spheres_capsules_scene()  512 randomSphere + 512 randomCapsule in one union (capsule stands in
+                                    for the reference's non-existent cone), 1920x1080
+config 5  mixed_scene()             256 each torus/sphere/capsule/triangle in one union, 7680x4320
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .api import (Camera, FColor, ImageSize, Lens, SdfForm, SdfLight, SdfMaterial, SdfObject, SdfScene)
+from .dotnet_random import DotNetRandom
+
+f32 = np.float32
+
+
+class SceneBuilder:
+    """the `random*` helpers of Program.fs:28-65 over one System.Random stream"""
+
+    def __init__(self, seed: int = 19):
+        self.rng = DotNetRandom(seed)  # Program.fs:14
+
+    def randomMaterial(self) -> SdfMaterial:  # Program.fs:28-30
+        r = self.rng.range_01()
+        g = self.rng.range_01()
+        b = self.rng.range_01()
+        return SdfMaterial.createSolid(FColor.ofRGB(r, g, b))
+
+    def randomSphere(self) -> SdfObject:  # Program.fs:32-37
+        center = self.rng.pointInBall(4.0)
+        radius = self.rng.range(0.3, 1.0)
+        form = SdfForm.Primitive.sphere(Center=center, Radius=radius)
+        return SdfObject.create(self.randomMaterial(), form)
+
+    def randomCapsule(self) -> SdfObject:  # Program.fs:39-46
+        center = self.rng.pointInBall(4.0)
+        length = self.rng.range(0.5, 2.0)
+        to = (center + self.rng.pointOnSphere(length)).astype(f32)
+        radius = self.rng.range(0.1, 0.3)
+        form = SdfForm.Primitive.capsule(From=center, To=to, Radius=radius)
+        return SdfObject.create(self.randomMaterial(), form)
+
+    def randomTorus(self) -> SdfObject:  # Program.fs:48-55
+        center = self.rng.pointInBall(4.0)
+        normal = self.rng.pointOnSphere(1.0)
+        major = self.rng.range(0.1, 0.4)
+        minor = self.rng.range(0.1, 0.3)
+        form = SdfForm.Primitive.torus(Center=center, Normal=normal, MajorRadius=major, MinorRadius=minor)
+        return SdfObject.create(self.randomMaterial(), form)
+
+    def randomTriangle(self) -> SdfObject:  # Program.fs:57-65
+        v1 = self.rng.pointInBall(4.0)
+        l2 = self.rng.range(0.2, 0.6)
+        v2 = (v1 + self.rng.pointOnSphere(l2)).astype(f32)
+        l3 = self.rng.range(0.2, 0.6)
+        v3 = (v1 + self.rng.pointOnSphere(l3)).astype(f32)
+        radius = self.rng.range(0.1, 0.3)
+        form = SdfForm.Primitive.triangle(V1=v1, V2=v2, V3=v3, Radius=radius)
+        return SdfObject.create(self.randomMaterial(), form)
+
+
+def default_lights():  # Program.fs:79-82
+    return [
+        SdfLight.directional((-0.5, -1.0, 1.0), FColor.ofRGB(0.5, 0.5, 0.5)),
+        SdfLight.point((-0.5, 0.0, -2.0), FColor.ofRGB(10.0, 0.0, 0.0)),
+    ]
+
+
+def default_camera() -> Camera:  # Program.fs:16-22
+    return Camera.lookAt(Position=(0.0, 0.0, -10.0), LookAt=(0.0, 0.0, 0.0), Up=(0.0, 1.0, 0.0),
+                         Lens=Lens.create(60.0))
+
+
+@dataclass
+class Workload:
+    name: str
+    scene: SdfScene
+    camera: Camera
+    size: ImageSize
+    epsilon: float
+    length: float
+    leaves: list  # leaf SdfObjects in generation order
+
+
+def default_scene(seed: int = 19, n_tori: int = 1000, size: int = 1000) -> Workload:
+    """config 1 -- Program.fs:67-93"""
+    b = SceneBuilder(seed)
+    tori = [b.randomTorus() for _ in range(n_tori)]
+    obj = SdfObject.subtract(
+        SdfObject.intersect(
+            SdfObject.union(tori),
+            [SdfForm.Primitive.sphere(Center=(0.0, 0.0, 0.0), Radius=3.5)]),
+        SdfForm.Primitive.sphere(Center=(-0.5, 1.0, -2.0), Radius=2.5))
+    scene = SdfScene(Object=obj, BackgroundColor=FColor.ofRGB(0.1, 0.1, 0.1), Lights=default_lights())
+    return Workload("config1_default_scene", scene, default_camera(), ImageSize(size, size), 0.01, 30.0, tori)
+
+
+def spheres_capsules_scene(seed: int = 19, n_spheres: int = 512, n_capsules: int = 512,
+                           width: int = 1920, height: int = 1080) -> Workload:
+    """config 2 -- SURVEY.md section 8(d)"""
+    b = SceneBuilder(seed)
+    objs = [b.randomSphere() for _ in range(n_spheres)] + [b.randomCapsule() for _ in range(n_capsules)]
+    scene = SdfScene(Object=SdfObject.union(objs), BackgroundColor=FColor.ofRGB(0.1, 0.1, 0.1),
+                     Lights=default_lights())
+    return Workload("config2_spheres_capsules_1080p", scene, default_camera(), ImageSize(width, height),
+                    0.01, 30.0, objs)
+
+
+def mixed_scene(seed: int = 19, n_each: int = 256, width: int = 7680, height: int = 4320) -> Workload:
+    """config 5 -- SURVEY.md section 8(d)"""
+    b = SceneBuilder(seed)
+    objs = ([b.randomTorus() for _ in range(n_each)] + [b.randomSphere() for _ in range(n_each)]
+            + [b.randomCapsule() for _ in range(n_each)] + [b.randomTriangle() for _ in range(n_each)])
+    scene = SdfScene(Object=SdfObject.union(objs), BackgroundColor=FColor.ofRGB(0.1, 0.1, 0.1),
+                     Lights=default_lights())
+    return Workload("config5_mixed_1024_8k", scene, default_camera(), ImageSize(width, height), 0.01, 30.0, objs)

@@ -1,0 +1,313 @@
+/*
+ * fraytracer_b200.h -- C ABI of the B200-native per-ray hot path of FrayTracer.
+ *
+ * This is the drop-in boundary.  It replaces, with one
+ * shared library `libfraytracer_b200.so`, the reference call
+ *
+ *     scene |> SdfScene.trace |> Image.render epsilon 30f imageSize camera
+ *         (src/FrayTracer.Console/Program.fs:90-93,
+ *          SdfScene.trace  src/FrayTracer/SdfScene.fs:7-28,
+ *          Image.render    src/FrayTracer/Image.fs:26-35)
+ *
+ * The reference's extension surface is records of opaque F# closures
+ * (src/FrayTracer/Types.fs:40-79).  Closures cannot cross an FFI, so the
+ * boundary takes the *reified* scene: one flat, blittable description whose
+ * entries mirror the reference constructors one to one.  The library compiles
+ * the description (grid build included) into device buffers and renders with
+ * hand-written sm_100a kernels.  There is no CPU fallback: every entry point
+ * that computes returns FT_ERR_NO_DEVICE / FT_ERR_CUDA when no B200 is usable.
+ *
+ * Conventions
+ *   - every function returns an int status (FT_OK == 0); no exception or abort
+ *     crosses the ABI; ft_last_error() gives a thread-local message;
+ *   - all structs are plain, 4-byte aligned, little-endian, no padding;
+ *   - float means IEEE binary32 everywhere (the reference computes in float32);
+ *   - ft_scene handles are immutable after creation (README.md:8 "Immutable
+ *     scenes") and may be used from any host thread; calls on one handle are
+ *     serialised internally.
+ */
+#ifndef FRAYTRACER_B200_H
+#define FRAYTRACER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FT_API __declspec(dllexport)
+#else
+#define FT_API __attribute__((visibility("default")))
+#endif
+
+#define FT_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define FT_OK 0
+#define FT_ERR_INVALID_ARGUMENT 1
+/* reference: failwith "No SdfObjects given." (SdfForm.fs:16,53; SdfObject.fs:14)
+ * and failwithf "blub" (SdfForm.fs:71) on an empty composite                */
+#define FT_ERR_EMPTY_COMPOSITE 2
+/* a node kind the device code cannot evaluate (user-written closures)       */
+#define FT_ERR_UNSUPPORTED_NODE 3
+#define FT_ERR_CUDA 4
+/* composite nesting deeper than FT_MAX_DEPTH                                */
+#define FT_ERR_DEPTH 5
+#define FT_ERR_NO_DEVICE 6
+#define FT_ERR_OUT_OF_MEMORY 7
+
+/* maximum nesting depth of composite forms the device evaluator supports    */
+#define FT_MAX_DEPTH 12
+
+/* ---- forms: mirror SdfForm constructors ---------------------------------- */
+enum {
+    /* SdfForm.Primitive.sphere  (SdfForm.fs:118-135) p = Center.xyz, Radius  */
+    FT_FORM_SPHERE = 1,
+    /* SdfForm.Primitive.capsule (SdfForm.fs:137-170) p = From.xyz, To.xyz, Radius */
+    FT_FORM_CAPSULE = 2,
+    /* SdfForm.Primitive.torus   (SdfForm.fs:172-203) p = Center.xyz, Normal.xyz
+     * (un-normalised, as the caller gives it), MajorRadius, MinorRadius      */
+    FT_FORM_TORUS = 3,
+    /* SdfForm.Primitive.triangle (SdfForm.fs:205-268) p = V1.xyz, V2.xyz, V3.xyz, Radius */
+    FT_FORM_TRIANGLE = 4,
+    /* SdfForm.union       (SdfForm.fs:14-40)   children = forms              */
+    FT_FORM_UNION = 16,
+    /* SdfForm.subtract    (SdfForm.fs:42-49)   children = [a, b]             */
+    FT_FORM_SUBTRACT = 17,
+    /* SdfForm.intersect   (SdfForm.fs:51-67)   children = forms              */
+    FT_FORM_INTERSECT = 18,
+    /* SdfForm.unionSmooth (SdfForm.fs:69-91)   p[0] = strength, children = forms */
+    FT_FORM_UNION_SMOOTH = 19
+};
+
+typedef struct ft_form_desc {
+    int32_t kind;        /* FT_FORM_*                                          */
+    int32_t first_child; /* composites: index into ft_scene_desc.children      */
+    int32_t child_count; /* composites: number of child form ids               */
+    float p[10];         /* parameters, see the enum                           */
+} ft_form_desc;
+
+/* ---- materials: mirror SdfMaterial (SdfMaterial.fs:4-10) ---------------- */
+enum {
+    FT_MATERIAL_SOLID = 1 /* SdfMaterial.createSolid color                     */
+};
+
+typedef struct ft_material_desc {
+    int32_t kind;
+    float rgb[3];
+} ft_material_desc;
+
+/* ---- objects: mirror SdfObject constructors (SdfObject.fs:6-64) ---------- */
+enum {
+    /* SdfObject.create material form: form = form id, material = material id  */
+    FT_OBJECT_LEAF = 1,
+    /* SdfObject.union objects: children = object ids                          */
+    FT_OBJECT_UNION = 2,
+    /* SdfObject.subtract object form: children = [object id], form = form id  */
+    FT_OBJECT_SUBTRACT = 3,
+    /* SdfObject.intersect object forms: children = [object id, form ids ...]  */
+    FT_OBJECT_INTERSECT = 4
+};
+
+typedef struct ft_object_desc {
+    int32_t kind;
+    int32_t form;        /* LEAF: its form; SUBTRACT: the subtracted form      */
+    int32_t material;    /* LEAF only                                          */
+    int32_t first_child; /* index into ft_scene_desc.children                  */
+    int32_t child_count;
+} ft_object_desc;
+
+/* ---- lights: mirror SdfLight constructors (SdfLight.fs:6-42) ------------ */
+enum {
+    FT_LIGHT_DIRECTIONAL = 1, /* SdfLight.directional direction color: v = direction */
+    FT_LIGHT_POINT = 2        /* SdfLight.point position color:        v = position  */
+};
+
+#define FT_MAX_LIGHTS 32
+
+typedef struct ft_light_desc {
+    int32_t kind;
+    float v[3];
+    float rgb[3];
+} ft_light_desc;
+
+/* ---- scene: mirrors the SdfScene record (Types.fs:74-79) ---------------- */
+typedef struct ft_scene_desc {
+    const ft_form_desc *forms;
+    const ft_object_desc *objects;
+    const int32_t *children;
+    const ft_material_desc *materials;
+    const ft_light_desc *lights;
+    int32_t n_forms;
+    int32_t n_objects;
+    int32_t n_children;
+    int32_t n_materials;
+    int32_t n_lights;
+    int32_t root_object;  /* SdfScene.Object                                   */
+    float background[3];  /* SdfScene.BackgroundColor                          */
+} ft_scene_desc;
+
+/* ---- camera: mirrors the Camera record (Camera.fs:16-22) ---------------- */
+typedef struct ft_camera {
+    float position[3];
+    float forward[3];
+    float up_scaled[3];
+    float right_scaled[3];
+} ft_camera;
+
+/* ---- ray: mirrors the Ray record (Types.fs:9-17), 32 bytes --------------- */
+typedef struct ft_ray {
+    float origin[3];
+    float direction[3];
+    float length;
+    float epsilon;
+} ft_ray;
+
+typedef struct ft_scene ft_scene; /* opaque */
+
+/* what the scene compiler produced, for DESIGN/bench reporting */
+typedef struct ft_scene_info {
+    int32_t n_nodes;         /* compiled form nodes (given + synthesised)      */
+    int32_t n_primitives;
+    int32_t n_grids;         /* grid-accelerated unions                        */
+    int32_t max_depth;
+    int64_t n_cells;         /* over all grids                                 */
+    int64_t n_entries;       /* candidate-list entries over all grids          */
+    int64_t device_bytes;    /* resident scene bytes in HBM                    */
+    int32_t device;          /* CUDA ordinal                                   */
+    int32_t sm_count;
+} ft_scene_info;
+
+/* per-grid introspection (tests compare this against the oracle's grid) */
+typedef struct ft_grid_info {
+    int32_t node;            /* compiled node id of the union                  */
+    int32_t count[3];        /* countX, countY, countZ (SdfBoundary.fs:237-239)*/
+    float aabb_min[3];
+    float cell_size[3];
+    float cell_size_inv[3];
+    int64_t n_entries;
+} ft_grid_info;
+
+/* counters filled by the render / trace calls */
+typedef struct ft_render_stats {
+    int64_t primary_rays;
+    int64_t primary_hits;
+    int64_t shadow_rays;     /* one per light per lit hit (SdfScene.fs:17-19)  */
+    int64_t capped_rays;     /* rays stopped by the watchdog step cap          */
+    int64_t march_steps;     /* Distance evaluations inside march loops (0 unless FT_FLAG_COUNTERS) */
+    int64_t eval_flops;      /* algorithmic f32 operations (0 unless FT_FLAG_COUNTERS) */
+    float kernel_ms;         /* device time of the kernels of this call        */
+    float total_ms;          /* device time incl. copies of this call          */
+    int32_t launches;        /* kernels launched by this call                  */
+    int32_t reserved;
+} ft_render_stats;
+
+/* flags for the compute calls */
+#define FT_FLAG_DEFAULT 0u
+/* collect march_steps / eval_flops with an instrumented kernel variant      */
+#define FT_FLAG_COUNTERS 1u
+/* contracted (FMA) arithmetic: faster, no longer bit-identical to the
+ * reference's individually rounded float32 operations                       */
+#define FT_FLAG_FAST_MATH 2u
+
+/* ---- library ------------------------------------------------------------ */
+FT_API int ft_abi_version(void);
+FT_API const char *ft_last_error(void);
+FT_API int ft_device_count(int *count);
+
+/* Lens.create fieldOfView (Camera.fs:10-14): sin(fov * 0.5f), the F# `sin` on
+ * float32 evaluates in double and rounds once.                               */
+FT_API float ft_lens_create(float field_of_view);
+/* Camera.lookAt (Camera.fs:33-42) */
+FT_API int ft_camera_look_at(const float position[3], const float look_at[3], const float up[3],
+                             float near_plane_size, ft_camera *out);
+
+/* ---- scene compiler ------------------------------------------------------ */
+/* Validates and compiles the description: primitive precomputation
+ * (SdfForm.fs:148-149,182-188,216-225), boundaries (SdfBoundary.fs:7-54), the
+ * uniform grid of every union (SdfBoundary.buildSpatialLookup,
+ * SdfBoundary.fs:225-282), upload to `device`.                              */
+FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out);
+/* device == FT_DEVICE_NONE compiles without uploading: the handle serves ft_scene_info_get and
+ * ft_scene_grid_* only (scene validation, tests of the compiler); every compute entry point
+ * returns FT_ERR_NO_DEVICE on it.                                                            */
+#define FT_DEVICE_NONE (-1)
+FT_API int ft_scene_destroy(ft_scene *scene);
+FT_API int ft_scene_info_get(const ft_scene *scene, ft_scene_info *out);
+/* watchdog: the reference's march loop has no step cap (SdfForm.fs:93-104);
+ * rays that exceed `max_steps` Distance evaluations are stopped as misses and
+ * counted in ft_render_stats.capped_rays.  Default 1<<22.                   */
+FT_API int ft_scene_set_step_cap(ft_scene *scene, int32_t max_steps);
+
+FT_API int ft_scene_grid_count(const ft_scene *scene, int32_t *count);
+FT_API int ft_scene_grid_info(const ft_scene *scene, int32_t grid, ft_grid_info *out);
+/* copies the grid back FROM THE DEVICE: cell_centers[3*ncells] (x-major:
+ * cell (x,y,z) at (x*countY + y)*countZ + z), cell_begin[ncells+1],
+ * entry_lower_bound[n_entries], entry_item[n_entries] (child position inside
+ * the union's child list).  Any pointer may be NULL.                        */
+FT_API int ft_scene_grid_read(const ft_scene *scene, int32_t grid, float *cell_centers,
+                              int64_t *cell_begin, float *entry_lower_bound, int32_t *entry_item);
+
+/* ---- the hot path -------------------------------------------------------- */
+/* Image.render epsilon length {X=width;Y=height} camera (SdfScene.trace scene)
+ * (Image.fs:26-35).  out_rgb is the reference's FColor[X,Y]: element (x,y) at
+ * (x*height + y), 3 floats each.  out_leaf (optional) receives the index of
+ * the leaf SdfObject whose material coloured the pixel (the arg-min of
+ * SdfObject.fs:27-46), -1 for background.  Both are HOST pointers; page-lock
+ * them with ft_host_register for full copy bandwidth.                       */
+FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
+                     float epsilon, float length, uint32_t flags, float *out_rgb, int32_t *out_leaf,
+                     ft_render_stats *stats);
+
+/* Same, DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL = the
+ * legacy default stream).  Renders only the column strips owned by `rank` of
+ * `world`: strip s covers columns [s*strip_width, (s+1)*strip_width) and
+ * belongs to rank s % world.  The strips land compacted, in ownership order,
+ * in out_rgb ([local_strip][strip_width][height][3]) so that N ranks can
+ * all-gather equal-sized buffers; world == 1 gives the plain FColor[X,Y].
+ * stats (optional, host) is filled only when FT_FLAG_COUNTERS forces a
+ * synchronisation.                                                           */
+FT_API int ft_render_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
+                            float epsilon, float length, uint32_t flags, int32_t strip_width,
+                            int32_t rank, int32_t world, float *d_out_rgb, int32_t *d_out_leaf,
+                            void *stream, ft_render_stats *stats);
+
+/* number of strips and of floats in the compact per-rank buffer above       */
+FT_API int ft_strip_layout(int32_t width, int32_t height, int32_t strip_width, int32_t world,
+                           int32_t *strips_per_rank, int64_t *floats_per_rank);
+
+/* all-gathered [world][strips_per_rank][strip_width][height][3] -> FColor[X,Y]
+ * (device pointers, asynchronous on stream)                                  */
+FT_API int ft_deinterleave_device(const float *d_gathered, int32_t width, int32_t height,
+                                  int32_t strip_width, int32_t world, int32_t channels,
+                                  float *d_out, void *stream);
+
+/* Batched SdfScene.trace scene ray (SdfScene.fs:7-28) for arbitrary rays.
+ * HOST pointers; every output is optional.  out_leaf: as above.  out_steps:
+ * Distance evaluations of the primary march (SdfForm.fs:93-104).
+ * out_shadow: bit l set when light l contributed (lit and unshadowed).      */
+FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_t flags,
+                         float *out_rgb, int32_t *out_leaf, int32_t *out_steps,
+                         uint32_t *out_shadow, ft_render_stats *stats);
+
+/* scene.Object.Form.Distance position for n positions (xyz interleaved, HOST)
+ * -- the closure every march step calls (Types.fs:42).                      */
+FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint32_t flags,
+                       float *out_distance);
+
+/* ---- host memory helpers ------------------------------------------------- */
+FT_API int ft_host_register(void *ptr, int64_t bytes);
+FT_API int ft_host_unregister(void *ptr);
+FT_API int ft_host_alloc(void **ptr, int64_t bytes);
+FT_API int ft_host_free(void *ptr);
+
+/* ---- measurement --------------------------------------------------------- */
+/* dependent-free FFMA stream over all SMs: the FP32 roofline denominator
+ * (MEASURED_PEAKS.json carries none).  TFLOP/s, FMA counted as 2.           */
+FT_API int ft_measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRAYTRACER_B200_H */

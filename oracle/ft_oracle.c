@@ -1,0 +1,1135 @@
+/*
+ * ft_oracle.c -- CPU restatement of FrayTracer's per-ray hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (fraytracer_b200/,
+ * include/) may include, link or call this file; only tests/,
+ * __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of
+ * bench.py use it, as the checker and as the timed CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (JanWosnitza/FrayTracer, F#) ships no tests,
+ * golden images or fixtures (FrayTracer.sln:6-9 lists two projects, no test
+ * project) and no .NET runtime exists in this environment, so this file could
+ * not be checked against the reference's own outputs.  It is pinned only by
+ * (a) known-answer tests derived by hand from the reference formulas and
+ * (b) the published behaviour of System.Random / System.Numerics (.NET 6),
+ * see tests/test_oracle_*.py.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/src/FrayTracer).  Arithmetic is IEEE binary32, one rounding
+ * per operation, no FMA contraction (compile with -ffp-contract=off), in the
+ * operation order of the F# source / System.Numerics:
+ *   Vector3.Dot(a,b)   = (a.x*b.x + a.y*b.y) + a.z*b.z   (x64 dpps reduction)
+ *   Length             = sqrt(Dot(v,v));  Distance(a,b) = Length(a-b)
+ *   Normalize(v)       = v / Length(v)    (per-component IEEE divide)
+ *   v / s, v * s       = per-component
+ *   Vector3.Lerp(a,b,t)= a*(1-t) + b*t    (.NET 5+)
+ *   MathF.Min/Max      = .NET Core 3.0+ semantics (NaN propagating)
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/fraytracer_b200.h" /* scene description structs only */
+
+#define FTO_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------ */
+/* System.Numerics restatement                                               */
+/* ------------------------------------------------------------------------ */
+typedef struct { float x, y, z; } v3;
+
+static inline v3 V(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 vmul(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline v3 vdivv(v3 a, v3 b) { return V(a.x / b.x, a.y / b.y, a.z / b.z); }
+static inline v3 vscale(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+static inline v3 vdiv(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
+static inline v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
+static inline float vdot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+static inline float vlen2(v3 a) { return vdot(a, a); }
+static inline float vlen(v3 a) { return sqrtf(vdot(a, a)); }
+static inline float vdist(v3 a, v3 b) { return vlen(vsub(a, b)); }
+static inline float vdist2(v3 a, v3 b) { return vlen2(vsub(a, b)); }
+static inline v3 vnormalize(v3 a) { return vdiv(a, vlen(a)); }
+static inline v3 vcross(v3 a, v3 b) {
+    return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+static inline v3 vmin(v3 a, v3 b) {
+    return V(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y, a.z < b.z ? a.z : b.z);
+}
+static inline v3 vmax(v3 a, v3 b) {
+    return V(a.x > b.x ? a.x : b.x, a.y > b.y ? a.y : b.y, a.z > b.z ? a.z : b.z);
+}
+static inline v3 vlerp(v3 a, v3 b, float t) { return vadd(vscale(a, 1.0f - t), vscale(b, t)); }
+/* Math.fs:69  Vector3.inverseLength v = v / v.LengthSquared() */
+static inline v3 vinverse_length(v3 a) { return vdiv(a, vlen2(a)); }
+
+/* System.MathF.Max / Min (.NET Core 3.0+) */
+static inline float net_max(float a, float b) {
+    if (a != b) {
+        if (!isnan(a)) return b < a ? a : b;
+        return a;
+    }
+    return signbit(b) ? a : b;
+}
+static inline float net_min(float a, float b) {
+    if (a != b) {
+        if (!isnan(a)) return a < b ? a : b;
+        return a;
+    }
+    return signbit(a) ? a : b;
+}
+/* Math.fs:51  clamp01 x = MathF.Max(0f, MathF.Min(1f, x)) */
+static inline float clamp01(float x) { return net_max(0.0f, net_min(1.0f, x)); }
+/* Math.fs:40  sign_i (NaN would throw in .NET; not reachable from finite input) */
+static inline int sign_i(float x) { return (x > 0.0f) - (x < 0.0f); }
+/* Math.fs:57-59  MathF.Floor/Ceiling |> int : x64 cvttss2si, out of range -> INT_MIN */
+static inline int conv_i4(float x) {
+    if (!(x >= -2147483648.0f && x < 2147483648.0f)) return INT32_MIN;
+    return (int)x;
+}
+static inline int floor_i(float x) { return conv_i4(floorf(x)); }
+static inline int ceiling_i(float x) { return conv_i4(ceilf(x)); }
+static inline int clamp_i(int lo, int hi, int x) {
+    int m = hi < x ? hi : x; /* Math.Min(max, x) */
+    return lo > m ? lo : m;  /* Math.Max(min, .) */
+}
+
+/* ------------------------------------------------------------------------ */
+/* System.Random(seed) -- Knuth subtractive generator, .NET seeded algorithm */
+/* (needed to regenerate Program.fs's scene; Program.fs:14, Random.fs:9-40)  */
+/* ------------------------------------------------------------------------ */
+typedef struct fto_random {
+    int32_t sa[56];
+    int inext, inextp;
+} fto_random;
+
+FTO_API fto_random *fto_random_create(int32_t seed) {
+    fto_random *r = (fto_random *)calloc(1, sizeof(fto_random));
+    const int32_t MBIG = 2147483647, MSEED = 161803398;
+    int32_t sub = (seed == INT32_MIN) ? INT32_MAX : (seed < 0 ? -seed : seed);
+    int32_t mj = MSEED - sub;
+    r->sa[55] = mj;
+    int32_t mk = 1;
+    int ii = 0;
+    for (int i = 1; i < 55; i++) {
+        ii += 21;
+        if (ii >= 55) ii -= 55;
+        r->sa[ii] = mk;
+        mk = mj - mk;
+        if (mk < 0) mk += MBIG;
+        mj = r->sa[ii];
+    }
+    for (int k = 1; k < 5; k++) {
+        for (int i = 1; i < 56; i++) {
+            int n = i + 30;
+            if (n >= 55) n -= 55;
+            r->sa[i] = (int32_t)((uint32_t)r->sa[i] - (uint32_t)r->sa[1 + n]);
+            if (r->sa[i] < 0) r->sa[i] += MBIG;
+        }
+    }
+    r->inext = 0;
+    r->inextp = 21;
+    return r;
+}
+FTO_API void fto_random_destroy(fto_random *r) { free(r); }
+FTO_API int32_t fto_random_next(fto_random *r) { /* InternalSample */
+    const int32_t MBIG = 2147483647;
+    int a = r->inext, b = r->inextp;
+    if (++a >= 56) a = 1;
+    if (++b >= 56) b = 1;
+    int32_t v = (int32_t)((uint32_t)r->sa[a] - (uint32_t)r->sa[b]);
+    if (v == MBIG) v--;
+    if (v < 0) v += MBIG;
+    r->sa[a] = v;
+    r->inext = a;
+    r->inextp = b;
+    return v;
+}
+FTO_API double fto_random_next_double(fto_random *r) {
+    return fto_random_next(r) * (1.0 / 2147483647.0);
+}
+
+/* ------------------------------------------------------------------------ */
+/* .NET 6 Array.Sort(keys, items) for float keys: NaNs to front + introsort. */
+/* F# Array.sortInPlaceBy (SdfBoundary.fs:267-268) lands here: it is NOT     */
+/* stable, so the order of equal LowerBounds is this algorithm's.            */
+/* ------------------------------------------------------------------------ */
+typedef struct { float lb; int32_t item; } gitem;
+
+static inline void gi_swap(gitem *a, int i, int j) { gitem t = a[i]; a[i] = a[j]; a[j] = t; }
+static inline void gi_swap_if_greater(gitem *a, int i, int j) {
+    if (a[i].lb > a[j].lb) gi_swap(a, i, j);
+}
+static void gi_insertion_sort(gitem *a, int n) {
+    for (int i = 0; i < n - 1; i++) {
+        gitem t = a[i + 1];
+        int j = i;
+        while (j >= 0 && t.lb < a[j].lb) { a[j + 1] = a[j]; j--; }
+        a[j + 1] = t;
+    }
+}
+static void gi_down_heap(gitem *a, int i, int n) {
+    gitem d = a[i - 1];
+    while (i <= n >> 1) {
+        int child = 2 * i;
+        if (child < n && a[child - 1].lb < a[child].lb) child++;
+        if (!(d.lb < a[child - 1].lb)) break;
+        a[i - 1] = a[child - 1];
+        i = child;
+    }
+    a[i - 1] = d;
+}
+static void gi_heap_sort(gitem *a, int n) {
+    for (int i = n >> 1; i >= 1; i--) gi_down_heap(a, i, n);
+    for (int i = n; i > 1; i--) { gi_swap(a, 0, i - 1); gi_down_heap(a, 1, i - 1); }
+}
+static int gi_pick_pivot_and_partition(gitem *a, int n) {
+    int hi = n - 1, middle = hi >> 1;
+    gi_swap_if_greater(a, 0, middle);
+    gi_swap_if_greater(a, 0, hi);
+    gi_swap_if_greater(a, middle, hi);
+    float pivot = a[middle].lb;
+    gi_swap(a, middle, hi - 1);
+    int left = 0, right = hi - 1;
+    while (left < right) {
+        while (pivot > a[++left].lb) {}
+        while (pivot < a[--right].lb) {}
+        if (left >= right) break;
+        gi_swap(a, left, right);
+    }
+    if (left != hi - 1) gi_swap(a, left, hi - 1);
+    return left;
+}
+static void gi_intro_sort(gitem *a, int n, int depth_limit) {
+    int size = n;
+    while (size > 1) {
+        if (size <= 16) {
+            if (size == 2) { gi_swap_if_greater(a, 0, 1); return; }
+            if (size == 3) {
+                gi_swap_if_greater(a, 0, 1);
+                gi_swap_if_greater(a, 0, 2);
+                gi_swap_if_greater(a, 1, 2);
+                return;
+            }
+            gi_insertion_sort(a, size);
+            return;
+        }
+        if (depth_limit == 0) { gi_heap_sort(a, size); return; }
+        depth_limit--;
+        int p = gi_pick_pivot_and_partition(a, size);
+        gi_intro_sort(a + p + 1, size - (p + 1), depth_limit);
+        size = p;
+    }
+}
+static void dotnet_sort_by_lower_bound(gitem *a, int n) {
+    if (n < 2) return;
+    int left = 0;
+    for (int i = 0; i < n; i++)
+        if (isnan(a[i].lb)) { gi_swap(a, left, i); left++; }
+    if (left == n) return;
+    a += left; n -= left;
+    int log2n = 0;
+    for (unsigned v = (unsigned)n; v >>= 1;) log2n++;
+    gi_intro_sort(a, n, 2 * (log2n + 1));
+}
+FTO_API void fto_dotnet_sort(float *keys, int32_t *items, int32_t n) { /* for tests */
+    gitem *a = (gitem *)malloc(sizeof(gitem) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) { a[i].lb = keys[i]; a[i].item = items[i]; }
+    dotnet_sort_by_lower_bound(a, n);
+    for (int i = 0; i < n; i++) { keys[i] = a[i].lb; items[i] = a[i].item; }
+    free(a);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Boundaries  (Types.fs:19-24, SdfBoundary.fs:7-63)                         */
+/* ------------------------------------------------------------------------ */
+typedef struct { v3 c; float r; } bnd;
+
+/* SdfBoundary.fs:7-22 */
+static bnd bnd_union(bnd a, bnd b) {
+    v3 diff = vsub(b.c, a.c);
+    float distance = vlen(diff);
+    if (distance + b.r <= a.r) return a;
+    if (distance + a.r <= b.r) return b;
+    v3 dir = vdiv(diff, distance);
+    v3 a2 = vsub(a.c, vscale(dir, a.r));
+    v3 b2 = vadd(b.c, vscale(dir, b.r));
+    bnd r;
+    r.c = vscale(vadd(a2, b2), 0.5f);
+    r.r = vdist(a2, b2) * 0.5f;
+    return r;
+}
+/* SdfBoundary.fs:29-49 (the radius formula is the reference's, kept verbatim) */
+static bnd bnd_intersection(bnd a, bnd b) {
+    v3 diff = vsub(b.c, a.c);
+    float distance = vlen(diff);
+    if (distance + b.r <= a.r) return b;
+    if (distance + a.r <= b.r) return a;
+    v3 dir = vdiv(diff, distance);
+    v3 a2 = vadd(a.c, vscale(dir, a.r));
+    v3 b2 = vsub(b.c, vscale(dir, b.r));
+    bnd r;
+    r.c = vscale(vadd(a2, b2), 0.5f);
+    float d2 = distance * distance;
+    float aR2 = a.r * a.r;
+    float bR2 = b.r * b.r;
+    r.r = sqrtf(4.0f * d2 * aR2 - (d2 - bR2 + aR2)) / (2.0f * distance);
+    return r;
+}
+/* SdfBoundary.fs:62-63 */
+static inline float bnd_min_distance(bnd b, v3 p) { return vdist(b.c, p) - b.r; }
+static inline float bnd_max_distance(bnd b, v3 p) { return vdist(b.c, p) + b.r; }
+
+/* ------------------------------------------------------------------------ */
+/* Spatial lookup (SdfBoundary.fs:211-282)                                   */
+/* ------------------------------------------------------------------------ */
+typedef struct { v3 center; int32_t n; gitem *items; } gcell;
+typedef struct grid {
+    v3 aabb_min, cell_size, cell_size_inv;
+    int cx, cy, cz;
+    gcell *cells; /* cells[(x*cy + y)*cz + z] as the .NET [,,] array */
+    int64_t n_entries;
+} grid;
+
+static grid *grid_build(const bnd *b, int n) {
+    grid *g = (grid *)calloc(1, sizeof(grid));
+    /* :229-230 */
+    v3 aabb_min = vsub(b[0].c, V(b[0].r, b[0].r, b[0].r));
+    v3 aabb_max = vadd(b[0].c, V(b[0].r, b[0].r, b[0].r));
+    float sum = b[0].r;
+    for (int i = 1; i < n; i++) {
+        aabb_min = vmin(aabb_min, vsub(b[i].c, V(b[i].r, b[i].r, b[i].r)));
+        aabb_max = vmax(aabb_max, vadd(b[i].c, V(b[i].r, b[i].r, b[i].r)));
+        sum = sum + b[i].r; /* :232 Seq.reduce (+) */
+    }
+    float count_size = 1.5f * (sum / (float)n); /* :233 */
+    v3 aabb_size = vsub(aabb_max, aabb_min);    /* :235 */
+    /* :237-239  all three counts use aabbSize.X */
+    int cx = ceiling_i(aabb_size.x / count_size); if (cx < 1) cx = 1;
+    int cy = cx, cz = cx;
+    v3 cell_size = vdivv(aabb_size, V((float)cx, (float)cy, (float)cz)); /* :240 */
+    v3 cell_size_inv = vdivv(V(1.0f, 1.0f, 1.0f), cell_size);            /* :241 */
+    g->aabb_min = aabb_min; g->cell_size = cell_size; g->cell_size_inv = cell_size_inv;
+    g->cx = cx; g->cy = cy; g->cz = cz;
+    g->cells = (gcell *)calloc((size_t)cx * cy * cz, sizeof(gcell));
+    v3 half = vscale(cell_size, 0.5f);
+    float half_len = vlen(half);
+    gitem *tmp = (gitem *)malloc(sizeof(gitem) * (size_t)n);
+    for (int x = 0; x < cx; x++)
+        for (int y = 0; y < cy; y++)
+            for (int z = 0; z < cz; z++) {
+                /* :246 */
+                v3 center = vadd(vadd(aabb_min, half), vmul(cell_size, V((float)x, (float)y, (float)z)));
+                /* :248-253 */
+                float m = bnd_max_distance(b[0], center);
+                for (int i = 1; i < n; i++) {
+                    float d = bnd_max_distance(b[i], center);
+                    if (d < m) m = d; /* Seq.min */
+                }
+                float upper_bound = m + half_len;
+                /* :255-264 */
+                int k = 0;
+                for (int i = 0; i < n; i++) {
+                    float md = bnd_min_distance(b[i], center);
+                    if (md < upper_bound) { tmp[k].lb = md; tmp[k].item = i; k++; }
+                }
+                dotnet_sort_by_lower_bound(tmp, k); /* :267-268 */
+                gcell *c = &g->cells[((size_t)x * cy + y) * cz + z];
+                c->center = center;
+                c->n = k;
+                c->items = (gitem *)malloc(sizeof(gitem) * (size_t)(k > 0 ? k : 1));
+                memcpy(c->items, tmp, sizeof(gitem) * (size_t)k);
+                g->n_entries += k;
+            }
+    free(tmp);
+    return g;
+}
+static void grid_free(grid *g) {
+    if (!g) return;
+    size_t nc = (size_t)g->cx * g->cy * g->cz;
+    for (size_t i = 0; i < nc; i++) free(g->cells[i].items);
+    free(g->cells);
+    free(g);
+}
+/* :276-282 */
+static inline const gcell *grid_lookup(const grid *g, v3 p) {
+    v3 c = vmul(vsub(p, g->aabb_min), g->cell_size_inv);
+    int ix = clamp_i(0, g->cx - 1, floor_i(c.x));
+    int iy = clamp_i(0, g->cy - 1, floor_i(c.y));
+    int iz = clamp_i(0, g->cz - 1, floor_i(c.z));
+    return &g->cells[((size_t)ix * g->cy + iy) * g->cz + iz];
+}
+
+/* ------------------------------------------------------------------------ */
+/* Forms (SdfForm.fs)                                                        */
+/* ------------------------------------------------------------------------ */
+typedef struct onode {
+    int kind;
+    bnd boundary;
+    /* primitives: precomputed closure captures */
+    v3 a, b, c;            /* sphere: a=C | capsule: a=From,b=dir,c=dirInv | torus: a=C,b=N | tri: V1,V2,V3 */
+    v3 e21, e32, e13;      /* triangle edges */
+    v3 i21, i32, i13;      /* triangle inverseLength edges */
+    v3 nor, n21, n32, n13; /* triangle normals */
+    float r0, r1, r2;      /* sphere: r0=R | capsule: r0=R | torus: r0=planeD r1=Major r2=Minor | tri: r0=R | smooth: r0=strength r1=-1/strength */
+    int nchild;
+    struct onode **child;
+    grid *g;
+} onode;
+
+/* counters of the reference algorithm's work (per thread, merged by caller) */
+typedef struct fto_counters {
+    int64_t march_steps;    /* Distance evaluations inside tryTrace loops    */
+    int64_t primary_rays, primary_hits, shadow_rays;
+    int64_t eval_sphere, eval_capsule, eval_torus, eval_triangle_edge, eval_triangle_face;
+    int64_t union_lookups;  /* grid cell lookups (form unions + material unions) */
+    int64_t lower_bound_tests, bound_tests; /* the two pruning tests          */
+    int64_t intersect_tests;
+    int64_t max_steps;      /* longest single march                           */
+} fto_counters;
+
+static __thread fto_counters *tl_ctr = NULL;
+#define CNT(field) do { if (tl_ctr) tl_ctr->field++; } while (0)
+
+static float form_distance(const onode *n, v3 p);
+
+/* SdfForm.fs:22-34 */
+static float union_distance(const onode *n, v3 p) {
+    const gcell *cell = grid_lookup(n->g, p);
+    CNT(union_lookups);
+    float dtc = vdist(p, cell->center);
+    float min = form_distance(n->child[cell->items[0].item], p);
+    for (int i = 1; i < cell->n; i++) {
+        const gitem *it = &cell->items[i];
+        const onode *f = n->child[it->item];
+        CNT(lower_bound_tests);
+        if (min > it->lb - dtc) {
+            CNT(bound_tests);
+            if (min > bnd_min_distance(f->boundary, p)) min = net_min(min, form_distance(f, p));
+        }
+    }
+    return min;
+}
+
+static float form_distance(const onode *n, v3 p) {
+    switch (n->kind) {
+    case FT_FORM_SPHERE: /* SdfForm.fs:127-129 */
+        CNT(eval_sphere);
+        return vdist(n->a, p) - n->r0;
+    case FT_FORM_CAPSULE: { /* SdfForm.fs:151-164 */
+        CNT(eval_capsule);
+        v3 diff = vsub(p, n->a);
+        float t = vdot(diff, n->c);
+        float d;
+        if (t <= 0.0f) d = vlen(diff);
+        else if (t >= 1.0f) d = vdist(diff, n->b);
+        else d = vdist(diff, vscale(n->b, t));
+        return d - n->r0;
+    }
+    case FT_FORM_TORUS: { /* SdfForm.fs:189-194 */
+        CNT(eval_torus);
+        float dplane = vdot(p, n->b) + n->r0;
+        float dcenter = vdist(n->a, vsub(p, vscale(n->b, dplane)));
+        float dcircle = dcenter - n->r1;
+        return sqrtf(dplane * dplane + dcircle * dcircle) - n->r2; /* Vector2.Length */
+    }
+    case FT_FORM_TRIANGLE: { /* SdfForm.fs:227-250 */
+        v3 p1 = vsub(p, n->a), p2 = vsub(p, n->b), p3 = vsub(p, n->c);
+        float d;
+        if (sign_i(vdot(n->n21, p1)) + sign_i(vdot(n->n32, p2)) + sign_i(vdot(n->n13, p3)) < 2) {
+            CNT(eval_triangle_edge);
+            float d21 = vdist2(p1, vscale(n->e21, clamp01(vdot(n->i21, p1))));
+            float d32 = vdist2(p2, vscale(n->e32, clamp01(vdot(n->i32, p2))));
+            float d13 = vdist2(p3, vscale(n->e13, clamp01(vdot(n->i13, p3))));
+            d = sqrtf(net_min(d13, net_min(d32, d21)));
+        } else {
+            CNT(eval_triangle_face);
+            d = fabsf(vdot(n->nor, p1));
+        }
+        return d - n->r0;
+    }
+    case FT_FORM_UNION:
+        return union_distance(n, p);
+    case FT_FORM_SUBTRACT: { /* SdfForm.fs:45-47: MathF.Max(-(b p), a p) */
+        float a = form_distance(n->child[0], p);
+        float b = form_distance(n->child[1], p);
+        return net_max(-b, a);
+    }
+    case FT_FORM_INTERSECT: { /* SdfForm.fs:58-64 */
+        float max = form_distance(n->child[0], p);
+        for (int i = 1; i < n->nchild; i++) {
+            CNT(intersect_tests);
+            if (max < bnd_max_distance(n->child[i]->boundary, p))
+                max = net_max(max, form_distance(n->child[i], p));
+        }
+        return max;
+    }
+    case FT_FORM_UNION_SMOOTH: { /* SdfForm.fs:75-82 */
+        float sum = 0.0f;
+        for (int i = 0; i < n->nchild; i++) sum = sum + expf(n->r1 * form_distance(n->child[i], p));
+        return -logf(sum) * n->r0;
+    }
+    }
+    return NAN;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Objects (SdfObject.fs)                                                    */
+/* ------------------------------------------------------------------------ */
+typedef struct oobj {
+    int kind;
+    onode *form;      /* the object's Form                                    */
+    int material;     /* LEAF                                                 */
+    int leaf_id;      /* index in the description's object table              */
+    struct oobj *base; /* SUBTRACT / INTERSECT: the object whose material is kept */
+    int nchild;
+    struct oobj **child; /* UNION */
+    grid *g;          /* UNION: the second, independently built lookup (SdfObject.fs:26) */
+} oobj;
+
+/* SdfObject.fs:27-46: returns the leaf object whose material colours p */
+static const oobj *object_material_leaf(const oobj *o, v3 p) {
+    for (;;) {
+        if (o->kind == FT_OBJECT_LEAF) return o;
+        if (o->kind == FT_OBJECT_SUBTRACT || o->kind == FT_OBJECT_INTERSECT) { o = o->base; continue; }
+        const gcell *cell = grid_lookup(o->g, p);
+        CNT(union_lookups);
+        const oobj *material = o->child[cell->items[0].item];
+        float min = form_distance(material->form, p);
+        float dtc = vdist(p, cell->center);
+        for (int i = 0; i < cell->n; i++) {
+            const gitem *it = &cell->items[i];
+            const oobj *c = o->child[it->item];
+            CNT(lower_bound_tests);
+            if (min > it->lb - dtc) {
+                CNT(bound_tests);
+                if (min > bnd_min_distance(c->form->boundary, p)) {
+                    float d = form_distance(c->form, p);
+                    if (d < min) { min = d; material = c; }
+                }
+            }
+        }
+        o = material; /* material |> SdfMaterial.getColor: recurse into the child's Material */
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* Scene                                                                     */
+/* ------------------------------------------------------------------------ */
+typedef struct olight {
+    int kind;
+    v3 v;      /* directional: normalize(-direction) (SdfLight.fs:7); point: position */
+    v3 color;
+} olight;
+
+typedef struct fto_scene {
+    int n_forms, n_objects, n_lights, n_materials;
+    onode **forms;   /* resolved node of each described form (single-child composites alias the child) */
+    onode **owned;   /* every allocated node */
+    int n_owned, cap_owned;
+    oobj **objects;
+    oobj **owned_obj;
+    int n_owned_obj;
+    olight *lights;
+    v3 *material_rgb;
+    v3 background;
+    oobj *root;
+    grid **grids; int n_grids, cap_grids; /* form-union grids in creation order, for tests */
+    int64_t step_cap;
+} fto_scene;
+
+typedef struct { v3 origin, direction; float length, epsilon; } oray;
+
+/* Ray.fs:6-13 */
+static inline v3 ray_get(const oray *r, float l) { return vadd(r->origin, vscale(r->direction, l)); }
+static inline oray ray_move(oray r, float l) {
+    r.origin = ray_get(&r, l);
+    r.length = r.length - l;
+    return r;
+}
+
+/* SdfForm.fs:93-104.  Returns 1 on hit; *hit is the (un-moved) hit ray.      */
+static int form_try_trace(const fto_scene *s, const onode *f, oray ray, oray *hit, int64_t *steps_out) {
+    int64_t steps = 0;
+    int result = 0;
+    for (;;) {
+        if (ray.length <= 0.0f) break;
+        if (steps >= s->step_cap) break; /* watchdog, not in the reference */
+        float d = form_distance(f, ray.origin);
+        steps++;
+        if (d < ray.epsilon) { *hit = ray; result = 1; break; }
+        ray = ray_move(ray, d);
+    }
+    if (tl_ctr) {
+        tl_ctr->march_steps += steps;
+        if (steps > tl_ctr->max_steps) tl_ctr->max_steps = steps;
+    }
+    if (steps_out) *steps_out = steps;
+    return result;
+}
+
+/* SdfForm.fs:106-115 */
+static v3 form_normal_from_ray(const onode *f, const oray *ray) {
+    float e = ray->epsilon * 0.125f;
+    v3 p = ray_get(ray, -ray->epsilon);
+    float dx = form_distance(f, V(p.x + e, p.y, p.z));
+    float dy = form_distance(f, V(p.x, p.y + e, p.z));
+    float dz = form_distance(f, V(p.x, p.y, p.z + e));
+    float d0 = form_distance(f, p);
+    return vnormalize(vsub(V(dx, dy, dz), V(d0, d0, d0)));
+}
+
+typedef struct { oray ray; v3 normal; v3 color; int leaf; } otrace;
+
+/* SdfObject.fs:66-78.  `shade` = 0 skips normal+colour (pure, discarded by
+ * the light closures, SdfLight.fs:17-20,38-41).                             */
+static int object_try_trace(const fto_scene *s, const oobj *o, oray ray, int shade, otrace *out, int64_t *steps) {
+    oray hit;
+    if (!form_try_trace(s, o->form, ray, &hit, steps)) return 0;
+    if (shade) {
+        out->normal = form_normal_from_ray(o->form, &hit);
+        out->ray = ray_move(hit, -ray.epsilon);
+        const oobj *leaf = object_material_leaf(o, hit.origin);
+        out->leaf = leaf->leaf_id;
+        out->color = s->material_rgb[leaf->material];
+    }
+    return 1;
+}
+
+typedef struct { v3 color; int leaf; int64_t steps; uint32_t shadow; } opixel;
+
+/* SdfScene.fs:7-28 */
+static opixel scene_trace(const fto_scene *s, oray ray) {
+    opixel px;
+    otrace res;
+    px.shadow = 0;
+    CNT(primary_rays);
+    if (!object_try_trace(s, s->root, ray, 1, &res, &px.steps)) {
+        px.color = s->background;
+        px.leaf = -1;
+        return px;
+    }
+    CNT(primary_hits);
+    v3 light_color = s->background;
+    for (int l = 0; l < s->n_lights; l++) {
+        const olight *lt = &s->lights[l];
+        v3 position = res.ray.origin; /* result.Position (Types.fs:65) */
+        v3 ldir = (lt->kind == FT_LIGHT_DIRECTIONAL) ? lt->v : vnormalize(vsub(lt->v, position));
+        float lcos = vdot(res.normal, ldir);
+        if (lcos > 0.0f) {
+            oray sr;
+            v3 intensity;
+            sr.origin = res.ray.origin;
+            sr.epsilon = res.ray.epsilon;
+            if (lt->kind == FT_LIGHT_DIRECTIONAL) { /* SdfLight.fs:10-20 */
+                sr.direction = lt->v;
+                sr.length = 1000.0f;
+                intensity = lt->color;
+            } else { /* SdfLight.fs:26-41 */
+                v3 diff = vsub(lt->v, res.ray.origin);
+                float d2 = vlen2(diff);
+                float d = sqrtf(d2);
+                sr.direction = vdiv(diff, d2);
+                sr.length = d;
+                intensity = vdiv(lt->color, d2);
+            }
+            CNT(shadow_rays);
+            otrace dummy;
+            if (!object_try_trace(s, s->root, sr, 0, &dummy, NULL)) {
+                light_color = vadd(light_color, vscale(intensity, lcos));
+                px.shadow |= (1u << l);
+            }
+        }
+    }
+    const float pi_inv = 1.0f / 3.14159274f; /* Math.fs:30  1f / MathF.PI */
+    px.color = vmul(res.color, vscale(light_color, pi_inv));
+    px.leaf = res.leaf;
+    return px;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Scene construction from the flat description                              */
+/* ------------------------------------------------------------------------ */
+static void set_err(char *err, int errlen, const char *msg) {
+    if (err && errlen > 0) { strncpy(err, msg, (size_t)errlen - 1); err[errlen - 1] = 0; }
+}
+static onode *new_node(fto_scene *s) {
+    if (s->n_owned == s->cap_owned) {
+        s->cap_owned = s->cap_owned ? s->cap_owned * 2 : 64;
+        s->owned = (onode **)realloc(s->owned, sizeof(onode *) * (size_t)s->cap_owned);
+    }
+    onode *n = (onode *)calloc(1, sizeof(onode));
+    s->owned[s->n_owned++] = n;
+    return n;
+}
+static void add_grid(fto_scene *s, grid *g) {
+    if (s->n_grids == s->cap_grids) {
+        s->cap_grids = s->cap_grids ? s->cap_grids * 2 : 8;
+        s->grids = (grid **)realloc(s->grids, sizeof(grid *) * (size_t)s->cap_grids);
+    }
+    s->grids[s->n_grids++] = g;
+}
+
+/* SdfForm.union / intersect / unionSmooth / subtract over already built children */
+static onode *make_composite(fto_scene *s, int kind, onode **kids, int n, float strength, char *err, int errlen) {
+    if (kind != FT_FORM_SUBTRACT) {
+        if (n == 0) { set_err(err, errlen, "No SdfObjects given."); return NULL; } /* SdfForm.fs:16,53,71 */
+        if (n == 1) return kids[0];                                                /* SdfForm.fs:17,54,72 */
+    } else if (n != 2) { set_err(err, errlen, "subtract needs exactly two forms"); return NULL; }
+    onode *nd = new_node(s);
+    nd->kind = kind;
+    nd->nchild = n;
+    nd->child = (onode **)malloc(sizeof(onode *) * (size_t)n);
+    memcpy(nd->child, kids, sizeof(onode *) * (size_t)n);
+    if (kind == FT_FORM_SUBTRACT) {
+        nd->boundary = kids[0]->boundary; /* SdfForm.fs:48 */
+    } else if (kind == FT_FORM_INTERSECT) {
+        bnd b = kids[0]->boundary;        /* SdfForm.fs:66, Seq.reduce */
+        for (int i = 1; i < n; i++) b = bnd_intersection(b, kids[i]->boundary);
+        nd->boundary = b;
+    } else {
+        bnd b = kids[0]->boundary;        /* SdfForm.fs:36-39 / 87-90, Seq.reduce */
+        for (int i = 1; i < n; i++) b = bnd_union(b, kids[i]->boundary);
+        nd->boundary = b;
+        if (kind == FT_FORM_UNION) {
+            bnd *bb = (bnd *)malloc(sizeof(bnd) * (size_t)n);
+            for (int i = 0; i < n; i++) bb[i] = kids[i]->boundary;
+            nd->g = grid_build(bb, n); /* SdfForm.fs:19 */
+            free(bb);
+            add_grid(s, nd->g);
+        } else {
+            nd->r0 = strength;
+            nd->r1 = -1.0f / strength; /* SdfForm.fs:75 */
+        }
+    }
+    return nd;
+}
+
+static onode *build_form(fto_scene *s, const ft_scene_desc *d, int id, int depth, char *err, int errlen) {
+    if (id < 0 || id >= d->n_forms) { set_err(err, errlen, "form id out of range"); return NULL; }
+    if (s->forms[id]) return s->forms[id];
+    if (depth > 64) { set_err(err, errlen, "form nesting too deep (cycle?)"); return NULL; }
+    const ft_form_desc *f = &d->forms[id];
+    const float *p = f->p;
+    onode *nd = NULL;
+    switch (f->kind) {
+    case FT_FORM_SPHERE: /* SdfForm.fs:125-135 */
+        nd = new_node(s); nd->kind = f->kind;
+        nd->a = V(p[0], p[1], p[2]); nd->r0 = p[3];
+        nd->boundary.c = nd->a; nd->boundary.r = nd->r0;
+        break;
+    case FT_FORM_CAPSULE: { /* SdfForm.fs:145-170 */
+        nd = new_node(s); nd->kind = f->kind;
+        v3 from = V(p[0], p[1], p[2]), to = V(p[3], p[4], p[5]);
+        nd->a = from; nd->b = vsub(to, from); nd->c = vinverse_length(nd->b); nd->r0 = p[6];
+        nd->boundary.c = vlerp(from, to, 0.5f);
+        nd->boundary.r = p[6] + vdist(from, to) * 0.5f;
+        break;
+    }
+    case FT_FORM_TORUS: { /* SdfForm.fs:181-203 */
+        nd = new_node(s); nd->kind = f->kind;
+        nd->a = V(p[0], p[1], p[2]);
+        nd->b = vnormalize(V(p[3], p[4], p[5]));
+        nd->r0 = -(vdot(nd->a, nd->b));
+        nd->r1 = p[6]; nd->r2 = p[7];
+        nd->boundary.c = nd->a; nd->boundary.r = p[6] + p[7];
+        break;
+    }
+    case FT_FORM_TRIANGLE: { /* SdfForm.fs:214-263 */
+        nd = new_node(s); nd->kind = f->kind;
+        v3 v1 = V(p[0], p[1], p[2]), v2 = V(p[3], p[4], p[5]), v3_ = V(p[6], p[7], p[8]);
+        float R = p[9];
+        nd->a = v1; nd->b = v2; nd->c = v3_; nd->r0 = R;
+        nd->e21 = vsub(v2, v1); nd->i21 = vinverse_length(nd->e21);
+        nd->e32 = vsub(v3_, v2); nd->i32 = vinverse_length(nd->e32);
+        nd->e13 = vsub(v1, v3_); nd->i13 = vinverse_length(nd->e13);
+        nd->nor = vnormalize(vcross(nd->e21, nd->e13));
+        nd->n21 = vnormalize(vcross(nd->e21, nd->nor));
+        nd->n32 = vnormalize(vcross(nd->e32, nd->nor));
+        nd->n13 = vnormalize(vcross(nd->e13, nd->nor));
+        float area_inv = 0.5f / vlen2(vcross(vsub(v1, v2), vsub(v2, v3_)));
+        float w1 = vlen2(vsub(v2, v3_)) * vdot(vsub(v1, v2), vsub(v1, v3_)) * area_inv;
+        float w2 = vlen2(vsub(v1, v3_)) * vdot(vsub(v2, v1), vsub(v2, v3_)) * area_inv;
+        float w3 = 1.0f - w1 - w2;
+        nd->boundary.c = vadd(vadd(vscale(v1, w1), vscale(v2, w2)), vscale(v3_, w3));
+        nd->boundary.r = vlen(nd->e21) * vlen(nd->e32) * vlen(nd->e13) / 2.0f / vlen(vcross(nd->e21, nd->e32)) + R;
+        break;
+    }
+    case FT_FORM_UNION: case FT_FORM_SUBTRACT: case FT_FORM_INTERSECT: case FT_FORM_UNION_SMOOTH: {
+        if (f->child_count < 0 || f->first_child < 0 || f->first_child + f->child_count > d->n_children) {
+            set_err(err, errlen, "form child range out of bounds"); return NULL;
+        }
+        onode **kids = (onode **)malloc(sizeof(onode *) * (size_t)(f->child_count + 1));
+        for (int i = 0; i < f->child_count; i++) {
+            kids[i] = build_form(s, d, d->children[f->first_child + i], depth + 1, err, errlen);
+            if (!kids[i]) { free(kids); return NULL; }
+        }
+        nd = make_composite(s, f->kind, kids, f->child_count, p[0], err, errlen);
+        free(kids);
+        if (!nd) return NULL;
+        break;
+    }
+    default:
+        set_err(err, errlen, "unsupported form kind");
+        return NULL;
+    }
+    s->forms[id] = nd;
+    return nd;
+}
+
+static oobj *build_object(fto_scene *s, const ft_scene_desc *d, int id, int depth, char *err, int errlen) {
+    if (id < 0 || id >= d->n_objects) { set_err(err, errlen, "object id out of range"); return NULL; }
+    if (s->objects[id]) return s->objects[id];
+    if (depth > 64) { set_err(err, errlen, "object nesting too deep (cycle?)"); return NULL; }
+    const ft_object_desc *od = &d->objects[id];
+    if (od->kind != FT_OBJECT_LEAF &&
+        (od->child_count < 0 || od->first_child < 0 || od->first_child + od->child_count > d->n_children)) {
+        set_err(err, errlen, "object child range out of bounds"); return NULL;
+    }
+    oobj *o = (oobj *)calloc(1, sizeof(oobj));
+    s->owned_obj[s->n_owned_obj++] = o;
+    o->kind = od->kind;
+    o->leaf_id = id;
+    switch (od->kind) {
+    case FT_OBJECT_LEAF: /* SdfObject.fs:6-10 */
+        if (od->material < 0 || od->material >= d->n_materials) { set_err(err, errlen, "material id out of range"); return NULL; }
+        o->form = build_form(s, d, od->form, 0, err, errlen);
+        if (!o->form) return NULL;
+        o->material = od->material;
+        break;
+    case FT_OBJECT_UNION: { /* SdfObject.fs:12-48 */
+        if (od->child_count == 0) { set_err(err, errlen, "No SdfObjects given."); return NULL; }
+        oobj **kids = (oobj **)malloc(sizeof(oobj *) * (size_t)od->child_count);
+        for (int i = 0; i < od->child_count; i++) {
+            kids[i] = build_object(s, d, d->children[od->first_child + i], depth + 1, err, errlen);
+            if (!kids[i]) { free(kids); return NULL; }
+        }
+        if (od->child_count == 1) { /* SdfObject.fs:16: the object itself */
+            oobj *only = kids[0];
+            free(kids);
+            s->objects[id] = only;
+            return only;
+        }
+        o->nchild = od->child_count;
+        o->child = kids;
+        onode **fk = (onode **)malloc(sizeof(onode *) * (size_t)o->nchild);
+        bnd *bb = (bnd *)malloc(sizeof(bnd) * (size_t)o->nchild);
+        for (int i = 0; i < o->nchild; i++) { fk[i] = kids[i]->form; bb[i] = kids[i]->form->boundary; }
+        o->form = make_composite(s, FT_FORM_UNION, fk, o->nchild, 0.0f, err, errlen); /* :18-21 */
+        o->g = grid_build(bb, o->nchild);                                              /* :26    */
+        free(fk); free(bb);
+        if (!o->form) return NULL;
+        break;
+    }
+    case FT_OBJECT_SUBTRACT: { /* SdfObject.fs:50-54 */
+        if (od->child_count != 1) { set_err(err, errlen, "subtract object needs one base object"); return NULL; }
+        o->base = build_object(s, d, d->children[od->first_child], depth + 1, err, errlen);
+        if (!o->base) return NULL;
+        onode *kids[2];
+        kids[0] = o->base->form;
+        kids[1] = build_form(s, d, od->form, 0, err, errlen);
+        if (!kids[1]) return NULL;
+        o->form = make_composite(s, FT_FORM_SUBTRACT, kids, 2, 0.0f, err, errlen);
+        if (!o->form) return NULL;
+        break;
+    }
+    case FT_OBJECT_INTERSECT: { /* SdfObject.fs:56-64 */
+        if (od->child_count < 1) { set_err(err, errlen, "intersect object needs a base object"); return NULL; }
+        o->base = build_object(s, d, d->children[od->first_child], depth + 1, err, errlen);
+        if (!o->base) return NULL;
+        onode **kids = (onode **)malloc(sizeof(onode *) * (size_t)od->child_count);
+        kids[0] = o->base->form;
+        for (int i = 1; i < od->child_count; i++) {
+            kids[i] = build_form(s, d, d->children[od->first_child + i], 0, err, errlen);
+            if (!kids[i]) { free(kids); return NULL; }
+        }
+        o->form = make_composite(s, FT_FORM_INTERSECT, kids, od->child_count, 0.0f, err, errlen);
+        free(kids);
+        if (!o->form) return NULL;
+        break;
+    }
+    default:
+        set_err(err, errlen, "unsupported object kind");
+        return NULL;
+    }
+    s->objects[id] = o;
+    return o;
+}
+
+FTO_API void fto_scene_destroy(fto_scene *s) {
+    if (!s) return;
+    for (int i = 0; i < s->n_owned; i++) {
+        if (s->owned[i]->g) grid_free(s->owned[i]->g);
+        free(s->owned[i]->child);
+        free(s->owned[i]);
+    }
+    for (int i = 0; i < s->n_owned_obj; i++) {
+        if (s->owned_obj[i]->g) grid_free(s->owned_obj[i]->g);
+        free(s->owned_obj[i]->child);
+        free(s->owned_obj[i]);
+    }
+    free(s->owned); free(s->owned_obj); free(s->forms); free(s->objects);
+    free(s->lights); free(s->material_rgb); free(s->grids);
+    free(s);
+}
+
+FTO_API int fto_scene_create(const ft_scene_desc *d, fto_scene **out, char *err, int errlen) {
+    if (!d || !out) { set_err(err, errlen, "null argument"); return FT_ERR_INVALID_ARGUMENT; }
+    fto_scene *s = (fto_scene *)calloc(1, sizeof(fto_scene));
+    s->n_forms = d->n_forms; s->n_objects = d->n_objects;
+    s->n_lights = d->n_lights; s->n_materials = d->n_materials;
+    s->forms = (onode **)calloc((size_t)d->n_forms + 1, sizeof(onode *));
+    s->objects = (oobj **)calloc((size_t)d->n_objects + 1, sizeof(oobj *));
+    s->owned_obj = (oobj **)calloc((size_t)d->n_objects + 1, sizeof(oobj *));
+    s->material_rgb = (v3 *)calloc((size_t)d->n_materials + 1, sizeof(v3));
+    s->lights = (olight *)calloc((size_t)d->n_lights + 1, sizeof(olight));
+    s->step_cap = (int64_t)1 << 22;
+    for (int i = 0; i < d->n_materials; i++)
+        s->material_rgb[i] = V(d->materials[i].rgb[0], d->materials[i].rgb[1], d->materials[i].rgb[2]);
+    for (int i = 0; i < d->n_lights; i++) {
+        const ft_light_desc *l = &d->lights[i];
+        s->lights[i].kind = l->kind;
+        s->lights[i].color = V(l->rgb[0], l->rgb[1], l->rgb[2]);
+        if (l->kind == FT_LIGHT_DIRECTIONAL) s->lights[i].v = vnormalize(vneg(V(l->v[0], l->v[1], l->v[2]))); /* SdfLight.fs:7 */
+        else if (l->kind == FT_LIGHT_POINT) s->lights[i].v = V(l->v[0], l->v[1], l->v[2]);
+        else { set_err(err, errlen, "unsupported light kind"); fto_scene_destroy(s); return FT_ERR_UNSUPPORTED_NODE; }
+    }
+    s->background = V(d->background[0], d->background[1], d->background[2]);
+    char local[256] = {0};
+    /* every constructor of the description runs, in index order (forms, then objects): an
+     * empty composite fails at construction like the reference's failwith */
+    int ok = 1;
+    for (int i = 0; ok && i < d->n_forms; i++) ok = build_form(s, d, i, 0, local, (int)sizeof(local)) != NULL;
+    for (int i = 0; ok && i < d->n_objects; i++) ok = build_object(s, d, i, 0, local, (int)sizeof(local)) != NULL;
+    s->root = ok ? build_object(s, d, d->root_object, 0, local, (int)sizeof(local)) : NULL;
+    if (!s->root) {
+        set_err(err, errlen, local);
+        int code = strstr(local, "No SdfObjects") ? FT_ERR_EMPTY_COMPOSITE
+                 : strstr(local, "unsupported") ? FT_ERR_UNSUPPORTED_NODE : FT_ERR_INVALID_ARGUMENT;
+        fto_scene_destroy(s);
+        return code;
+    }
+    *out = s;
+    return FT_OK;
+}
+
+FTO_API void fto_scene_set_step_cap(fto_scene *s, int64_t cap) { s->step_cap = cap; }
+
+/* ---- grid introspection (form-union grids in creation order) ------------- */
+FTO_API int fto_grid_count(const fto_scene *s) { return s->n_grids; }
+FTO_API int fto_grid_info(const fto_scene *s, int gi, ft_grid_info *out) {
+    if (gi < 0 || gi >= s->n_grids) return FT_ERR_INVALID_ARGUMENT;
+    const grid *g = s->grids[gi];
+    out->node = -1;
+    out->count[0] = g->cx; out->count[1] = g->cy; out->count[2] = g->cz;
+    out->aabb_min[0] = g->aabb_min.x; out->aabb_min[1] = g->aabb_min.y; out->aabb_min[2] = g->aabb_min.z;
+    out->cell_size[0] = g->cell_size.x; out->cell_size[1] = g->cell_size.y; out->cell_size[2] = g->cell_size.z;
+    out->cell_size_inv[0] = g->cell_size_inv.x; out->cell_size_inv[1] = g->cell_size_inv.y; out->cell_size_inv[2] = g->cell_size_inv.z;
+    out->n_entries = g->n_entries;
+    return FT_OK;
+}
+FTO_API int fto_grid_read(const fto_scene *s, int gi, float *centers, int64_t *begin, float *lb, int32_t *item) {
+    if (gi < 0 || gi >= s->n_grids) return FT_ERR_INVALID_ARGUMENT;
+    const grid *g = s->grids[gi];
+    size_t nc = (size_t)g->cx * g->cy * g->cz;
+    int64_t off = 0;
+    for (size_t c = 0; c < nc; c++) {
+        if (centers) { centers[3 * c] = g->cells[c].center.x; centers[3 * c + 1] = g->cells[c].center.y; centers[3 * c + 2] = g->cells[c].center.z; }
+        if (begin) begin[c] = off;
+        for (int i = 0; i < g->cells[c].n; i++) {
+            if (lb) lb[off + i] = g->cells[c].items[i].lb;
+            if (item) item[off + i] = g->cells[c].items[i].item;
+        }
+        off += g->cells[c].n;
+    }
+    if (begin) begin[nc] = off;
+    return FT_OK;
+}
+
+/* ---- camera (Camera.fs) --------------------------------------------------- */
+FTO_API float fto_lens_create(float fov) { return (float)sin((double)(fov * 0.5f)); } /* Camera.fs:13 */
+FTO_API void fto_camera_look_at(const float pos[3], const float look_at[3], const float up[3], float nps, ft_camera *out) {
+    v3 position = V(pos[0], pos[1], pos[2]);
+    v3 forward = vnormalize(vsub(V(look_at[0], look_at[1], look_at[2]), position)); /* Camera.fs:34 */
+    v3 right = vnormalize(vcross(V(up[0], up[1], up[2]), forward));                 /* Camera.fs:35 */
+    v3 ups = vscale(vcross(forward, right), nps);                                   /* Camera.fs:40 */
+    v3 rs = vscale(right, nps);                                                     /* Camera.fs:41 */
+    out->position[0] = position.x; out->position[1] = position.y; out->position[2] = position.z;
+    out->forward[0] = forward.x; out->forward[1] = forward.y; out->forward[2] = forward.z;
+    out->up_scaled[0] = ups.x; out->up_scaled[1] = ups.y; out->up_scaled[2] = ups.z;
+    out->right_scaled[0] = rs.x; out->right_scaled[1] = rs.y; out->right_scaled[2] = rs.z;
+}
+
+/* Image.fs:17-23 + Camera.fs:44-54 */
+static oray pixel_ray(const ft_camera *cam, int x, int y, int W, int H, float eps, float len) {
+    float max_size = (float)(W > H ? W : H);
+    float u = (float)x / max_size, v = (float)y / max_size;
+    v3 fwd = V(cam->forward[0], cam->forward[1], cam->forward[2]);
+    v3 rs = V(cam->right_scaled[0], cam->right_scaled[1], cam->right_scaled[2]);
+    v3 us = V(cam->up_scaled[0], cam->up_scaled[1], cam->up_scaled[2]);
+    oray r;
+    r.origin = V(cam->position[0], cam->position[1], cam->position[2]);
+    r.direction = vnormalize(vadd(vadd(fwd, vscale(rs, u - 0.5f)), vscale(us, v - 0.5f)));
+    r.epsilon = eps;
+    r.length = len;
+    return r;
+}
+
+/* ---- parallel drivers ------------------------------------------------------ */
+typedef struct {
+    const fto_scene *s;
+    const ft_camera *cam;
+    int W, H;
+    float eps, len;
+    int64_t n;
+    const ft_ray *rays;
+    const float *points;
+    float *out_rgb; int32_t *out_leaf; int32_t *out_steps; uint32_t *out_shadow; float *out_dist;
+    volatile int64_t next;
+    int64_t start;
+    int64_t chunk;
+    int mode; /* 0 render, 1 rays, 2 distance */
+    int want_counters;
+    pthread_mutex_t mu;
+    fto_counters total;
+} job;
+
+static void merge_counters(fto_counters *t, const fto_counters *c) {
+    t->march_steps += c->march_steps; t->primary_rays += c->primary_rays;
+    t->primary_hits += c->primary_hits; t->shadow_rays += c->shadow_rays;
+    t->eval_sphere += c->eval_sphere; t->eval_capsule += c->eval_capsule; t->eval_torus += c->eval_torus;
+    t->eval_triangle_edge += c->eval_triangle_edge; t->eval_triangle_face += c->eval_triangle_face;
+    t->union_lookups += c->union_lookups; t->lower_bound_tests += c->lower_bound_tests;
+    t->bound_tests += c->bound_tests; t->intersect_tests += c->intersect_tests;
+    if (c->max_steps > t->max_steps) t->max_steps = c->max_steps;
+}
+
+static void store_pixel(job *j, int64_t idx, const opixel *px) {
+    if (j->out_rgb) { j->out_rgb[3 * idx] = px->color.x; j->out_rgb[3 * idx + 1] = px->color.y; j->out_rgb[3 * idx + 2] = px->color.z; }
+    if (j->out_leaf) j->out_leaf[idx] = px->leaf;
+    if (j->out_steps) j->out_steps[idx] = (int32_t)px->steps;
+    if (j->out_shadow) j->out_shadow[idx] = px->shadow;
+}
+
+static void *worker(void *arg) {
+    job *j = (job *)arg;
+    fto_counters local;
+    memset(&local, 0, sizeof(local));
+    tl_ctr = j->want_counters ? &local : NULL;
+    for (;;) {
+        int64_t b = __sync_fetch_and_add(&j->next, j->chunk);
+        if (b >= j->n) break;
+        int64_t e = b + j->chunk < j->n ? b + j->chunk : j->n;
+        for (int64_t i = b; i < e; i++) {
+            if (j->mode == 0) {
+                /* Array2D.fs:30-38: columns x in parallel, rows y sequential; FColor[X,Y] is x-major */
+                int x = (int)i;
+                for (int y = 0; y < j->H; y++) {
+                    opixel px = scene_trace(j->s, pixel_ray(j->cam, x, y, j->W, j->H, j->eps, j->len));
+                    store_pixel(j, (int64_t)x * j->H + y, &px);
+                }
+            } else if (j->mode == 1) {
+                const ft_ray *r = &j->rays[i];
+                oray ry;
+                ry.origin = V(r->origin[0], r->origin[1], r->origin[2]);
+                ry.direction = V(r->direction[0], r->direction[1], r->direction[2]);
+                ry.length = r->length; ry.epsilon = r->epsilon;
+                opixel px = scene_trace(j->s, ry);
+                store_pixel(j, i, &px);
+            } else {
+                j->out_dist[i] = form_distance(j->s->root->form, V(j->points[3 * i], j->points[3 * i + 1], j->points[3 * i + 2]));
+            }
+        }
+    }
+    tl_ctr = NULL;
+    if (j->want_counters) {
+        pthread_mutex_lock(&j->mu);
+        merge_counters(&j->total, &local);
+        pthread_mutex_unlock(&j->mu);
+    }
+    return NULL;
+}
+
+static void run_job(job *j, int threads, fto_counters *ctr) {
+    if (threads < 1) threads = 1;
+    if (threads > 1024) threads = 1024;
+    j->next = j->start;
+    j->want_counters = ctr != NULL;
+    memset(&j->total, 0, sizeof(j->total));
+    pthread_mutex_init(&j->mu, NULL);
+    if (threads == 1) {
+        worker(j);
+    } else {
+        pthread_t *t = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+        for (int i = 0; i < threads; i++) pthread_create(&t[i], NULL, worker, j);
+        for (int i = 0; i < threads; i++) pthread_join(t[i], NULL);
+        free(t);
+    }
+    pthread_mutex_destroy(&j->mu);
+    if (ctr) *ctr = j->total;
+}
+
+/* Image.render (Image.fs:26-35), columns [x_begin, x_end) only; outputs are
+ * full-size x-major FColor[X,Y] arrays (only the requested columns written). */
+FTO_API int fto_render(const fto_scene *s, const ft_camera *cam, int W, int H, float eps, float len,
+                       int x_begin, int x_end, int threads, float *out_rgb, int32_t *out_leaf,
+                       int32_t *out_steps, uint32_t *out_shadow, fto_counters *ctr) {
+    if (!s || !cam || W <= 0 || H <= 0 || x_begin < 0 || x_end > W) return FT_ERR_INVALID_ARGUMENT;
+    job j;
+    memset(&j, 0, sizeof(j));
+    j.s = s; j.cam = cam; j.W = W; j.H = H; j.eps = eps; j.len = len;
+    j.out_rgb = out_rgb; j.out_leaf = out_leaf; j.out_steps = out_steps; j.out_shadow = out_shadow;
+    j.mode = 0; j.chunk = 1;
+    j.start = x_begin; j.n = x_end;
+    run_job(&j, threads, ctr);
+    return FT_OK;
+}
+
+/* batched SdfScene.trace */
+FTO_API int fto_trace_rays(const fto_scene *s, int64_t n, const ft_ray *rays, int threads, float *out_rgb,
+                           int32_t *out_leaf, int32_t *out_steps, uint32_t *out_shadow, fto_counters *ctr) {
+    if (!s || (n > 0 && !rays)) return FT_ERR_INVALID_ARGUMENT;
+    job j;
+    memset(&j, 0, sizeof(j));
+    j.s = s; j.n = n; j.rays = rays;
+    j.out_rgb = out_rgb; j.out_leaf = out_leaf; j.out_steps = out_steps; j.out_shadow = out_shadow;
+    j.mode = 1; j.chunk = 256;
+    run_job(&j, threads, ctr);
+    return FT_OK;
+}
+
+/* scene.Object.Form.Distance for n points */
+FTO_API int fto_distance(const fto_scene *s, int64_t n, const float *points, int threads, float *out, fto_counters *ctr) {
+    if (!s || (n > 0 && (!points || !out))) return FT_ERR_INVALID_ARGUMENT;
+    job j;
+    memset(&j, 0, sizeof(j));
+    j.s = s; j.n = n; j.points = points; j.out_dist = out;
+    j.mode = 2; j.chunk = 1024;
+    run_job(&j, threads, ctr);
+    return FT_OK;
+}
+
+/* Distance and Boundary of one described form (KATs for primitives/composites) */
+FTO_API int fto_form_distance(const fto_scene *s, int form_id, int64_t n, const float *points, float *out) {
+    if (!s || form_id < 0 || form_id >= s->n_forms || !s->forms[form_id]) return FT_ERR_INVALID_ARGUMENT;
+    for (int64_t i = 0; i < n; i++)
+        out[i] = form_distance(s->forms[form_id], V(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+    return FT_OK;
+}
+FTO_API int fto_form_boundary(const fto_scene *s, int form_id, float out[4]) {
+    if (!s || form_id < 0 || form_id >= s->n_forms || !s->forms[form_id]) return FT_ERR_INVALID_ARGUMENT;
+    bnd b = s->forms[form_id]->boundary;
+    out[0] = b.c.x; out[1] = b.c.y; out[2] = b.c.z; out[3] = b.r;
+    return FT_OK;
+}
+FTO_API int fto_root_boundary(const fto_scene *s, float out[4]) {
+    bnd b = s->root->form->boundary;
+    out[0] = b.c.x; out[1] = b.c.y; out[2] = b.c.z; out[3] = b.r;
+    return FT_OK;
+}
