@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -13,6 +14,8 @@
 #include "scene_compiler.h"
 
 namespace {
+
+constexpr unsigned kCounterRing = 256;
 
 thread_local std::string g_last_error;
 
@@ -73,6 +76,10 @@ struct ft_scene {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long *d_stats = nullptr, *h_stats = nullptr;
+    // ring of work counters for the persistent kernels: every launch zeroes and uses the next one, so that
+    // launches in flight on different streams never share a counter
+    unsigned long long *d_counters = nullptr;
+    unsigned counter_next = 0;
     // scratch for the host-pointer entry points, grown on demand
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -93,6 +100,7 @@ struct ft_scene {
         for (const void *p : ptrs)
             if (p) cudaFree(const_cast<void *>(p));
         if (d_stats) cudaFree(d_stats);
+        if (d_counters) cudaFree(d_counters);
         if (h_stats) cudaFreeHost(h_stats);
         if (d_scratch) cudaFree(d_scratch);
         for (auto &e : ev)
@@ -105,6 +113,12 @@ struct ft_scene {
 namespace {
 
 constexpr size_t kStatWords = (size_t)FT_STAT_SLOTS * FT_STAT_STRIDE;
+
+cudaError_t fresh_counter(ft_scene *scene, cudaStream_t stream, unsigned long long **out) {
+    unsigned long long *c = scene->d_counters + (size_t)(scene->counter_next++ % kCounterRing) * 16;
+    *out = c;
+    return cudaMemsetAsync(c, 0, sizeof(unsigned long long), stream);
+}
 
 void sum_stats(const unsigned long long *h, ft_render_stats *st) {
     unsigned long long hits = 0, shadow = 0, capped = 0, steps = 0, flops = 0;
@@ -255,6 +269,7 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&s->d_stats, kStatWords * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc stats");
     if ((e = cudaMemset(s->d_stats, 0, kStatWords * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset stats");
+    if ((e = cudaMalloc(&s->d_counters, kCounterRing * 16 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc counters");
     if ((e = cudaMallocHost(&s->h_stats, kStatWords * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMallocHost stats");
     *out = s;
     return FT_OK;
@@ -389,9 +404,11 @@ FT_API int ft_render_device(ft_scene *scene, const ft_camera *camera, int32_t wi
     const bool count = (flags & FT_FLAG_COUNTERS) != 0;
     const RenderParams P = make_params(width, height, epsilon, length, strip_width, rank, world);
     if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    unsigned long long *wc;
+    CU(fresh_counter(scene, s, &wc));
     cudaError_t e = (flags & FT_FLAG_FAST_MATH)
-                        ? ft_fast::launch_render(scene->dev, *camera, P, d_out_rgb, d_out_leaf, scene->d_stats, count, s)
-                        : ft_strict::launch_render(scene->dev, *camera, P, d_out_rgb, d_out_leaf, scene->d_stats, count, s);
+                        ? ft_fast::launch_render(scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, scene->d_stats, count, scene->sm_count, s)
+                        : ft_strict::launch_render(scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, scene->d_stats, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -428,36 +445,42 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
     int32_t *d_leaf = out_leaf ? (int32_t *)((char *)scene->d_scratch + rgb_bytes) : nullptr;
     const bool count = (flags & FT_FLAG_COUNTERS) != 0;
     const bool fast = (flags & FT_FLAG_FAST_MATH) != 0;
-    cudaStream_t s = scene->stream;
+    cudaStream_t s = scene->stream, s2 = scene->copy_stream;
     CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     CU(cudaEventRecord(scene->ev[0], s));
-    // Column bands: band k+1 renders while band k's pixels travel to the host on the copy stream.
-    const int bands = (npix >= (size_t)1 << 19) ? 8 : 1;
+    CU(cudaStreamWaitEvent(s2, scene->ev[0], 0));
+    // Column bands on two alternating streams: each band's pixels travel to the host right behind its
+    // kernel, while the other stream's band renders (and fills the SMs the draining band leaves idle).
+    int bands = (npix >= (size_t)1 << 19) ? 6 : 1;
+    if (const char *eb = getenv("FT_BANDS")) bands = std::max(1, atoi(eb));  // experiments only
     const int band_cols = ((width + bands - 1) / bands + 3) & ~3;
     int launches = 0;
     for (int x0 = 0; x0 < width; x0 += band_cols) {
+        cudaStream_t bs = (launches & 1) ? s2 : s;
         const int cols = std::min(band_cols, width - x0);
         RenderParams P = make_params(width, height, epsilon, length, cols, 0, 1);
         P.local_cols = cols;
         P.x_offset = x0;
         float *band_rgb = d_rgb + (size_t)x0 * height * 3;
         int32_t *band_leaf = d_leaf ? d_leaf + (size_t)x0 * height : nullptr;
-        cudaError_t e = fast ? ft_fast::launch_render(scene->dev, *camera, P, band_rgb, band_leaf, scene->d_stats, count, s)
-                             : ft_strict::launch_render(scene->dev, *camera, P, band_rgb, band_leaf, scene->d_stats, count, s);
+        unsigned long long *wc;
+        CU(fresh_counter(scene, bs, &wc));
+        cudaError_t e = fast ? ft_fast::launch_render(scene->dev, *camera, P, band_rgb, band_leaf, wc, scene->d_stats, count, scene->sm_count, bs)
+                             : ft_strict::launch_render(scene->dev, *camera, P, band_rgb, band_leaf, wc, scene->d_stats, count, scene->sm_count, bs);
         if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
         launches++;
-        CU(cudaEventRecord(scene->ev[3], s));
-        CU(cudaStreamWaitEvent(scene->copy_stream, scene->ev[3], 0));
+        CU(cudaEventRecord((launches & 1) ? scene->ev[1] : scene->ev[3], bs));  // end of the last kernel on each stream
         CU(cudaMemcpyAsync(out_rgb + (size_t)x0 * height * 3, band_rgb, (size_t)cols * height * 3 * sizeof(float),
-                           cudaMemcpyDeviceToHost, scene->copy_stream));
+                           cudaMemcpyDeviceToHost, bs));
         if (out_leaf)
             CU(cudaMemcpyAsync(out_leaf + (size_t)x0 * height, band_leaf, (size_t)cols * height * sizeof(int32_t),
-                               cudaMemcpyDeviceToHost, scene->copy_stream));
+                               cudaMemcpyDeviceToHost, bs));
     }
-    CU(cudaEventRecord(scene->ev[1], s));
+    if (launches > 1) {
+        CU(cudaEventRecord(scene->ev[2], s2));
+        CU(cudaStreamWaitEvent(s, scene->ev[2], 0));
+    }
     CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(scene->ev[2], scene->copy_stream));
-    CU(cudaStreamWaitEvent(s, scene->ev[2], 0));
     CU(cudaEventRecord(scene->ev[2], s));
     CU(cudaStreamSynchronize(s));
     if (stats) {
@@ -466,6 +489,11 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
         stats->primary_rays = (int64_t)npix;
         stats->launches = launches;
         cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
+        if (launches > 1) {
+            float other = 0.f;
+            cudaEventElapsedTime(&other, scene->ev[0], scene->ev[3]);
+            stats->kernel_ms = std::max(stats->kernel_ms, other);
+        }
         cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
     }
     return FT_OK;
@@ -505,9 +533,11 @@ FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_
     CU(cudaEventRecord(scene->ev[0], s));
     CU(cudaMemcpyAsync(d_rays, rays, ray_bytes, cudaMemcpyHostToDevice, s));
     CU(cudaEventRecord(scene->ev[3], s));
+    unsigned long long *wc;
+    CU(fresh_counter(scene, s, &wc));
     cudaError_t e = (flags & FT_FLAG_FAST_MATH)
-                        ? ft_fast::launch_trace_rays(scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, scene->d_stats, count, s)
-                        : ft_strict::launch_trace_rays(scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, scene->d_stats, count, s);
+                        ? ft_fast::launch_trace_rays(scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, wc, scene->d_stats, count, scene->sm_count, s)
+                        : ft_strict::launch_trace_rays(scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, wc, scene->d_stats, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "trace_rays kernel launch");
     CU(cudaEventRecord(scene->ev[1], s));
     if (out_rgb) CU(cudaMemcpyAsync(out_rgb, d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, s));

@@ -24,10 +24,11 @@ struct RenderParams {
 #define FT_DECLARE_LAUNCHERS(NS)                                                                                      \
     namespace NS {                                                                                                    \
     cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb,         \
-                              int *out_leaf, unsigned long long *stats, bool count, cudaStream_t stream);             \
+                              int *out_leaf, unsigned long long *work_counter, unsigned long long *stats, bool count, \
+                              int sm_count, cudaStream_t stream);                                                     \
     cudaError_t launch_trace_rays(const DevScene &S, const float4 *rays, long long n, float *out_rgb, int *out_leaf,  \
-                                  int *out_steps, unsigned *out_shadow, unsigned long long *stats, bool count,        \
-                                  cudaStream_t stream);                                                               \
+                                  int *out_steps, unsigned *out_shadow, unsigned long long *work_counter,             \
+                                  unsigned long long *stats, bool count, int sm_count, cudaStream_t stream);          \
     cudaError_t launch_distance(const DevScene &S, const float *pts, long long n, float *out, cudaStream_t stream);   \
     }
 

@@ -150,7 +150,7 @@ struct Frame {
 
 // ---- Form.Distance position for an arbitrary compiled form (the closure of Types.fs:42)
 template <bool COUNT>
-__device__ float eval_form(const DevScene &S, uint32_t root, V3 p, Acc &acc) {
+__device__ __forceinline__ float eval_form(const DevScene &S, uint32_t root, V3 p, Acc &acc) {
     if (FT_IS_PRIMITIVE(root)) return prim_distance<COUNT>(S, root, ld4(S.nodes + FT_WORD_OFF(root)), p, acc);
     Frame stack[FT_MAX_DEPTH];
     int sp = 0;
@@ -283,21 +283,10 @@ __device__ float eval_form(const DevScene &S, uint32_t root, V3 p, Acc &acc) {
     }
 }
 
-// ---- SdfForm.tryTrace (SdfForm.fs:93-104).  On return `o`/`len` are the (un-moved) hit ray's.
-// result: 1 hit, 0 miss, -1 stopped by the watchdog (treated as a miss by the callers)
+// out-of-line copy for the rare callers (composite children inside the material arg-min)
 template <bool COUNT>
-__device__ __forceinline__ int march(const DevScene &S, V3 &o, V3 d, float &len, float eps, int &steps, Acc &acc) {
-    steps = 0;
-    for (;;) {
-        if (len <= 0.0f) return 0;
-        if (steps >= S.step_cap) return -1;
-        const float dist = eval_form<COUNT>(S, S.root_word, o, acc);
-        steps++;
-        if (dist < eps) return 1;
-        o = o + d * dist;  // Ray.move (Ray.fs:9-13)
-        len = len - dist;
-        add_flops<COUNT>(acc, FLOPS_MOVE);
-    }
+__device__ __noinline__ float eval_form_call(const DevScene &S, uint32_t root, V3 p, Acc &acc) {
+    return eval_form<COUNT>(S, root, p, acc);
 }
 
 // ---- material arg-min: the leaf SdfObject whose material colours p (SdfObject.fs:27-46, 50-64)
@@ -315,7 +304,9 @@ __device__ int material_leaf(const DevScene &S, V3 p, Acc &acc) {
         float dtc;
         grid_cell<COUNT>(S, FT_WORD_OFF((uint32_t)rec.y), p, begin, dtc, acc);
         uint32_t best = begin;
-        float m = eval_form<COUNT>(S, __ldg(S.entries + begin).y, p, acc);  // :30
+        const uint32_t w0 = __ldg(S.entries + begin).y;
+        float m = FT_IS_PRIMITIVE(w0) ? prim_distance<COUNT>(S, w0, ld4(S.nodes + FT_WORD_OFF(w0)), p, acc)
+                                      : eval_form_call<COUNT>(S, w0, p, acc);  // :30
         // the reference's loop starts again at item 0 (:34); re-testing it cannot change min or material
         for (uint32_t i = begin + 1;; i++) {
             const uint2 e = __ldg(S.entries + i);
@@ -325,7 +316,9 @@ __device__ int material_leaf(const DevScene &S, V3 p, Acc &acc) {
             const float bd = distance(xyz(b0), p) - b0.w;
             add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
             if (m > bd) {
-                const float dd = (FT_WORD_KIND(e.y) == FT_K_SPHERE) ? bd : eval_form<COUNT>(S, e.y, p, acc);
+                const float dd = (FT_WORD_KIND(e.y) == FT_K_SPHERE) ? bd
+                                 : FT_IS_PRIMITIVE(e.y)              ? prim_distance<COUNT>(S, e.y, b0, p, acc)
+                                                                     : eval_form_call<COUNT>(S, e.y, p, acc);
                 if (dd < m) {  // :41-43
                     m = dd;
                     best = i;
@@ -334,89 +327,6 @@ __device__ int material_leaf(const DevScene &S, V3 p, Acc &acc) {
         }
         o = __ldg(S.obj_links + rec.z + __ldg(S.entry_child + best));
     }
-}
-
-struct TraceOut {
-    float r, g, b;
-    int leaf;
-    int steps;
-    uint32_t shadow;   // bit l: light l contributed
-    uint32_t n_shadow; // shadow rays cast
-    uint32_t capped;   // rays stopped by the watchdog
-};
-
-// ---- SdfScene.trace (SdfScene.fs:7-28) incl. SdfObject.tryTrace (SdfObject.fs:66-78) and the lights
-template <bool COUNT>
-__device__ TraceOut scene_trace(const DevScene &S, V3 o, V3 d, float len, float eps, Acc &acc) {
-    TraceOut out;
-    out.shadow = 0;
-    out.n_shadow = 0;
-    out.capped = 0;
-    const int hit = march<COUNT>(S, o, d, len, eps, out.steps, acc);
-    if (COUNT) acc.steps += (unsigned)out.steps;
-    if (hit <= 0) {
-        out.capped = hit < 0;
-        out.r = S.bg[0]; out.g = S.bg[1]; out.b = S.bg[2];
-        out.leaf = -1;
-        return out;
-    }
-    // SdfForm.normalFromRay (SdfForm.fs:106-115) on the un-moved hit ray
-    V3 n;
-    {
-        const float h = eps * 0.125f;
-        const V3 q = o + d * (-eps);
-        const float dx = eval_form<COUNT>(S, S.root_word, V3{q.x + h, q.y, q.z}, acc);
-        const float dy = eval_form<COUNT>(S, S.root_word, V3{q.x, q.y + h, q.z}, acc);
-        const float dz = eval_form<COUNT>(S, S.root_word, V3{q.x, q.y, q.z + h}, acc);
-        const float d0 = eval_form<COUNT>(S, S.root_word, q, acc);
-        n = normalize(V3{dx, dy, dz} - V3{d0, d0, d0});
-        add_flops<COUNT>(acc, FLOPS_NORMAL);
-    }
-    // Material.Color at the un-moved hit origin (SdfObject.fs:75-77)
-    const int leaf_obj = material_leaf<COUNT>(S, o, acc);
-    const int4 lrec = __ldg(S.objects + leaf_obj);
-    const float4 col = ld4(S.materials + lrec.z);
-    out.leaf = lrec.w;
-    // result.Ray = hit ray moved by -epsilon (SdfObject.fs:73)
-    const V3 pos = o + d * (-eps);
-    V3 lc = V3{S.bg[0], S.bg[1], S.bg[2]};  // SdfScene.fs:12
-    for (int l = 0; l < S.n_lights; l++) {
-        const float4 lv = ld4(S.lights + 2 * l), lrgb = ld4(S.lights + 2 * l + 1);
-        const bool directional = __float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL;
-        const V3 ldir = directional ? xyz(lv) : normalize(xyz(lv) - pos);  // SdfLight.fs:9 / :25
-        const float lcos = dot(n, ldir);                                    // SdfScene.fs:15
-        add_flops<COUNT>(acc, FLOPS_LIGHT);
-        if (lcos > 0.0f) {
-            V3 so = pos, sd, intensity;
-            float slen;
-            if (directional) {  // SdfLight.fs:10-20
-                sd = xyz(lv);
-                slen = 1000.0f;
-                intensity = xyz(lrgb);
-            } else {  // SdfLight.fs:26-41: direction = diff / distance2 (not unit length), Length = distance
-                const V3 diff = xyz(lv) - pos;
-                const float d2 = length2(diff);
-                slen = sqrtf(d2);
-                sd = diff / d2;
-                intensity = xyz(lrgb) / d2;
-                add_flops<COUNT>(acc, FLOPS_POINT_LIGHT);
-            }
-            int ssteps;
-            const int sh = march<COUNT>(S, so, sd, slen, eps, ssteps, acc);
-            if (COUNT) acc.steps += (unsigned)ssteps;
-            out.n_shadow++;
-            out.capped += sh < 0;
-            if (sh <= 0) {  // no shadow (SdfScene.fs:21-23)
-                lc = lc + intensity * lcos;
-                out.shadow |= 1u << l;
-            }
-        }
-    }
-    const float pi_inv = 1.0f / 3.14159274f;  // Math.fs:30
-    const V3 c = xyz(col) * (lc * pi_inv);    // SdfScene.fs:28
-    add_flops<COUNT>(acc, FLOPS_FINAL);
-    out.r = c.x; out.g = c.y; out.b = c.z;
-    return out;
 }
 
 // ---- Image.getUniformPixelPos + Camera.uniformPixelToRay (Image.fs:17-23, Camera.fs:44-54)

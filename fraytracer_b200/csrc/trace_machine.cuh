@@ -1,0 +1,313 @@
+// trace_machine.cuh -- the persistent "ray machine" kernel.
+//
+// Every lane runs a small state machine over ONE inlined call site of the distance evaluator:
+//
+//     FETCH -> primary march -> (hit) 4 normal probes -> material arg-min -> per light: shadow march -> store
+//
+// so that lanes of one warp that are in different phases of SdfScene.trace (one still marching its primary
+// ray, one probing its normal, one following a shadow ray) still execute the same instructions.  Lanes that
+// finish pull the next work item from a warp-private chunk (ballot + popc prefix ranks, no atomics); the
+// warp leader refills the chunk from one global counter (one atomic per FT_CHUNK items).  The grid is
+// persistent: resident-CTAs-per-SM x SM count, sized by the occupancy API.
+#pragma once
+#include "trace_device.cuh"
+
+namespace FT_NS {
+
+#ifndef FT_MINB
+#define FT_MINB 1
+#endif
+constexpr int MB = 128;             // threads per CTA
+constexpr int FT_CHUNK = 32;        // work items per global-counter grab (one tile of 4x8 pixels)
+
+enum : int {
+    PH_DONE = -1,
+    PH_FETCH = 0,
+    PH_PRIMARY = 1,   // marching the primary ray
+    PH_SHADOW = 2,    // marching a shadow ray
+    PH_N0 = 3,        // normal probes: +x, +y, +z, centre (SdfForm.fs:106-112)
+    PH_N1 = 4,
+    PH_N2 = 5,
+    PH_N3 = 6,
+};
+
+// ---- work sources -----------------------------------------------------------------------------------------
+// Image.render: item i -> pixel, tiles of 4 (x) by 8 (y) pixels, tiles ordered along y first so that a chunk
+// of 8 tiles is a 4 x 64 pixel block of the x-major FColor[X,Y] output.
+struct RenderJob {
+    ft_camera cam;
+    RenderParams P;
+    float *out_rgb;
+    int *out_leaf;
+    long long n_items;  // tiles * 32
+
+    __device__ __forceinline__ long long total() const { return n_items; }
+    // returns false when the item is padding (outside the image)
+    __device__ __forceinline__ bool load(long long i, V3 &o, V3 &d, float &len, float &eps, long long &slot) const {
+        const long long tile = i >> 5;
+        const int lane = (int)(i & 31);
+        const int tiles_y = (P.height + 7) >> 3;
+        const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
+        const int xl = tx * 4 + (lane >> 3);
+        const int y = ty * 8 + (lane & 7);
+        const int strip = xl / P.strip_width;
+        const int x = P.x_offset + (strip * P.world + P.rank) * P.strip_width + (xl - strip * P.strip_width);
+        if (xl >= P.local_cols || y >= P.height) return false;
+        slot = (long long)xl * P.height + y;
+        if (x >= P.width) {  // padding column of a strip buffer: defined contents for the all-gather
+            out_rgb[3 * slot + 0] = 0.f;
+            out_rgb[3 * slot + 1] = 0.f;
+            out_rgb[3 * slot + 2] = 0.f;
+            if (out_leaf) out_leaf[slot] = -1;
+            return false;
+        }
+        o = V3{cam.position[0], cam.position[1], cam.position[2]};
+        d = pixel_direction(cam, x, y, P.max_size);
+        len = P.length;
+        eps = P.epsilon;
+        return true;
+    }
+    __device__ __forceinline__ void store(long long slot, float r, float g, float b, int leaf, int, unsigned) const {
+        out_rgb[3 * slot + 0] = r;
+        out_rgb[3 * slot + 1] = g;
+        out_rgb[3 * slot + 2] = b;
+        if (out_leaf) out_leaf[slot] = leaf;
+    }
+};
+
+// batched SdfScene.trace: 32-byte ft_ray records read as two LDG.128
+struct RaysJob {
+    const float4 *rays;
+    long long n;
+    float *out_rgb;
+    int *out_leaf;
+    int *out_steps;
+    unsigned *out_shadow;
+
+    __device__ __forceinline__ long long total() const { return n; }
+    __device__ __forceinline__ bool load(long long i, V3 &o, V3 &d, float &len, float &eps, long long &slot) const {
+        const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+        o = V3{a.x, a.y, a.z};
+        d = V3{a.w, b.x, b.y};
+        len = b.z;
+        eps = b.w;
+        slot = i;
+        return true;
+    }
+    __device__ __forceinline__ void store(long long slot, float r, float g, float b, int leaf, int steps, unsigned shadow) const {
+        if (out_rgb) {
+            out_rgb[3 * slot + 0] = r;
+            out_rgb[3 * slot + 1] = g;
+            out_rgb[3 * slot + 2] = b;
+        }
+        if (out_leaf) out_leaf[slot] = leaf;
+        if (out_steps) out_steps[slot] = steps;
+        if (out_shadow) out_shadow[slot] = shadow;
+    }
+};
+
+template <bool COUNT, class Job>
+__global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_constant__ DevScene S, const __grid_constant__ Job job,
+                                                     unsigned long long *__restrict__ work_counter,
+                                                     unsigned long long *__restrict__ stats) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long total = job.total();
+
+    // warp-private chunk of work items
+    long long chunk_next = 0, chunk_end = 0;
+    bool exhausted = false;
+
+    // lane state
+    int phase = PH_FETCH;
+    long long slot = 0;
+    V3 o{0, 0, 0}, d{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, lc{0, 0, 0}, contrib{0, 0, 0};
+    float len = 0.f, eps = 1.f;
+    int steps = 0, primary_steps = 0, light = 0, leaf_obj = 0;
+    unsigned shadow_mask = 0;
+    // per-lane totals for the stats flush
+    unsigned n_hits = 0, n_shadow = 0, n_capped = 0;
+    Acc acc{0ull, 0ull};
+
+    for (;;) {
+        // ------------------------------------------------------------------ refill idle lanes
+        unsigned idle = __ballot_sync(FULL, phase == PH_FETCH);
+        while (idle) {
+            if (chunk_next >= chunk_end) {
+                if (exhausted) break;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)FT_CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                chunk_next = (long long)base;
+                chunk_end = chunk_next + FT_CHUNK < total ? chunk_next + FT_CHUNK : total;
+                if (chunk_next >= total) {
+                    exhausted = true;
+                    chunk_next = chunk_end = 0;
+                    break;
+                }
+            }
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            const long long mine = chunk_next + rank;
+            if (phase == PH_FETCH && mine < chunk_end) {
+                if (job.load(mine, o, d, len, eps, slot)) {
+                    add_flops<COUNT>(acc, FLOPS_PRIMARY_RAY);
+                    phase = PH_PRIMARY;
+                    steps = 0;
+                } else {
+                    phase = PH_FETCH;  // padding item: stay idle, take another one
+                }
+            }
+            const long long taken = chunk_end - chunk_next < (long long)__popc(idle) ? chunk_end - chunk_next : (long long)__popc(idle);
+            chunk_next += taken;
+            idle = __ballot_sync(FULL, phase == PH_FETCH);
+        }
+        if (exhausted && phase == PH_FETCH) phase = PH_DONE;
+        if (__all_sync(FULL, phase == PH_DONE)) break;
+
+        // ------------------------------------------------------------------ march pre-check (SdfForm.fs:94)
+        // a ray whose Length is exhausted (or that hit the watchdog) ends as a miss without another evaluation
+        int event = 0;  // 1 primary miss, 2 primary hit, 3 shadow finished (miss), 4 shadow finished (hit), 5 normal done
+        if (phase == PH_PRIMARY || phase == PH_SHADOW) {
+            if (len <= 0.0f || steps >= S.step_cap) {
+                if (!(len <= 0.0f)) n_capped++;
+                event = phase == PH_PRIMARY ? 1 : 3;
+            }
+        }
+        // ------------------------------------------------------------------ the one distance evaluation
+        if (phase > PH_FETCH && event == 0) {
+            V3 p = o;
+            if (phase >= PH_N0) {
+                const float h = eps * 0.125f;  // SdfForm.fs:115
+                p = q;
+                if (phase == PH_N0) p.x = q.x + h;
+                else if (phase == PH_N1) p.y = q.y + h;
+                else if (phase == PH_N2) p.z = q.z + h;
+            }
+            const float dist = eval_form<COUNT>(S, S.root_word, p, acc);
+            if (phase <= PH_SHADOW) {  // SdfForm.fs:97-104
+                steps++;
+                if (COUNT) acc.steps++;
+                if (dist < eps) {
+                    event = phase == PH_PRIMARY ? 2 : 4;
+                } else {
+                    o = o + d * dist;  // Ray.move
+                    len = len - dist;
+                    add_flops<COUNT>(acc, FLOPS_MOVE);
+                }
+            } else if (phase == PH_N0) {
+                n.x = dist;
+                phase = PH_N1;
+            } else if (phase == PH_N1) {
+                n.y = dist;
+                phase = PH_N2;
+            } else if (phase == PH_N2) {
+                n.z = dist;
+                phase = PH_N3;
+            } else {
+                n = normalize(n - V3{dist, dist, dist});  // SdfForm.fs:107-112
+                add_flops<COUNT>(acc, FLOPS_NORMAL);
+                event = 5;
+            }
+        }
+        // ------------------------------------------------------------------ transitions (once or a few times per ray)
+        if (event != 0) {
+            bool next_light = false, finish = false;
+            float r = S.bg[0], g = S.bg[1], b = S.bg[2];
+            int leaf = -1;
+            if (event == 1) {  // SdfScene.fs:10
+                primary_steps = steps;
+                shadow_mask = 0;
+                finish = true;
+            } else if (event == 2) {  // primary hit: SdfObject.fs:70-73
+                primary_steps = steps;
+                n_hits++;
+                q = o + d * (-eps);  // Ray.get (-epsilon): the normal's probe point and result.Ray's origin
+                phase = PH_N0;
+            } else if (event == 5) {
+                // Material.Color at the un-moved hit origin `o` (SdfObject.fs:75-77)
+                leaf_obj = material_leaf<COUNT>(S, o, acc);
+                lc = V3{S.bg[0], S.bg[1], S.bg[2]};  // SdfScene.fs:12
+                shadow_mask = 0;
+                light = 0;
+                next_light = true;
+            } else {  // shadow march finished
+                if (event == 3) {  // SdfScene.fs:21-23 no shadow
+                    lc = lc + contrib;
+                    shadow_mask |= 1u << light;
+                }
+                light++;
+                next_light = true;
+            }
+            if (next_light) {
+                finish = true;
+                for (; light < S.n_lights; light++) {  // SdfScene.fs:13-19
+                    const float4 lv = ld4(S.lights + 2 * light), lrgb = ld4(S.lights + 2 * light + 1);
+                    const bool directional = __float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL;
+                    const V3 ldir = directional ? xyz(lv) : normalize(xyz(lv) - q);  // SdfLight.fs:9 / :25
+                    const float lcos = dot(n, ldir);
+                    add_flops<COUNT>(acc, FLOPS_LIGHT);
+                    if (lcos > 0.0f) {
+                        V3 intensity;
+                        o = q;
+                        if (directional) {  // SdfLight.fs:10-20
+                            d = xyz(lv);
+                            len = 1000.0f;
+                            intensity = xyz(lrgb);
+                        } else {  // SdfLight.fs:26-41
+                            const V3 diff = xyz(lv) - q;
+                            const float d2 = length2(diff);
+                            len = sqrtf(d2);
+                            d = diff / d2;
+                            intensity = xyz(lrgb) / d2;
+                            add_flops<COUNT>(acc, FLOPS_POINT_LIGHT);
+                        }
+                        contrib = intensity * lcos;
+                        steps = 0;
+                        n_shadow++;
+                        phase = PH_SHADOW;
+                        finish = false;
+                        break;
+                    }
+                }
+                if (finish) {  // SdfScene.fs:28
+                    const int4 lrec = __ldg(S.objects + leaf_obj);
+                    const float4 col = ld4(S.materials + lrec.z);
+                    const float pi_inv = 1.0f / 3.14159274f;
+                    const V3 c = xyz(col) * (lc * pi_inv);
+                    add_flops<COUNT>(acc, FLOPS_FINAL);
+                    r = c.x; g = c.y; b = c.z;
+                    leaf = lrec.w;
+                }
+            }
+            if (finish) {
+                job.store(slot, r, g, b, leaf, primary_steps, shadow_mask);
+                phase = PH_FETCH;
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------------- stats
+    const unsigned hits = __reduce_add_sync(FULL, n_hits);
+    const unsigned shadows = __reduce_add_sync(FULL, n_shadow);
+    const unsigned capped = __reduce_add_sync(FULL, n_capped);
+    unsigned long long st = acc.steps, fl = acc.flops;
+    if (COUNT) {
+        for (int k = 16; k > 0; k >>= 1) {
+            st += __shfl_xor_sync(FULL, st, k);
+            fl += __shfl_xor_sync(FULL, fl, k);
+        }
+    }
+    if (lane == 0) {
+        const unsigned w = (blockIdx.x * (MB / 32) + (threadIdx.x >> 5)) & (FT_STAT_SLOTS - 1);
+        unsigned long long *s = stats + w * FT_STAT_STRIDE;
+        if (hits) atomicAdd(s + FT_STAT_HITS, (unsigned long long)hits);
+        if (shadows) atomicAdd(s + FT_STAT_SHADOW, (unsigned long long)shadows);
+        if (capped) atomicAdd(s + FT_STAT_CAPPED, (unsigned long long)capped);
+        if (COUNT) {
+            atomicAdd(s + FT_STAT_STEPS, st);
+            atomicAdd(s + FT_STAT_FLOPS, fl);
+        }
+    }
+}
+
+}  // namespace FT_NS
