@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s (primary + shadow rays) of the per-ray hot path, the metric BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config2|config1|config5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one frame of synthetic input: Image.render of the workload's
+scene through the compiled device scene (scene compilation happens once, outside the timed region, exactly
+like the reference's Stopwatch scope, Program.fs:89-94).
+
+  value      whole-job Mrays/s with everything resident in HBM (ft_render_device), CUDA events on the
+             launching stream, L2 flushed between timed iterations, max over ranks
+  e2e        the same metric through the reference-facing call (ft_render = Image.render) with HOST buffers:
+             camera/parameters host->device and the FColor[X,Y] framebuffer device->pinned host inside the
+             timed region
+  roofline   FP32 issue roofline of the dominant kernel (machine_kernel): algorithmic float32 operations of one
+             launch (instrumented variant, same inputs) / event-timed launch duration, against the FFMA peak
+             measured live on this GPU (MEASURED_PEAKS.json carries no FP32 number)
+  cpu_baseline / --impl reference
+             the CPU oracle (C restatement of the reference's F# path; .NET is unavailable)
+             on all host cores, on a bounded column sample of the same workload
+
+N > 1 is weak scaling: every GPU renders 1080p worth of pixels of an N-times larger frame of the same scene
+(column strips dealt round-robin, one NCCL all-gather of the framebuffer, de-interleave kernel), all inside
+the timed step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s (primary+secondary)"
+UNIT = "Mrays/s"
+
+
+def workload(name: str, world: int):
+    from fraytracer_b200 import scenes
+
+    s = math.sqrt(world)
+    if name == "config1":
+        n = int(round(1000 * s / 8)) * 8 if world > 1 else 1000
+        return scenes.default_scene(size=n)
+    if name == "config5":
+        return scenes.mixed_scene(width=int(round(3840 * s / 8)) * 8, height=int(round(2160 * s / 8)) * 8)
+    # config 2: BASELINE.json configs[1]
+    if world == 1:
+        return scenes.spheres_capsules_scene()
+    return scenes.spheres_capsules_scene(width=int(round(1920 * s / 8)) * 8, height=int(round(1080 * s / 8)) * 8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(orc, w, budget_s: float, threads: int):
+    """pick a column stride so that one oracle pass over the sample takes about budget_s"""
+    X, Y = w.size.X, w.size.Y
+    t0 = time.perf_counter()
+    r = orc.render(w.camera, X, Y, w.epsilon, w.length, threads=threads, x_stride=64, counters=True)
+    dt = time.perf_counter() - t0
+    rays = r["counters"]["primary_rays"] + r["counters"]["shadow_rays"]
+    rate = rays / max(dt, 1e-6)
+    full_rays = rays * 64.0
+    stride = 1
+    while stride < 64 and full_rays / stride / rate > budget_s:
+        stride *= 2
+    return stride
+
+
+def run_cpu(orc, w, stride: int, threads: int):
+    X, Y = w.size.X, w.size.Y
+    t0 = time.perf_counter()
+    r = orc.render(w.camera, X, Y, w.epsilon, w.length, threads=threads, x_stride=stride, counters=True)
+    dt = time.perf_counter() - t0
+    c = r["counters"]
+    return (c["primary_rays"] + c["shadow_rays"]), dt
+
+
+def bench_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The F# reference
+    cannot run here (no .NET), so this is the oracle port (cpu_baseline.kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import fraytracer_b200 as ft
+    from oracle import oracle as O
+
+    w = workload(args.workload, 1)
+    orc = O.OracleScene(ft.SceneDescription(w.scene))
+    threads = os.cpu_count() or 1
+    per_step = max(1.0, min(10.0, 150.0 / max(1, args.steps + args.warmup)))
+    stride = cpu_sample(orc, w, per_step, threads)
+    for _ in range(args.warmup):
+        run_cpu(orc, w, stride, threads)
+    rays = secs = 0.0
+    for _ in range(args.steps):
+        r, dt = run_cpu(orc, w, stride, threads)
+        rays += r
+        secs += dt
+    value = rays / secs / 1e6
+    sample = f"every {stride}th column of the {w.size.X}x{w.size.Y} frame ({int(rays / args.steps)} rays per step)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name, "image": f"{w.size.X}x{w.size.Y}", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C restatement of the F# path (oracle/ft_oracle.c); .NET unavailable"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def bench_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fraytracer_b200 as ft
+    from fraytracer_b200 import _abi as A
+    from fraytracer_b200.distributed import DistributedRenderer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    flags = A.FT_FLAG_FAST_MATH if args.fast else 0
+
+    w = workload(args.workload, world)
+    tracer = ft.SceneTracer(w.scene, device=local_rank)  # scene compile: outside the timed region (Program.fs:67-93)
+    renderer = DistributedRenderer(tracer, w.size, strip_width=8)
+    X, Y = w.size.X, w.size.Y
+    lib = tracer.lib
+
+    def allreduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    # ---- work of one step (deterministic): rays and algorithmic flops of this rank's strips
+    buf = renderer.local if world > 1 else renderer.final
+    st = tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(),
+                              stream=torch.cuda.current_stream().cuda_stream, flags=flags | A.FT_FLAG_COUNTERS,
+                              strip_width=8, rank=rank, world=world, want_stats=True)
+    my_rays = st["primary_rays"] + st["shadow_rays"]
+    my_flops = st["eval_flops"]
+    total_rays = allreduce(float(my_rays), dist.ReduceOp.SUM if world > 1 else None)
+    capped = allreduce(float(st["capped_rays"]), dist.ReduceOp.SUM if world > 1 else None)
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(timed):
+        flush.zero_()
+        stream = torch.cuda.current_stream().cuda_stream
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        if world == 1:
+            renderer.render(w.camera, w.epsilon, w.length, flags)
+            e1.record()
+        else:
+            tracer.render_device(w.camera, w.size, w.epsilon, w.length, renderer.local.data_ptr(), stream=stream,
+                                 flags=flags, strip_width=8, rank=rank, world=world)
+            e1.record()
+            dist.all_gather_into_tensor(renderer.gathered.view(-1, Y, 3), renderer.local)
+            A.check(lib.ft_deinterleave_device(C.c_void_p(renderer.gathered.data_ptr()), X, Y, 8, world, 3,
+                                               C.c_void_p(renderer.final.data_ptr()), C.c_void_p(stream) if stream else None))
+        e2.record()
+        return (e0, e1, e2) if timed else None
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    events = [one_step(True) for _ in range(args.steps)]
+    barrier()
+    step_ms = sum(e0.elapsed_time(e2) for e0, _, e2 in events)
+    kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in events) / args.steps
+    clocks = sampler.stop() if sampler else None
+    step_ms = allreduce(step_ms, dist.ReduceOp.MAX if world > 1 else None)
+    ms_per_step = step_ms / args.steps
+    value = total_rays / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the reference-facing call, host buffers
+    if world == 1:
+        host = C.c_void_p()
+        nbytes = X * Y * 12
+        A.check(lib.ft_host_alloc(C.byref(host), nbytes))  # page-locked FColor[X,Y]
+        out = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(X, Y, 3))
+        for _ in range(3):
+            tracer.render(w.camera, w.size, w.epsilon, w.length, flags=flags, out=out)
+        e2e_s = 0.0
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tracer.render(w.camera, w.size, w.epsilon, w.length, flags=flags, out=out)  # Image.render
+            e2e_s += time.perf_counter() - t0
+        checksum = float(out[::97, ::89].sum())
+        A.check(lib.ft_host_free(host))
+        h2d = C.sizeof(A.ft_camera) + 16
+        e2e_launches = 6 if X * Y >= (1 << 19) else 1
+    else:
+        pinned = torch.empty((X, Y, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+        e2e_s = 0.0
+        for it in range(args.steps + 2):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            final = renderer.render(w.camera, w.epsilon, w.length, flags)
+            if rank == 0:
+                pinned.copy_(final, non_blocking=True)
+            torch.cuda.synchronize()
+            if it >= 2:
+                e2e_s += time.perf_counter() - t0
+        e2e_s = allreduce(e2e_s, dist.ReduceOp.MAX)
+        checksum = float(pinned[::97, ::89].sum()) if rank == 0 else 0.0
+        h2d = C.sizeof(A.ft_camera) + 16
+        e2e_launches = 2
+    e2e_value = total_rays * args.steps / e2e_s / 1e6
+
+    if rank == 0:
+        # ---- FP32 roofline of the dominant kernel
+        tf, mhz = C.c_float(), C.c_float()
+        A.check(lib.ft_measure_fp32_peak(local_rank, C.byref(tf), C.byref(mhz)))
+        achieved = my_flops / (kern_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(w.name if world == 1 else "", None)
+        roofline = {"bound": "fp32", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
+                    "frac": achieved / tf.value if tf.value else None, "traffic": traffic,
+                    "kernel": "machine_kernel<RenderJob>", "kernel_ms": kern_ms, "flops_per_launch": my_flops,
+                    "peak_source": "measured live: dependent-free FFMA stream on all SMs, FMA = 2 flops "
+                                   "(MEASURED_PEAKS.json has no FP32 entry); strict mode issues no FMA, so its "
+                                   "ceiling is half of this",
+                    "mode": "fast (FMA contraction)" if args.fast else "strict (bit-exact, -fmad=false)"}
+        # ---- CPU baseline on this box's host cores (bounded sample)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle as O
+
+            orc = O.OracleScene(tracer.description)
+            threads = os.cpu_count() or 1
+            stride = cpu_sample(orc, w, 15.0, threads)
+            rays, secs = run_cpu(orc, w, stride, threads)
+            cpu = {"value": rays / secs / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"every {stride}th column of the {X}x{Y} frame ({rays} rays, {secs:.1f} s)",
+                   "note": "C restatement of the F# path (oracle/ft_oracle.c); .NET unavailable"}
+        info = tracer.info()
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "image": f"{X}x{Y}", "rays_per_step": int(total_rays),
+                       "primitives": info["n_primitives"], "grid_entries": info["n_entries"],
+                       "parallelism": f"image strips x{world}" + (" + NCCL all-gather" if world > 1 else ""),
+                       "l2": "flushed between timed iterations (512 MiB write)", "capped_rays": int(capped),
+                       "mode": "fast" if args.fast else "strict"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": X * Y * 12,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": checksum},
+            "gpu_launches": args.steps * renderer.launches_per_frame,
+            "e2e_gpu_launches": args.steps * e2e_launches,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config5"])
+    ap.add_argument("--fast", action="store_true", help="FT_FLAG_FAST_MATH (FMA contraction, not bit-exact)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_b200(args)
+
+
+if __name__ == "__main__":
+    main()

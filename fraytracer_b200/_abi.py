@@ -101,6 +101,7 @@ class ft_grid_info(C.Structure):
 class ft_render_stats(C.Structure):
     _fields_ = [("primary_rays", C.c_int64), ("primary_hits", C.c_int64), ("shadow_rays", C.c_int64),
                 ("capped_rays", C.c_int64), ("march_steps", C.c_int64), ("eval_flops", C.c_int64),
+                ("escaped_rays", C.c_int64),
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_int32),
                 ("reserved", C.c_int32)]
 
@@ -133,7 +134,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("FT_LIB") or LIB_PATH  # FT_LIB: development experiments only
     if not os.path.exists(p):
         raise FrayTracerError(
             FT_ERR_NO_DEVICE,

@@ -17,11 +17,13 @@
 //       intersect [1] bits{nchild, linkBase, -, -}    links[linkBase+i] = child word (SdfForm.fs:58-64)
 //       smooth    [1] {strength, -1/strength, bits(nchild), bits(linkBase)}         (SdfForm.fs:75-82)
 //   cells[]   float4   {centre.xyz, bits(entryBegin)} per grid cell, x-major like the .NET [,,] array
-//   entries[] uint2    {bits(LowerBound), child word}; each cell's list is sorted ascending by LowerBound
-//                      (SdfBoundary.fs:267-268) and closed by a sentinel {+inf, 0}: the loop
-//                      `if !(min > lb - dtc) break` is exactly equivalent to the reference's full scan
-//                      because the list is sorted and `min` never grows (DESIGN.md "early exit").
-//   entry_child[] int  child position inside the union (for the material arg-min and introspection)
+//   entries[] float4x2 one 32-byte record per candidate: {LowerBound, bits(child word), cx, cy} {cz, r,
+//                      bits(child position), -}: the child's bounding sphere is inlined so that the two
+//                      pruning tests of SdfForm.fs:29-31 need no dependent load.  Each cell's list is sorted
+//                      ascending by LowerBound (SdfBoundary.fs:267-268) and closed by a sentinel {+inf, ..}:
+//                      the loop `if !(min > lb - dtc) break` is exactly equivalent to the reference's full
+//                      scan because the list is sorted and `min` never grows (DESIGN.md "early exit").
+//                      Two padding records follow the last list (the scan prefetches one record ahead).
 //   objects[] int4     {kind, form word, a, b}: LEAF a=material b=leaf id | UNION a=objLinkBase b=unused
 //                      | SUBTRACT/INTERSECT a=base object
 //   obj_links[] int    object index of child i of an object union
@@ -58,8 +60,7 @@ enum : uint32_t {
 struct DevScene {
     const float4 *nodes;
     const float4 *cells;
-    const uint2 *entries;
-    const int32_t *entry_child;
+    const float4 *entries;  // 2 float4 per record
     const uint32_t *links;
     const int4 *objects;
     const int32_t *obj_links;
@@ -70,4 +71,14 @@ struct DevScene {
     int32_t n_lights;
     int32_t step_cap;
     float bg[3];
+    // world-space box of the largest spatial lookup.  Scheduling hint only (never used in arithmetic):
+    // evaluations outside it scan whole candidate lists, inside it only a few entries.
+    float pg_lo[3], pg_hi[3];
+    // Escape box: a box (already inflated by a safety slack) such that scene.Object.Form.Distance(p) >=
+    // dist(p, box) for every p (every primitive's bounding sphere lies inside it and the composites above
+    // only increase the distance).  A ray whose remaining half-line stays farther than epsilon from it can
+    // never satisfy `distance < epsilon` (SdfForm.fs:98): it is a miss without marching.  esc_valid == 0
+    // disables the shortcut (smooth unions with non-positive strength, non-finite boundaries, ...).
+    float esc_lo[3], esc_hi[3];
+    int32_t esc_valid;
 };

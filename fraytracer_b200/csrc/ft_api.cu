@@ -95,7 +95,7 @@ struct ft_scene {
         return e;
     }
     void release() {
-        const void *ptrs[] = {dev.nodes, dev.cells, dev.entries, dev.entry_child, dev.links,
+        const void *ptrs[] = {dev.nodes, dev.cells, dev.entries, dev.links,
                               dev.objects, dev.obj_links, dev.materials, dev.lights};
         for (const void *p : ptrs)
             if (p) cudaFree(const_cast<void *>(p));
@@ -121,7 +121,7 @@ cudaError_t fresh_counter(ft_scene *scene, cudaStream_t stream, unsigned long lo
 }
 
 void sum_stats(const unsigned long long *h, ft_render_stats *st) {
-    unsigned long long hits = 0, shadow = 0, capped = 0, steps = 0, flops = 0;
+    unsigned long long hits = 0, shadow = 0, capped = 0, steps = 0, flops = 0, escaped = 0;
     for (int s = 0; s < FT_STAT_SLOTS; s++) {
         const unsigned long long *p = h + (size_t)s * FT_STAT_STRIDE;
         hits += p[FT_STAT_HITS];
@@ -129,7 +129,9 @@ void sum_stats(const unsigned long long *h, ft_render_stats *st) {
         capped += p[FT_STAT_CAPPED];
         steps += p[FT_STAT_STEPS];
         flops += p[FT_STAT_FLOPS];
+        escaped += p[FT_STAT_ESCAPED];
     }
+    st->escaped_rays = (int64_t)escaped;
     st->primary_hits = (int64_t)hits;
     st->shadow_rays = (int64_t)shadow;
     st->capped_rays = (int64_t)capped;
@@ -248,8 +250,7 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
     int64_t bytes = 0;
     if ((e = upload(h.nodes, &s->dev.nodes, &bytes)) != cudaSuccess) return bail(e, "upload nodes");
     if ((e = upload(h.cells, &s->dev.cells, &bytes)) != cudaSuccess) return bail(e, "upload cells");
-    if ((e = upload(h.entries, &s->dev.entries, &bytes)) != cudaSuccess) return bail(e, "upload entries");
-    if ((e = upload(h.entry_child, &s->dev.entry_child, &bytes)) != cudaSuccess) return bail(e, "upload entry_child");
+    if ((e = upload(h.fat_entries, &s->dev.entries, &bytes)) != cudaSuccess) return bail(e, "upload entries");
     if ((e = upload(h.links, &s->dev.links, &bytes)) != cudaSuccess) return bail(e, "upload links");
     if ((e = upload(h.objects, &s->dev.objects, &bytes)) != cudaSuccess) return bail(e, "upload objects");
     if ((e = upload(h.obj_links, &s->dev.obj_links, &bytes)) != cudaSuccess) return bail(e, "upload obj_links");
@@ -263,6 +264,14 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
     s->dev.bg[0] = h.bg[0];
     s->dev.bg[1] = h.bg[1];
     s->dev.bg[2] = h.bg[2];
+    for (int k = 0; k < 3; k++) {
+        s->dev.pg_lo[k] = h.pg_lo[k];
+        s->dev.pg_hi[k] = h.pg_hi[k];
+        s->dev.esc_lo[k] = h.esc_lo[k];
+        s->dev.esc_hi[k] = h.esc_hi[k];
+    }
+    s->dev.esc_valid = h.esc_valid;
+    if (getenv("FT_NO_ESCAPE")) s->dev.esc_valid = 0;  // experiments only
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto &ev : s->ev)
@@ -340,17 +349,14 @@ FT_API int ft_scene_grid_read(const ft_scene *scene, int32_t grid, float *cell_c
     const ftc::GridHost &g = scene->host.grids[(size_t)grid];
     std::vector<float4> cells((size_t)g.n_cells);
     const size_t n_dev_entries = scene->host.entries.size();
-    std::vector<uint2> entries(n_dev_entries);
-    std::vector<int32_t> child(n_dev_entries);
+    std::vector<float4> fat(2 * n_dev_entries);
     if (scene->device == FT_DEVICE_NONE) {  // compile-only handle: the arrays that would have been uploaded
         std::copy(scene->host.cells.begin() + g.cell_base, scene->host.cells.begin() + g.cell_base + g.n_cells, cells.begin());
-        entries = scene->host.entries;
-        child = scene->host.entry_child;
+        std::copy(scene->host.fat_entries.begin(), scene->host.fat_entries.begin() + 2 * n_dev_entries, fat.begin());
     } else {  // read back what the kernels actually see
         DeviceGuard guard(scene->device);
         CU(cudaMemcpy(cells.data(), scene->dev.cells + g.cell_base, sizeof(float4) * (size_t)g.n_cells, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(entries.data(), scene->dev.entries, sizeof(uint2) * n_dev_entries, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(child.data(), scene->dev.entry_child, sizeof(int32_t) * n_dev_entries, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(fat.data(), scene->dev.entries, sizeof(float4) * 2 * n_dev_entries, cudaMemcpyDeviceToHost));
     }
     int64_t off = 0;
     for (int64_t c = 0; c < g.n_cells; c++) {
@@ -363,12 +369,13 @@ FT_API int ft_scene_grid_read(const ft_scene *scene, int32_t grid, float *cell_c
         uint32_t b;
         std::memcpy(&b, &cells[(size_t)c].w, 4);
         for (size_t i = b; i < n_dev_entries; i++) {
-            float lb;
-            std::memcpy(&lb, &entries[i].x, 4);
-            if (child[i] < 0) break;  // sentinel
+            const float lb = fat[2 * i].x;
+            int32_t child_i;
+            std::memcpy(&child_i, &fat[2 * i + 1].z, 4);
+            if (child_i < 0) break;  // sentinel
             if (off >= g.n_entries) return fail(FT_ERR_CUDA, "device grid is longer than the compiled grid");
             if (entry_lower_bound) entry_lower_bound[off] = lb;
-            if (entry_item) entry_item[off] = child[i];
+            if (entry_item) entry_item[off] = child_i;
             off++;
         }
     }
@@ -525,8 +532,8 @@ FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_
     float4 *d_rays = (float4 *)base;
     float *d_rgb = (float *)(base + ray_bytes);
     int32_t *d_leaf = (int32_t *)(base + ray_bytes + rgb_bytes);
-    int32_t *d_steps = d_leaf + N;
-    uint32_t *d_shadow = (uint32_t *)(d_steps + N);
+    int32_t *d_steps = out_steps ? d_leaf + N : nullptr;  // null: the kernel may use the escape proof
+    uint32_t *d_shadow = (uint32_t *)(d_leaf + 2 * N);
     cudaStream_t s = scene->stream;
     const bool count = (flags & FT_FLAG_COUNTERS) != 0;
     CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));

@@ -12,6 +12,7 @@
 #define FT_STAT_CAPPED 2
 #define FT_STAT_STEPS 3
 #define FT_STAT_FLOPS 4
+#define FT_STAT_ESCAPED 5
 
 struct RenderParams {
     int width, height;   // image X, Y

@@ -45,11 +45,11 @@ cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderP
     unsigned grid = 1;
     cudaError_t e;
     if (count) {
-        if ((e = persistent_grid(machine_kernel<true, RenderJob>, job.n_items, sm_count, &grid)) != cudaSuccess) return e;
-        machine_kernel<true, RenderJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);
+        if ((e = persistent_grid(machine_kernel<true, true, RenderJob>, job.n_items, sm_count, &grid)) != cudaSuccess) return e;
+        machine_kernel<true, true, RenderJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);
     } else {
-        if ((e = persistent_grid(machine_kernel<false, RenderJob>, job.n_items, sm_count, &grid)) != cudaSuccess) return e;
-        machine_kernel<false, RenderJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);
+        if ((e = persistent_grid(machine_kernel<false, true, RenderJob>, job.n_items, sm_count, &grid)) != cudaSuccess) return e;
+        machine_kernel<false, true, RenderJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);
     }
     return cudaGetLastError();
 }
@@ -61,13 +61,18 @@ cudaError_t launch_trace_rays(const DevScene &S, const float4 *rays, long long n
     RaysJob job{rays, n, out_rgb, out_leaf, out_steps, out_shadow};
     unsigned grid = 1;
     cudaError_t e;
-    if (count) {
-        if ((e = persistent_grid(machine_kernel<true, RaysJob>, n, sm_count, &grid)) != cudaSuccess) return e;
-        machine_kernel<true, RaysJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);
-    } else {
-        if ((e = persistent_grid(machine_kernel<false, RaysJob>, n, sm_count, &grid)) != cudaSuccess) return e;
-        machine_kernel<false, RaysJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);
-    }
+    // per-ray step counts requested: every march is followed to its end (no escape proof)
+    const bool escape = out_steps == nullptr;
+#define FT_LAUNCH_RAYS(C, E)                                                                                          \
+    do {                                                                                                              \
+        if ((e = persistent_grid(machine_kernel<C, E, RaysJob>, n, sm_count, &grid)) != cudaSuccess) return e;        \
+        machine_kernel<C, E, RaysJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);                          \
+    } while (0)
+    if (count && escape) FT_LAUNCH_RAYS(true, true);
+    else if (count) FT_LAUNCH_RAYS(true, false);
+    else if (escape) FT_LAUNCH_RAYS(false, true);
+    else FT_LAUNCH_RAYS(false, false);
+#undef FT_LAUNCH_RAYS
     return cudaGetLastError();
 }
 

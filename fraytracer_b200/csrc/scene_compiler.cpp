@@ -572,6 +572,45 @@ class Compiler {
         return FT_OK;
     }
 
+    // Conservative box with Distance(p) >= dist(p, box) - slack for the form rooted at node i (device_scene.h).
+    struct EscBox {
+        double lo[3], hi[3], slack;
+        bool ok;
+    };
+    EscBox escape_box(int i, int depth = 0) const {
+        const FormNode &n = nodes_[(size_t)i];
+        EscBox b{{0, 0, 0}, {0, 0, 0}, 0.0, true};
+        if (depth > 64) { b.ok = false; return b; }
+        switch (n.kind) {
+            case FT_FORM_SPHERE: case FT_FORM_CAPSULE: case FT_FORM_TORUS: case FT_FORM_TRIANGLE: {
+                // every primitive's surface lies inside its bounding sphere (SdfForm.fs:131-134,166-169,199-202,252-263)
+                const double c[3] = {n.b.c.x, n.b.c.y, n.b.c.z}, r = n.b.r;
+                b.ok = std::isfinite(r) && r >= 0.0 && std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]);
+                for (int k = 0; k < 3; k++) { b.lo[k] = c[k] - r; b.hi[k] = c[k] + r; }
+                return b;
+            }
+            case FT_FORM_SUBTRACT:   // Max(-b, a) >= a
+            case FT_FORM_INTERSECT:  // running max >= first child
+                return escape_box(n.kids[0], depth + 1);
+            default: {               // union: min over children; smooth union: >= min - strength*ln(n)
+                for (size_t k = 0; k < n.kids.size(); k++) {
+                    EscBox c = escape_box(n.kids[k], depth + 1);
+                    if (!c.ok) { b.ok = false; return b; }
+                    for (int a = 0; a < 3; a++) {
+                        b.lo[a] = k ? std::min(b.lo[a], c.lo[a]) : c.lo[a];
+                        b.hi[a] = k ? std::max(b.hi[a], c.hi[a]) : c.hi[a];
+                    }
+                    b.slack = std::max(b.slack, c.slack);
+                }
+                if (n.kind == FT_FORM_UNION_SMOOTH) {
+                    if (!(n.strength > 0.f) || !std::isfinite(n.strength)) { b.ok = false; return b; }
+                    b.slack += (double)n.strength * std::log((double)n.kids.size());
+                }
+                return b;
+            }
+        }
+    }
+
     int emit() {
         CompiledScene &o = *out_;
         // 1. offsets
@@ -690,9 +729,48 @@ class Compiler {
         if (o.lights.empty()) o.lights.push_back(f4(0, 0, 0, 0));
         o.n_lights = d_->n_lights;
         o.bg[0] = d_->background[0]; o.bg[1] = d_->background[1]; o.bg[2] = d_->background[2];
+        {
+            const float inf = std::numeric_limits<float>::infinity();
+            for (int k = 0; k < 3; k++) { o.pg_lo[k] = inf; o.pg_hi[k] = -inf; }
+            int64_t best = -1;
+            for (const GridHost &g : grids_)
+                if (g.n_entries > best) {
+                    best = g.n_entries;
+                    for (int k = 0; k < 3; k++) {
+                        o.pg_lo[k] = g.aabb_min[k];
+                        o.pg_hi[k] = g.aabb_min[k] + g.cell_size[k] * (float)g.count[k];
+                    }
+                }
+        }
+        {
+            EscBox b = escape_box(objs_[(size_t)o.root_object].form);
+            o.esc_valid = b.ok ? 1 : 0;
+            for (int k = 0; k < 3 && b.ok; k++) {
+                // inflate: composite slack + generous room for float32 rounding of positions and distances
+                const double ext = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+                const double pad = b.slack + 1e-3 * (1.0 + ext + (b.hi[k] - b.lo[k]));
+                o.esc_lo[k] = (float)(b.lo[k] - pad);
+                o.esc_hi[k] = (float)(b.hi[k] + pad);
+                if (!std::isfinite(o.esc_lo[k]) || !std::isfinite(o.esc_hi[k])) o.esc_valid = 0;
+            }
+        }
         o.grids = std::move(grids_);
         if (o.cells.empty()) o.cells.push_back(f4(0, 0, 0, 0));
-        if (o.entries.empty()) { o.entries.push_back(uint2{0, 0}); o.entry_child.push_back(-1); }
+        if (o.entries.empty()) { o.entries.push_back(uint2{as_uint(std::numeric_limits<float>::infinity()), 0}); o.entry_child.push_back(-1); }
+        // 6. the 32-byte candidate records the kernels read (bounding sphere inlined) + 2 padding records
+        o.fat_entries.reserve(2 * (o.entries.size() + 2));
+        for (size_t e = 0; e < o.entries.size(); e++) {
+            const uint2 en = o.entries[e];
+            const int32_t child = o.entry_child[e];
+            float4 b = f4(0, 0, 0, 0);
+            if (child >= 0) b = o.nodes[FT_WORD_OFF(en.y)];
+            o.fat_entries.push_back(f4(as_float(en.x), as_float(child >= 0 ? en.y : 0u), b.x, b.y));
+            o.fat_entries.push_back(f4(b.z, b.w, as_float((uint32_t)child), 0.f));
+        }
+        for (int k = 0; k < 2; k++) {
+            o.fat_entries.push_back(f4(std::numeric_limits<float>::infinity(), 0.f, 0.f, 0.f));
+            o.fat_entries.push_back(f4(0.f, 0.f, as_float((uint32_t)-1), 0.f));
+        }
         return FT_OK;
     }
 };

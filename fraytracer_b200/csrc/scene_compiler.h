@@ -27,8 +27,9 @@ struct GridHost {
 struct CompiledScene {
     std::vector<float4> nodes;
     std::vector<float4> cells;
-    std::vector<uint2> entries;
-    std::vector<int32_t> entry_child;
+    std::vector<uint2> entries;        // host staging: {bits(LowerBound), child word}
+    std::vector<int32_t> entry_child;  // host staging: child position, -1 for sentinels
+    std::vector<float4> fat_entries;   // what is uploaded: see device_scene.h
     std::vector<uint32_t> links;
     std::vector<int4> objects;
     std::vector<int32_t> obj_links;
@@ -39,6 +40,9 @@ struct CompiledScene {
     int32_t root_object = 0;
     int32_t n_lights = 0;
     float bg[3] = {0, 0, 0};
+    float pg_lo[3] = {0, 0, 0}, pg_hi[3] = {0, 0, 0};  // box of the largest grid (scheduling hint)
+    float esc_lo[3] = {0, 0, 0}, esc_hi[3] = {0, 0, 0};  // escape box (device_scene.h)
+    int32_t esc_valid = 0;
     int32_t n_nodes = 0, n_primitives = 0, max_depth = 0;
 };
 

@@ -113,30 +113,65 @@ __device__ __forceinline__ void grid_cell(const DevScene &S, uint32_t uoff, V3 p
     begin = __float_as_uint(cell.w);
 }
 
+// one 32-byte candidate record (device_scene.h): two independent LDG.128 from the same sector
+struct Entry {
+    float4 a;  // {LowerBound, bits(child word), cx, cy}
+    float4 b;  // {cz, r, bits(child position), -}
+    __device__ __forceinline__ float lb() const { return a.x; }
+    __device__ __forceinline__ uint32_t word() const { return __float_as_uint(a.y); }
+    __device__ __forceinline__ float4 bound() const { return float4{a.z, a.w, b.x, b.y}; }
+    __device__ __forceinline__ int child() const { return __float_as_int(b.z); }
+};
+__device__ __forceinline__ Entry ld_entry(const DevScene &S, uint32_t i) {
+    const float4 *p = S.entries + 2ull * i;
+    return Entry{__ldg(p), __ldg(p + 1)};
+}
+
+// ---- the second pruning test, SdfForm.fs:31 / SdfObject.fs:38:  min > Vector3.Distance(C, p) - R.
+// s = |C - p|^2 is formed exactly like the reference; the root is only taken when the outcome is open:
+//   m + R <= 0              =>  sqrt(s) - R >= -R >= m          =>  false
+//   s > (m+R)^2 (1 + 2^-12)  =>  fl(sqrt(s)) > m + R (the 2^-13 margin dwarfs the 3 roundings involved)
+//                            =>  fl(sqrt(s)) - R > m, and rounding is monotone  =>  false
+// Otherwise bd = fl(fl(sqrt(s)) - R) is computed as the reference does and compared.  `bd` is only valid
+// when the function returns true.  NaNs fall through to the exact path (all comparisons false).
+__device__ __forceinline__ bool bound_test(float m, float4 b0, V3 p, float &bd) {
+    const V3 dl = xyz(b0) - p;
+    const float s = dot(dl, dl);
+    const float u = m + b0.w;
+    if (u <= 0.0f || s > (u * u) * 1.000244140625f) return false;
+    bd = sqrtf(s) - b0.w;
+    return m > bd;
+}
+
 // ---- union candidate scan (SdfForm.fs:27-33) from entry i with running minimum m.
 // Returns true when the list is exhausted (early exit on the sorted LowerBound, see device_scene.h);
 // false when entry i is a composite child that must be evaluated by the caller.
+// The next record is fetched before the current one is tested (the list is closed by a sentinel and the
+// array by two padding records, so the speculative load is always in bounds).
 template <bool COUNT>
 __device__ __forceinline__ bool union_scan(const DevScene &S, V3 p, float dtc, uint32_t &i, float &m, uint32_t &child, Acc &acc) {
+    Entry e = ld_entry(S, i);
     for (;;) {
-        const uint2 e = __ldg(S.entries + i);
+        const Entry nx = ld_entry(S, i + 1);
         add_flops<COUNT>(acc, FLOPS_LB_TEST);
-        if (!(m > __uint_as_float(e.x) - dtc)) return true;
-        const float4 b0 = ld4(S.nodes + FT_WORD_OFF(e.y));
-        const float bd = distance(xyz(b0), p) - b0.w;  // SdfBoundary.getMinDistance
+        if (!(m > e.lb() - dtc)) return true;
+        const float4 b0 = e.bound();
+        float bd;
         add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
-        if (m > bd) {
-            if (FT_WORD_KIND(e.y) == FT_K_SPHERE) {
+        if (bound_test(m, b0, p, bd)) {  // m > SdfBoundary.getMinDistance boundary position
+            const uint32_t w = e.word();
+            if (FT_WORD_KIND(w) == FT_K_SPHERE) {
                 m = bd;  // the sphere's Distance is the same expression: Min(m, bd) = bd here
                 add_flops<COUNT>(acc, FLOPS_MINMAX);
-            } else if (FT_IS_PRIMITIVE(e.y)) {
-                m = fminf(m, prim_distance<COUNT>(S, e.y, b0, p, acc));
+            } else if (FT_IS_PRIMITIVE(w)) {
+                m = fminf(m, prim_distance<COUNT>(S, w, b0, p, acc));
                 add_flops<COUNT>(acc, FLOPS_MINMAX);
             } else {
-                child = e.y;
+                child = w;
                 return false;
             }
         }
+        e = nx;
         i++;
     }
 }
@@ -168,9 +203,10 @@ __device__ __forceinline__ float eval_form(const DevScene &S, uint32_t root, V3 
                 uint32_t i;
                 float dtc;
                 grid_cell<COUNT>(S, off, p, i, dtc, acc);
-                const uint32_t first = __ldg(S.entries + i).y;
+                const Entry e0 = ld_entry(S, i);
+                const uint32_t first = e0.word();
                 if (FT_IS_PRIMITIVE(first)) {
-                    float m = prim_distance<COUNT>(S, first, ld4(S.nodes + FT_WORD_OFF(first)), p, acc);  // :26
+                    float m = prim_distance<COUNT>(S, first, e0.bound(), p, acc);  // :26
                     i++;
                     uint32_t child;
                     if (union_scan<COUNT>(S, p, dtc, i, m, child, acc)) {
@@ -304,29 +340,56 @@ __device__ int material_leaf(const DevScene &S, V3 p, Acc &acc) {
         float dtc;
         grid_cell<COUNT>(S, FT_WORD_OFF((uint32_t)rec.y), p, begin, dtc, acc);
         uint32_t best = begin;
-        const uint32_t w0 = __ldg(S.entries + begin).y;
-        float m = FT_IS_PRIMITIVE(w0) ? prim_distance<COUNT>(S, w0, ld4(S.nodes + FT_WORD_OFF(w0)), p, acc)
+        const Entry e0 = ld_entry(S, begin);
+        const uint32_t w0 = e0.word();
+        float m = FT_IS_PRIMITIVE(w0) ? prim_distance<COUNT>(S, w0, e0.bound(), p, acc)
                                       : eval_form_call<COUNT>(S, w0, p, acc);  // :30
         // the reference's loop starts again at item 0 (:34); re-testing it cannot change min or material
         for (uint32_t i = begin + 1;; i++) {
-            const uint2 e = __ldg(S.entries + i);
+            const Entry e = ld_entry(S, i);
             add_flops<COUNT>(acc, FLOPS_LB_TEST);
-            if (!(m > __uint_as_float(e.x) - dtc)) break;
-            const float4 b0 = ld4(S.nodes + FT_WORD_OFF(e.y));
-            const float bd = distance(xyz(b0), p) - b0.w;
+            if (!(m > e.lb() - dtc)) break;
+            const float4 b0 = e.bound();
+            const uint32_t w = e.word();
+            float bd;
             add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
-            if (m > bd) {
-                const float dd = (FT_WORD_KIND(e.y) == FT_K_SPHERE) ? bd
-                                 : FT_IS_PRIMITIVE(e.y)              ? prim_distance<COUNT>(S, e.y, b0, p, acc)
-                                                                     : eval_form_call<COUNT>(S, e.y, p, acc);
+            if (bound_test(m, b0, p, bd)) {
+                const float dd = (FT_WORD_KIND(w) == FT_K_SPHERE) ? bd
+                                 : FT_IS_PRIMITIVE(w)              ? prim_distance<COUNT>(S, w, b0, p, acc)
+                                                                   : eval_form_call<COUNT>(S, w, p, acc);
                 if (dd < m) {  // :41-43
                     m = dd;
                     best = i;
                 }
             }
         }
-        o = __ldg(S.obj_links + rec.z + __ldg(S.entry_child + best));
+        o = __ldg(S.obj_links + rec.z + ld_entry(S, best).child());
     }
+}
+
+// ---- escape proof (device_scene.h "Escape box"): true when the half-line {o + t d, t >= 0} certainly stays
+// farther than eps from the escape box, so that no future Distance along the ray can be < eps.  Conservative:
+// any NaN or doubt answers false.  The reciprocal may be approximate: the box carries a 1e-3 relative slack.
+__device__ __forceinline__ bool ray_escapes(const DevScene &S, V3 o, V3 d, float eps) {
+    const float ov[3] = {o.x, o.y, o.z}, dv[3] = {d.x, d.y, d.z};
+    float tmin = 0.0f, tmax = __int_as_float(0x7f800000);
+    bool apart = false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float lo = S.esc_lo[k] - eps, hi = S.esc_hi[k] + eps;
+        if (dv[k] == 0.0f) {
+            apart = apart || ov[k] < lo || ov[k] > hi;  // parallel to the slab and outside it
+        } else {
+            const float inv = __fdividef(1.0f, dv[k]);
+            const float t1 = (lo - ov[k]) * inv, t2 = (hi - ov[k]) * inv;
+            tmin = fmaxf(tmin, fminf(t1, t2));
+            tmax = fminf(tmax, fmaxf(t1, t2));
+        }
+    }
+    return apart || tmax < tmin;
+}
+__device__ __forceinline__ bool outside_box(const float lo[3], const float hi[3], V3 p) {
+    return p.x < lo[0] || p.y < lo[1] || p.z < lo[2] || p.x >= hi[0] || p.y >= hi[1] || p.z >= hi[2];
 }
 
 // ---- Image.getUniformPixelPos + Camera.uniformPixelToRay (Image.fs:17-23, Camera.fs:44-54)

@@ -15,9 +15,12 @@
 namespace FT_NS {
 
 #ifndef FT_MINB
-#define FT_MINB 1
+#define FT_MINB 8  // <= 64 registers: 32 resident warps per SM (measured faster than 96 regs without spills)
 #endif
 constexpr int MB = 128;             // threads per CTA
+#ifndef FT_LONG_BATCH
+#define FT_LONG_BATCH 16
+#endif
 constexpr int FT_CHUNK = 32;        // work items per global-counter grab (one tile of 4x8 pixels)
 
 enum : int {
@@ -29,6 +32,7 @@ enum : int {
     PH_N1 = 4,
     PH_N2 = 5,
     PH_N3 = 6,
+    PH_PROBE = 7,     // Distance at the common origin of all primary rays (render jobs), once per warp
 };
 
 // ---- work sources -----------------------------------------------------------------------------------------
@@ -42,8 +46,12 @@ struct RenderJob {
     long long n_items;  // tiles * 32
 
     __device__ __forceinline__ long long total() const { return n_items; }
+    // all primary rays start at the camera position: Distance there is evaluated once per warp
+    static constexpr bool kProbe = true;
+    __device__ __forceinline__ V3 probe_point() const { return V3{cam.position[0], cam.position[1], cam.position[2]}; }
     // returns false when the item is padding (outside the image)
-    __device__ __forceinline__ bool load(long long i, V3 &o, V3 &d, float &len, float &eps, long long &slot) const {
+    __device__ __forceinline__ bool load(long long i, float d0, V3 &o, V3 &d, float &len, float &eps, long long &slot,
+                                         int &steps) const {
         const long long tile = i >> 5;
         const int lane = (int)(i & 31);
         const int tiles_y = (P.height + 7) >> 3;
@@ -65,6 +73,14 @@ struct RenderJob {
         d = pixel_direction(cam, x, y, P.max_size);
         len = P.length;
         eps = P.epsilon;
+        steps = 0;
+        // first iteration of SdfForm.tryTrace (SdfForm.fs:94-104) with the shared Distance d0 = D(camera):
+        // Length > 0 and not a hit  =>  Ray.move d0.  Any other case is left to the generic path.
+        if (len > 0.0f && d0 >= eps) {
+            o = o + d * d0;
+            len = len - d0;
+            steps = 1;
+        }
         return true;
     }
     __device__ __forceinline__ void store(long long slot, float r, float g, float b, int leaf, int, unsigned) const {
@@ -85,7 +101,11 @@ struct RaysJob {
     unsigned *out_shadow;
 
     __device__ __forceinline__ long long total() const { return n; }
-    __device__ __forceinline__ bool load(long long i, V3 &o, V3 &d, float &len, float &eps, long long &slot) const {
+    static constexpr bool kProbe = false;
+    __device__ __forceinline__ V3 probe_point() const { return V3{0.f, 0.f, 0.f}; }
+    __device__ __forceinline__ bool load(long long i, float, V3 &o, V3 &d, float &len, float &eps, long long &slot,
+                                         int &steps) const {
+        steps = 0;
         const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
         o = V3{a.x, a.y, a.z};
         d = V3{a.w, b.x, b.y};
@@ -106,7 +126,9 @@ struct RaysJob {
     }
 };
 
-template <bool COUNT, class Job>
+// ESCAPE: resolve rays by the escape proof (identical colours / leaf / shadow mask; the step counters then
+// count only the evaluations actually performed, so it is off when per-ray step counts are requested).
+template <bool COUNT, bool ESCAPE, class Job>
 __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_constant__ DevScene S, const __grid_constant__ Job job,
                                                      unsigned long long *__restrict__ work_counter,
                                                      unsigned long long *__restrict__ stats) {
@@ -119,14 +141,15 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     bool exhausted = false;
 
     // lane state
-    int phase = PH_FETCH;
+    int phase = Job::kProbe ? PH_PROBE : PH_FETCH;
+    float d0 = 0.f;
     long long slot = 0;
     V3 o{0, 0, 0}, d{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, lc{0, 0, 0}, contrib{0, 0, 0};
     float len = 0.f, eps = 1.f;
     int steps = 0, primary_steps = 0, light = 0, leaf_obj = 0;
     unsigned shadow_mask = 0;
     // per-lane totals for the stats flush
-    unsigned n_hits = 0, n_shadow = 0, n_capped = 0;
+    unsigned n_hits = 0, n_shadow = 0, n_capped = 0, n_escaped = 0;
     Acc acc{0ull, 0ull};
 
     for (;;) {
@@ -149,10 +172,9 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
             const int rank = __popc(idle & ((1u << lane) - 1u));
             const long long mine = chunk_next + rank;
             if (phase == PH_FETCH && mine < chunk_end) {
-                if (job.load(mine, o, d, len, eps, slot)) {
+                if (job.load(mine, d0, o, d, len, eps, slot, steps)) {
                     add_flops<COUNT>(acc, FLOPS_PRIMARY_RAY);
                     phase = PH_PRIMARY;
-                    steps = 0;
                 } else {
                     phase = PH_FETCH;  // padding item: stay idle, take another one
                 }
@@ -171,18 +193,31 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
             if (len <= 0.0f || steps >= S.step_cap) {
                 if (!(len <= 0.0f)) n_capped++;
                 event = phase == PH_PRIMARY ? 1 : 3;
+            } else if (ESCAPE && S.esc_valid && outside_box(S.esc_lo, S.esc_hi, o) && ray_escapes(S, o, d, eps)) {
+                n_escaped++;
+                event = phase == PH_PRIMARY ? 1 : 3;
             }
         }
         // ------------------------------------------------------------------ the one distance evaluation
-        if (phase > PH_FETCH && event == 0) {
-            V3 p = o;
-            if (phase >= PH_N0) {
-                const float h = eps * 0.125f;  // SdfForm.fs:115
-                p = q;
-                if (phase == PH_N0) p.x = q.x + h;
-                else if (phase == PH_N1) p.y = q.y + h;
-                else if (phase == PH_N2) p.z = q.z + h;
-            }
+        V3 p = o;
+        if (Job::kProbe && phase == PH_PROBE) {
+            p = job.probe_point();
+        } else if (phase >= PH_N0) {
+            const float h = eps * 0.125f;  // SdfForm.fs:115
+            p = q;
+            if (phase == PH_N0) p.x = q.x + h;
+            else if (phase == PH_N1) p.y = q.y + h;
+            else if (phase == PH_N2) p.z = q.z + h;
+        }
+        // Scheduling only (no arithmetic depends on it): positions outside the largest lookup's box scan whole
+        // candidate lists (50-140 entries), positions inside it a handful.  The warp runs the two classes in
+        // separate iterations so that one long scan does not hold 31 short ones hostage.
+        const bool wants = phase > PH_FETCH && event == 0;
+        const bool is_long = p.x < S.pg_lo[0] || p.y < S.pg_lo[1] || p.z < S.pg_lo[2] || p.x >= S.pg_hi[0] ||
+                             p.y >= S.pg_hi[1] || p.z >= S.pg_hi[2];
+        const unsigned m_long = __ballot_sync(FULL, wants && is_long), m_short = __ballot_sync(FULL, wants && !is_long);
+        const bool run_long = m_short == 0u || __popc(m_long) >= FT_LONG_BATCH;
+        if (wants && is_long == run_long) {
             const float dist = eval_form<COUNT>(S, S.root_word, p, acc);
             if (phase <= PH_SHADOW) {  // SdfForm.fs:97-104
                 steps++;
@@ -194,6 +229,9 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                     len = len - dist;
                     add_flops<COUNT>(acc, FLOPS_MOVE);
                 }
+            } else if (Job::kProbe && phase == PH_PROBE) {
+                d0 = dist;
+                phase = PH_FETCH;
             } else if (phase == PH_N0) {
                 n.x = dist;
                 phase = PH_N1;
@@ -290,6 +328,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     const unsigned hits = __reduce_add_sync(FULL, n_hits);
     const unsigned shadows = __reduce_add_sync(FULL, n_shadow);
     const unsigned capped = __reduce_add_sync(FULL, n_capped);
+    const unsigned escaped = __reduce_add_sync(FULL, n_escaped);
     unsigned long long st = acc.steps, fl = acc.flops;
     if (COUNT) {
         for (int k = 16; k > 0; k >>= 1) {
@@ -303,6 +342,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         if (hits) atomicAdd(s + FT_STAT_HITS, (unsigned long long)hits);
         if (shadows) atomicAdd(s + FT_STAT_SHADOW, (unsigned long long)shadows);
         if (capped) atomicAdd(s + FT_STAT_CAPPED, (unsigned long long)capped);
+        if (escaped) atomicAdd(s + FT_STAT_ESCAPED, (unsigned long long)escaped);
         if (COUNT) {
             atomicAdd(s + FT_STAT_STEPS, st);
             atomicAdd(s + FT_STAT_FLOPS, fl);

@@ -1,0 +1,83 @@
+"""Multi-GPU image partitioning: pixels are independent, the compiled scene is small
+and replicated on every GPU, the image is cut into column strips dealt round-robin to the ranks
+(strip s -> rank s % world), every rank renders its strips into a compact buffer, one NCCL all-gather
+moves the framebuffer over NVLink and a de-interleave kernel restores the x-major FColor[X,Y].
+
+One process per GPU; torch.distributed is only the plumbing around the C ABI (`ft_render_device`,
+`ft_deinterleave_device`).  The N-GPU framebuffer must be bit-identical to the 1-GPU one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _abi as A
+
+
+def strip_layout(width: int, height: int, strip_width: int, world: int):
+    """(strips_per_rank, floats_per_rank) of the compact per-rank buffer -- same arithmetic as ft_strip_layout"""
+    strips = (width + strip_width - 1) // strip_width
+    spr = (strips + world - 1) // world
+    cols = width if world == 1 else spr * strip_width
+    return spr, cols * height * 3
+
+
+def owned_columns(width: int, strip_width: int, rank: int, world: int):
+    """[(local_column_begin, image_column_begin, n_columns)] of the strips rank owns, in buffer order"""
+    strips = (width + strip_width - 1) // strip_width
+    out = []
+    for local, s in enumerate(range(rank, strips, world)):
+        x0 = s * strip_width
+        out.append((local * strip_width, x0, min(strip_width, width - x0)))
+    return out
+
+
+def deinterleave_reference(gathered, width: int, height: int, strip_width: int, world: int):
+    """numpy/torch restatement of ft_deinterleave_device for the CPU (gloo) tests:
+    gathered [world, spr*strip_width, height, C] -> [width, height, C]"""
+    out = gathered.new_zeros((width, height, gathered.shape[-1])) if hasattr(gathered, "new_zeros") else None
+    if out is None:
+        import numpy as np
+
+        out = np.zeros((width, height, gathered.shape[-1]), gathered.dtype)
+    for rank in range(world):
+        for lc, x0, n in owned_columns(width, strip_width, rank, world):
+            out[x0:x0 + n] = gathered[rank, lc:lc + n]
+    return out
+
+
+class DistributedRenderer:
+    """Renders one frame cooperatively on all ranks of `group`; every rank ends with the full framebuffer."""
+
+    def __init__(self, tracer, size, strip_width: int = 8, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.tracer, self.size, self.strip_width, self.group = tracer, size, strip_width, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        dev = torch.device("cuda", tracer.device)
+        X, Y = size.X, size.Y
+        self.spr, _ = strip_layout(X, Y, strip_width, self.world)
+        self.final = torch.empty((X, Y, 3), dtype=torch.float32, device=dev)
+        if self.world > 1:
+            cols = self.spr * strip_width
+            self.local = torch.empty((cols, Y, 3), dtype=torch.float32, device=dev)
+            self.gathered = torch.empty((self.world, cols, Y, 3), dtype=torch.float32, device=dev)
+        self.launches_per_frame = 1 if self.world == 1 else 2
+
+    def render(self, camera, epsilon: float, length: float, flags: int = 0):
+        torch = self.torch
+        stream = torch.cuda.current_stream().cuda_stream
+        X, Y = self.size.X, self.size.Y
+        if self.world == 1:
+            self.tracer.render_device(camera, self.size, epsilon, length, self.final.data_ptr(), stream=stream,
+                                      flags=flags, strip_width=self.strip_width, rank=0, world=1)
+            return self.final
+        self.tracer.render_device(camera, self.size, epsilon, length, self.local.data_ptr(), stream=stream,
+                                  flags=flags, strip_width=self.strip_width, rank=self.rank, world=self.world)
+        self.dist.all_gather_into_tensor(self.gathered.view(-1, Y, 3), self.local, group=self.group)  # NCCL over NVLink
+        A.check(self.tracer.lib.ft_deinterleave_device(C.c_void_p(self.gathered.data_ptr()), X, Y, self.strip_width,
+                                                       self.world, 3, C.c_void_p(self.final.data_ptr()),
+                                                       C.c_void_p(stream) if stream else None))
+        return self.final

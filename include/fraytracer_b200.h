@@ -197,6 +197,8 @@ typedef struct ft_render_stats {
     int64_t capped_rays;     /* rays stopped by the watchdog step cap          */
     int64_t march_steps;     /* Distance evaluations inside march loops (0 unless FT_FLAG_COUNTERS) */
     int64_t eval_flops;      /* algorithmic f32 operations (0 unless FT_FLAG_COUNTERS) */
+    int64_t escaped_rays;    /* rays (primary or shadow) ended by the escape proof: their remaining
+                              * half-line stays outside the scene's bounding box, so they cannot hit */
     float kernel_ms;         /* device time of the kernels of this call        */
     float total_ms;          /* device time incl. copies of this call          */
     int32_t launches;        /* kernels launched by this call                  */

@@ -358,11 +358,14 @@ static void grid_free(grid *g) {
     free(g);
 }
 /* :276-282 */
+static __thread int tl_outside = 0;
 static inline const gcell *grid_lookup(const grid *g, v3 p) {
     v3 c = vmul(vsub(p, g->aabb_min), g->cell_size_inv);
-    int ix = clamp_i(0, g->cx - 1, floor_i(c.x));
-    int iy = clamp_i(0, g->cy - 1, floor_i(c.y));
-    int iz = clamp_i(0, g->cz - 1, floor_i(c.z));
+    int fx = floor_i(c.x), fy = floor_i(c.y), fz = floor_i(c.z);
+    int ix = clamp_i(0, g->cx - 1, fx);
+    int iy = clamp_i(0, g->cy - 1, fy);
+    int iz = clamp_i(0, g->cz - 1, fz);
+    tl_outside = (ix != fx) || (iy != fy) || (iz != fz);
     return &g->cells[((size_t)ix * g->cy + iy) * g->cz + iz];
 }
 
@@ -392,6 +395,7 @@ typedef struct fto_counters {
     int64_t lower_bound_tests, bound_tests; /* the two pruning tests          */
     int64_t intersect_tests;
     int64_t max_steps;      /* longest single march                           */
+    int64_t outside_lookups, outside_bound_tests, outside_evals; /* same, for positions outside the grid AABB */
 } fto_counters;
 
 static __thread fto_counters *tl_ctr = NULL;
@@ -402,7 +406,9 @@ static float form_distance(const onode *n, v3 p);
 /* SdfForm.fs:22-34 */
 static float union_distance(const onode *n, v3 p) {
     const gcell *cell = grid_lookup(n->g, p);
+    const int outside = tl_outside;
     CNT(union_lookups);
+    if (outside) CNT(outside_lookups);
     float dtc = vdist(p, cell->center);
     float min = form_distance(n->child[cell->items[0].item], p);
     for (int i = 1; i < cell->n; i++) {
@@ -411,7 +417,11 @@ static float union_distance(const onode *n, v3 p) {
         CNT(lower_bound_tests);
         if (min > it->lb - dtc) {
             CNT(bound_tests);
-            if (min > bnd_min_distance(f->boundary, p)) min = net_min(min, form_distance(f, p));
+            if (outside) CNT(outside_bound_tests);
+            if (min > bnd_min_distance(f->boundary, p)) {
+                if (outside) CNT(outside_evals);
+                min = net_min(min, form_distance(f, p));
+            }
         }
     }
     return min;
@@ -994,6 +1004,7 @@ typedef struct {
     volatile int64_t next;
     int64_t start;
     int64_t chunk;
+    int x0, xstride; /* render: column of item i is x0 + i*xstride */
     int mode; /* 0 render, 1 rays, 2 distance */
     int want_counters;
     pthread_mutex_t mu;
@@ -1008,6 +1019,8 @@ static void merge_counters(fto_counters *t, const fto_counters *c) {
     t->union_lookups += c->union_lookups; t->lower_bound_tests += c->lower_bound_tests;
     t->bound_tests += c->bound_tests; t->intersect_tests += c->intersect_tests;
     if (c->max_steps > t->max_steps) t->max_steps = c->max_steps;
+    t->outside_lookups += c->outside_lookups; t->outside_bound_tests += c->outside_bound_tests;
+    t->outside_evals += c->outside_evals;
 }
 
 static void store_pixel(job *j, int64_t idx, const opixel *px) {
@@ -1029,7 +1042,7 @@ static void *worker(void *arg) {
         for (int64_t i = b; i < e; i++) {
             if (j->mode == 0) {
                 /* Array2D.fs:30-38: columns x in parallel, rows y sequential; FColor[X,Y] is x-major */
-                int x = (int)i;
+                int x = j->x0 + (int)i * j->xstride;
                 for (int y = 0; y < j->H; y++) {
                     opixel px = scene_trace(j->s, pixel_ray(j->cam, x, y, j->W, j->H, j->eps, j->len));
                     store_pixel(j, (int64_t)x * j->H + y, &px);
@@ -1075,18 +1088,19 @@ static void run_job(job *j, int threads, fto_counters *ctr) {
     if (ctr) *ctr = j->total;
 }
 
-/* Image.render (Image.fs:26-35), columns [x_begin, x_end) only; outputs are
+/* Image.render (Image.fs:26-35), columns x_begin, x_begin+x_stride, ... < x_end only; outputs are
  * full-size x-major FColor[X,Y] arrays (only the requested columns written). */
 FTO_API int fto_render(const fto_scene *s, const ft_camera *cam, int W, int H, float eps, float len,
-                       int x_begin, int x_end, int threads, float *out_rgb, int32_t *out_leaf,
+                       int x_begin, int x_end, int x_stride, int threads, float *out_rgb, int32_t *out_leaf,
                        int32_t *out_steps, uint32_t *out_shadow, fto_counters *ctr) {
-    if (!s || !cam || W <= 0 || H <= 0 || x_begin < 0 || x_end > W) return FT_ERR_INVALID_ARGUMENT;
+    if (!s || !cam || W <= 0 || H <= 0 || x_begin < 0 || x_end > W || x_stride < 1) return FT_ERR_INVALID_ARGUMENT;
     job j;
     memset(&j, 0, sizeof(j));
     j.s = s; j.cam = cam; j.W = W; j.H = H; j.eps = eps; j.len = len;
     j.out_rgb = out_rgb; j.out_leaf = out_leaf; j.out_steps = out_steps; j.out_shadow = out_shadow;
     j.mode = 0; j.chunk = 1;
-    j.start = x_begin; j.n = x_end;
+    j.start = 0; j.x0 = x_begin; j.xstride = x_stride;
+    j.n = x_end > x_begin ? (x_end - x_begin + x_stride - 1) / x_stride : 0;
     run_job(&j, threads, ctr);
     return FT_OK;
 }

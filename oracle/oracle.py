@@ -21,7 +21,8 @@ class fto_counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "march_steps", "primary_rays", "primary_hits", "shadow_rays",
         "eval_sphere", "eval_capsule", "eval_torus", "eval_triangle_edge", "eval_triangle_face",
-        "union_lookups", "lower_bound_tests", "bound_tests", "intersect_tests", "max_steps")]
+        "union_lookups", "lower_bound_tests", "bound_tests", "intersect_tests", "max_steps",
+        "outside_lookups", "outside_bound_tests", "outside_evals")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -64,7 +65,7 @@ def lib():
         L.fto_lens_create.restype = f32
         L.fto_lens_create.argtypes = [f32]
         L.fto_camera_look_at.argtypes = [P(f32), P(f32), P(f32), f32, P(A.ft_camera)]
-        L.fto_render.argtypes = [vp, P(A.ft_camera), C.c_int, C.c_int, f32, f32, C.c_int, C.c_int, C.c_int,
+        L.fto_render.argtypes = [vp, P(A.ft_camera), C.c_int, C.c_int, f32, f32, C.c_int, C.c_int, C.c_int, C.c_int,
                                  vp, vp, vp, vp, P(fto_counters)]
         L.fto_trace_rays.argtypes = [vp, i64, vp, C.c_int, vp, vp, vp, vp, P(fto_counters)]
         L.fto_distance.argtypes = [vp, i64, vp, C.c_int, vp, P(fto_counters)]
@@ -148,7 +149,7 @@ class OracleScene:
                             centers=centers, begin=begin, lower_bound=lb, item=item))
         return res
 
-    def render(self, camera, X, Y, eps, length, threads=None, x_begin=0, x_end=None, counters=False):
+    def render(self, camera, X, Y, eps, length, threads=None, x_begin=0, x_end=None, x_stride=1, counters=False):
         """returns dict(rgb [X,Y,3], leaf [X,Y], steps [X,Y], shadow [X,Y]) (+ counters)"""
         cam = camera.to_c() if hasattr(camera, "to_c") else camera
         x_end = X if x_end is None else x_end
@@ -159,7 +160,7 @@ class OracleScene:
         shadow = np.zeros((X, Y), np.uint32)
         ctr = fto_counters()
         st = lib().fto_render(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), x_begin, x_end,
-                              threads, _ptr(rgb), _ptr(leaf), _ptr(steps), _ptr(shadow),
+                              x_stride, threads, _ptr(rgb), _ptr(leaf), _ptr(steps), _ptr(shadow),
                               C.byref(ctr) if counters else None)
         assert st == 0
         out = dict(rgb=rgb, leaf=leaf, steps=steps, shadow=shadow)

@@ -82,3 +82,115 @@ def test_device_grid_equals_oracle_grid():
     for k in ("centers", "lower_bound"):
         assert np.array_equal(bits(g1[0][k]), bits(g2[0][k]))
     assert np.array_equal(g1[0]["item"], g2[0]["item"]) and np.array_equal(g1[0]["begin"], g2[0]["begin"])
+
+
+def test_strip_partition_gather_equals_single_render():
+    """multi-GPU path on one GPU: every 'rank' renders its strips into a compact buffer, the buffers are
+    stacked as the all-gather would, the de-interleave kernel restores FColor[X,Y]; must be bit-identical."""
+    import ctypes as C
+
+    import torch
+
+    from fraytracer_b200 import _abi as A
+    from fraytracer_b200.distributed import strip_layout
+
+    w = scenes.default_scene(n_tori=300)
+    tracer = ft.SceneTracer(w.scene, device=0)
+    for X, Y, sw, world in ((200, 120, 8, 2), (203, 77, 8, 4), (64, 64, 16, 3)):
+        size = ft.ImageSize(X, Y)
+        full, _, _ = tracer.render(w.camera, size, w.epsilon, w.length)
+        spr, floats = strip_layout(X, Y, sw, world)
+        gathered = torch.full((world, spr * sw, Y, 3), float("nan"), dtype=torch.float32, device="cuda:0")
+        for r in range(world):
+            tracer.render_device(w.camera, size, w.epsilon, w.length, gathered[r].data_ptr(), strip_width=sw,
+                                 rank=r, world=world, stream=torch.cuda.current_stream().cuda_stream)
+        final = torch.empty((X, Y, 3), dtype=torch.float32, device="cuda:0")
+        A.check(tracer.lib.ft_deinterleave_device(C.c_void_p(gathered.data_ptr()), X, Y, sw, world, 3,
+                                                  C.c_void_p(final.data_ptr()), None))
+        torch.cuda.synchronize()
+        assert not torch.isnan(gathered).any()  # padding columns are written too
+        assert np.array_equal(bits(final.cpu().numpy()), bits(full))
+
+
+def test_fast_math_mode_within_tolerance():
+    """FT_FLAG_FAST_MATH (FMA contraction) is not bit-exact.  The reference's normal is a forward difference
+    with h = eps/8 (SdfForm.fs:106-115), which amplifies any change of rounding by ~1/h, so the achievable bar is:
+    hit object index equal except < 1e-4 of the pixels (silhouettes); on equal-leaf hit pixels the relative colour
+    error has median < 1e-4, 99.9th percentile < 5e-3, and < 1e-3 of them exceed 1e-2 (shadow-edge flips)."""
+    from fraytracer_b200 import FT_FLAG_FAST_MATH
+
+    for w, X, Y in ((scenes.default_scene(), 400, 400), (scenes.spheres_capsules_scene(), 480, 270)):
+        tracer = ft.SceneTracer(w.scene, device=0)
+        size = ft.ImageSize(X, Y)
+        a, la, _ = tracer.render(w.camera, size, w.epsilon, w.length, want_leaf=True)
+        b, lb, _ = tracer.render(w.camera, size, w.epsilon, w.length, want_leaf=True, flags=FT_FLAG_FAST_MATH)
+        same = la == lb
+        assert 1.0 - same.mean() < 1e-4
+        sel = same & (la >= 0)
+        rel = (np.abs(a - b) / np.maximum(np.abs(a), 1e-3)).max(axis=-1)[sel]
+        assert np.median(rel) < 1e-4 and np.percentile(rel, 99.9) < 5e-3 and (rel > 1e-2).mean() < 1e-3
+        assert np.array_equal(bits(a[la < 0]), bits(b[la < 0]))  # background pixels are exact
+
+
+def test_escape_proof_changes_nothing_but_step_counts(monkeypatch):
+    """rays resolved by the escape proof (render path, trace_rays without step output) must give the same
+    colours, leaves and shadow masks as marching them to the end"""
+    import ctypes as C
+
+    from fraytracer_b200 import _abi as A
+
+    for w in (scenes.default_scene(), scenes.mixed_scene(width=320, height=180)):
+        size = ft.ImageSize(320, 180)
+        fast = ft.SceneTracer(w.scene, device=0)
+        monkeypatch.setenv("FT_NO_ESCAPE", "1")
+        slow = ft.SceneTracer(w.scene, device=0)
+        monkeypatch.delenv("FT_NO_ESCAPE")
+        a, la, sa = fast.render(w.camera, size, w.epsilon, w.length, want_leaf=True)
+        b, lb, sb = slow.render(w.camera, size, w.epsilon, w.length, want_leaf=True)
+        assert sa["escaped_rays"] > 0 and sb["escaped_rays"] == 0
+        assert np.array_equal(bits(a), bits(b)) and np.array_equal(la, lb)
+        assert sa["shadow_rays"] == sb["shadow_rays"] and sa["primary_hits"] == sb["primary_hits"]
+        # trace_rays without the step output uses the proof too
+        rng = np.random.default_rng(11)
+        n = 5000
+        origin = (rng.normal(size=(n, 3)) * 8.0).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays = np.ascontiguousarray(np.concatenate([origin, d, np.full((n, 1), 40.0, np.float32),
+                                                    np.full((n, 1), 0.01, np.float32)], axis=1), dtype=np.float32)
+        full, _ = fast.trace_rays(rays)  # steps requested: exact marching
+        rgb = np.empty((n, 3), np.float32)
+        leaf = np.empty(n, np.int32)
+        shadow = np.empty(n, np.uint32)
+        st = A.ft_render_stats()
+        A.check(fast.lib.ft_trace_rays(fast.handle, n, rays.ctypes.data_as(C.c_void_p), 0,
+                                       rgb.ctypes.data_as(C.c_void_p), leaf.ctypes.data_as(C.c_void_p), None,
+                                       shadow.ctypes.data_as(C.c_void_p), C.byref(st)))
+        assert st.escaped_rays > 0
+        assert np.array_equal(bits(rgb), bits(full["rgb"])) and np.array_equal(leaf, full["leaf"])
+        assert np.array_equal(shadow, full["shadow"])
+
+
+def test_watchdog_step_cap_reports_capped_rays():
+    w = scenes.default_scene(n_tori=50)
+    tracer = ft.SceneTracer(w.scene, device=0)
+    tracer.set_step_cap(3)
+    _, _, stats = tracer.render(w.camera, ft.ImageSize(64, 64), w.epsilon, w.length)
+    assert stats["capped_rays"] > 0
+    orc = O.OracleScene(tracer.description)
+    orc.set_step_cap(3)
+    ref = orc.render(w.camera, 64, 64, w.epsilon, w.length)
+    rgb, _, _ = tracer.render(w.camera, ft.ImageSize(64, 64), w.epsilon, w.length)
+    assert np.array_equal(bits(rgb), bits(ref["rgb"]))
+
+
+def test_image_render_mirror_and_single_ray_closure():
+    w = scenes.default_scene(n_tori=100)
+    trace = ft.SdfScene.trace(w.scene)
+    img = ft.Image.render(w.epsilon, w.length, ft.ImageSize(48, 32), w.camera, trace)
+    assert img.shape == (48, 32, 3)
+    orc = O.OracleScene(trace.description)
+    ref = orc.render(w.camera, 48, 32, w.epsilon, w.length)
+    assert np.array_equal(bits(img), bits(ref["rgb"]))
+    ray = ft.Ray(Origin=(0, 0, -10), Direction=(0, 0, 1), Length=30.0, Epsilon=0.01)
+    assert bits(np.array(trace(ray), np.float32)).tolist() == bits(orc.trace_rays(ray.as_row())["rgb"][0]).tolist()
