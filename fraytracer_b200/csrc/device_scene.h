@@ -81,4 +81,17 @@ struct DevScene {
     // disables the shortcut (smooth unions with non-positive strength, non-finite boundaries, ...).
     float esc_lo[3], esc_hi[3];
     int32_t esc_valid;
+    // Chain program: when scene.Object.Form is  op_k(... op_1(U) ...)  with U a spatial-lookup union whose
+    // children are all primitives and every op an SdfForm.intersect / SdfForm.subtract whose other operands
+    // are primitives (the shape of the reference's own scenes, Program.fs:69-78), the form is evaluated by a
+    // specialised linear evaluator instead of the generic interpreter.  links[chain_ops + 2k] = opcode
+    // (FT_OP_*), links[chain_ops + 2k + 1] = primitive word, in evaluation order.
+    int32_t chain_valid;
+    uint32_t chain_union;  // node offset of U
+    int32_t chain_n_ops;
+    uint32_t chain_ops;
+};
+enum : uint32_t {
+    FT_OP_INTERSECT = 1,  // if v < dist(C,p)+R then v = Max(v, D(p))      SdfForm.fs:62-63
+    FT_OP_SUBTRACT = 2,   // v = Max(-D(p), v)                             SdfForm.fs:45-47
 };

@@ -271,6 +271,11 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
         s->dev.esc_hi[k] = h.esc_hi[k];
     }
     s->dev.esc_valid = h.esc_valid;
+    s->dev.chain_valid = h.chain_valid;
+    s->dev.chain_union = h.chain_union;
+    s->dev.chain_n_ops = h.chain_n_ops;
+    s->dev.chain_ops = h.chain_ops;
+    if (getenv("FT_NO_CHAIN")) s->dev.chain_valid = 0;  // experiments / tests of the generic interpreter
     if (getenv("FT_NO_ESCAPE")) s->dev.esc_valid = 0;  // experiments only
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");

@@ -32,6 +32,12 @@ static cudaError_t persistent_grid(K kernel, long long items, int sm_count, unsi
     return cudaSuccess;
 }
 
+#define FT_LAUNCH(C, E, H, JOB, ITEMS)                                                                               \
+    do {                                                                                                              \
+        if ((e = persistent_grid(machine_kernel<C, E, H, JOB>, ITEMS, sm_count, &grid)) != cudaSuccess) return e;     \
+        machine_kernel<C, E, H, JOB><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);                           \
+    } while (0)
+
 cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb, int *out_leaf,
                           unsigned long long *work_counter, unsigned long long *stats, bool count, int sm_count,
                           cudaStream_t stream) {
@@ -44,13 +50,11 @@ cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderP
     if (job.n_items <= 0) return cudaSuccess;
     unsigned grid = 1;
     cudaError_t e;
-    if (count) {
-        if ((e = persistent_grid(machine_kernel<true, true, RenderJob>, job.n_items, sm_count, &grid)) != cudaSuccess) return e;
-        machine_kernel<true, true, RenderJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);
-    } else {
-        if ((e = persistent_grid(machine_kernel<false, true, RenderJob>, job.n_items, sm_count, &grid)) != cudaSuccess) return e;
-        machine_kernel<false, true, RenderJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);
-    }
+    const bool chain = S.chain_valid != 0;
+    if (count && chain) FT_LAUNCH(true, true, true, RenderJob, job.n_items);
+    else if (count) FT_LAUNCH(true, true, false, RenderJob, job.n_items);
+    else if (chain) FT_LAUNCH(false, true, true, RenderJob, job.n_items);
+    else FT_LAUNCH(false, true, false, RenderJob, job.n_items);
     return cudaGetLastError();
 }
 
@@ -62,19 +66,20 @@ cudaError_t launch_trace_rays(const DevScene &S, const float4 *rays, long long n
     unsigned grid = 1;
     cudaError_t e;
     // per-ray step counts requested: every march is followed to its end (no escape proof)
-    const bool escape = out_steps == nullptr;
-#define FT_LAUNCH_RAYS(C, E)                                                                                          \
-    do {                                                                                                              \
-        if ((e = persistent_grid(machine_kernel<C, E, RaysJob>, n, sm_count, &grid)) != cudaSuccess) return e;        \
-        machine_kernel<C, E, RaysJob><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);                          \
-    } while (0)
-    if (count && escape) FT_LAUNCH_RAYS(true, true);
-    else if (count) FT_LAUNCH_RAYS(true, false);
-    else if (escape) FT_LAUNCH_RAYS(false, true);
-    else FT_LAUNCH_RAYS(false, false);
-#undef FT_LAUNCH_RAYS
+    const bool escape = out_steps == nullptr, chain = S.chain_valid != 0;
+    if (count) {  // the instrumented variant is not performance critical: generic interpreter only
+        if (escape) FT_LAUNCH(true, true, false, RaysJob, n);
+        else FT_LAUNCH(true, false, false, RaysJob, n);
+    } else if (escape) {
+        if (chain) FT_LAUNCH(false, true, true, RaysJob, n);
+        else FT_LAUNCH(false, true, false, RaysJob, n);
+    } else {
+        if (chain) FT_LAUNCH(false, false, true, RaysJob, n);
+        else FT_LAUNCH(false, false, false, RaysJob, n);
+    }
     return cudaGetLastError();
 }
+#undef FT_LAUNCH
 
 cudaError_t launch_distance(const DevScene &S, const float *pts, long long n, float *out, cudaStream_t stream) {
     const long long blocks = (n + BLOCK - 1) / BLOCK;

@@ -697,6 +697,39 @@ class Compiler {
                 }
             }
         }
+        // 3b. chain program of the root form (device_scene.h)
+        {
+            std::vector<std::pair<uint32_t, uint32_t>> ops;  // collected from the root downwards
+            int node = objs_[(size_t)obj_node_[(size_t)d_->root_object]].form;
+            bool ok = true;
+            auto is_prim = [&](int k) { return nodes_[(size_t)k].kind < FT_FORM_UNION; };
+            while (ok && (nodes_[(size_t)node].kind == FT_FORM_SUBTRACT || nodes_[(size_t)node].kind == FT_FORM_INTERSECT)) {
+                const FormNode &n = nodes_[(size_t)node];
+                if (n.kind == FT_FORM_SUBTRACT) {
+                    if (!is_prim(n.kids[1])) { ok = false; break; }
+                    ops.emplace_back(FT_OP_SUBTRACT, nodes_[(size_t)n.kids[1]].word);
+                } else {
+                    for (size_t k = n.kids.size(); k-- > 1;) {  // reversed here, restored below
+                        if (!is_prim(n.kids[k])) { ok = false; break; }
+                        ops.emplace_back(FT_OP_INTERSECT, nodes_[(size_t)n.kids[k]].word);
+                    }
+                }
+                node = n.kids[0];
+            }
+            if (ok && nodes_[(size_t)node].kind == FT_FORM_UNION) {
+                for (int k : nodes_[(size_t)node].kids) ok = ok && is_prim(k);
+                if (ok) {
+                    o.chain_valid = 1;
+                    o.chain_union = FT_WORD_OFF(nodes_[(size_t)node].word);
+                    o.chain_n_ops = (int32_t)ops.size();
+                    o.chain_ops = (uint32_t)o.links.size();
+                    for (size_t k = ops.size(); k-- > 0;) {  // innermost operation first
+                        o.links.push_back(ops[k].first);
+                        o.links.push_back(ops[k].second);
+                    }
+                }
+            }
+        }
         if (o.links.empty()) o.links.push_back(0);
         // 4. objects
         for (const ObjNode &ob : objs_) {

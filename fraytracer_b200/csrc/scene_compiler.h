@@ -43,6 +43,8 @@ struct CompiledScene {
     float pg_lo[3] = {0, 0, 0}, pg_hi[3] = {0, 0, 0};  // box of the largest grid (scheduling hint)
     float esc_lo[3] = {0, 0, 0}, esc_hi[3] = {0, 0, 0};  // escape box (device_scene.h)
     int32_t esc_valid = 0;
+    int32_t chain_valid = 0, chain_n_ops = 0;
+    uint32_t chain_union = 0, chain_ops = 0;
     int32_t n_nodes = 0, n_primitives = 0, max_depth = 0;
 };
 

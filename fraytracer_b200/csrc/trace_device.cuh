@@ -30,6 +30,10 @@ constexpr int FLOPS_POINT_LIGHT = 24; // normalize(pos-p) 12, diff 3, len2 5, sq
 constexpr int FLOPS_FINAL = 6;
 constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 
+#ifndef FT_INLINE_PRIM
+#define FT_INLINE_PRIM 0  // 1: primitives met by the candidate scan are evaluated inside the scan loop
+#endif
+
 struct Acc {
     unsigned long long flops;
     unsigned long long steps;
@@ -145,35 +149,42 @@ __device__ __forceinline__ bool bound_test(float m, float4 b0, V3 p, float &bd) 
 
 // ---- union candidate scan (SdfForm.fs:27-33) from entry i with running minimum m.
 // Returns true when the list is exhausted (early exit on the sorted LowerBound, see device_scene.h);
-// false when entry i is a composite child that must be evaluated by the caller.
-// The next record is fetched before the current one is tested (the list is closed by a sentinel and the
-// array by two padding records, so the speculative load is always in bounds).
+// false when entry i is a child whose Distance must be evaluated by the caller (anything but a sphere:
+// a sphere's Distance is the bound test's own value).  Started at the cell's first entry with m = +inf it
+// also performs the reference's unconditional first evaluation (SdfForm.fs:26): +inf passes both tests.
+// Two records are in flight (ping-pong, no register rotation); the list is closed by a sentinel and the
+// array by two padding records, so the speculative loads stay in bounds.
 template <bool COUNT>
 __device__ __forceinline__ bool union_scan(const DevScene &S, V3 p, float dtc, uint32_t &i, float &m, uint32_t &child, Acc &acc) {
-    Entry e = ld_entry(S, i);
+#define FT_SCAN_ONE(E)                                                                    \
+    {                                                                                     \
+        add_flops<COUNT>(acc, FLOPS_LB_TEST);                                             \
+        if (!(m > (E).lb() - dtc)) return true;                                           \
+        float bd;                                                                         \
+        add_flops<COUNT>(acc, FLOPS_BOUND_TEST);                                          \
+        if (bound_test(m, (E).bound(), p, bd)) { /* m > getMinDistance boundary p */      \
+            if (FT_WORD_KIND((E).word()) == FT_K_SPHERE) {                                \
+                m = bd; /* Min(m, Distance) with Distance == bd < m */                    \
+                add_flops<COUNT>(acc, FLOPS_MINMAX);                                      \
+            } else if (FT_INLINE_PRIM && FT_IS_PRIMITIVE((E).word())) {                   \
+                m = fminf(m, prim_distance<COUNT>(S, (E).word(), (E).bound(), p, acc));   \
+                add_flops<COUNT>(acc, FLOPS_MINMAX);                                      \
+            } else {                                                                      \
+                child = (E).word();                                                       \
+                return false;                                                             \
+            }                                                                             \
+        }                                                                                 \
+    }
+    Entry e0 = ld_entry(S, i);
     for (;;) {
-        const Entry nx = ld_entry(S, i + 1);
-        add_flops<COUNT>(acc, FLOPS_LB_TEST);
-        if (!(m > e.lb() - dtc)) return true;
-        const float4 b0 = e.bound();
-        float bd;
-        add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
-        if (bound_test(m, b0, p, bd)) {  // m > SdfBoundary.getMinDistance boundary position
-            const uint32_t w = e.word();
-            if (FT_WORD_KIND(w) == FT_K_SPHERE) {
-                m = bd;  // the sphere's Distance is the same expression: Min(m, bd) = bd here
-                add_flops<COUNT>(acc, FLOPS_MINMAX);
-            } else if (FT_IS_PRIMITIVE(w)) {
-                m = fminf(m, prim_distance<COUNT>(S, w, b0, p, acc));
-                add_flops<COUNT>(acc, FLOPS_MINMAX);
-            } else {
-                child = w;
-                return false;
-            }
-        }
-        e = nx;
+        const Entry e1 = ld_entry(S, i + 1);
+        FT_SCAN_ONE(e0)
+        i++;
+        e0 = ld_entry(S, i + 1);
+        FT_SCAN_ONE(e1)
         i++;
     }
+#undef FT_SCAN_ONE
 }
 
 struct Frame {
@@ -183,94 +194,83 @@ struct Frame {
     float aux;
 };
 
-// ---- Form.Distance position for an arbitrary compiled form (the closure of Types.fs:42)
+// ---- Form.Distance position for an arbitrary compiled form (the closure of Types.fs:42).
+// A resumable evaluate/feed loop: "evaluate" turns `cur` into a value (the ONE primitive site) or opens a
+// composite frame; "feed" hands the value to the innermost open composite, which either asks for its next
+// child or closes.  Lanes of a warp therefore meet at the primitive site for their k-th child evaluation
+// instead of evaluating primitives at different iterations of their private scan loops.  The innermost
+// frame lives in registers; only deeper nesting touches the local-memory stack.
 template <bool COUNT>
 __device__ __forceinline__ float eval_form(const DevScene &S, uint32_t root, V3 p, Acc &acc) {
-    if (FT_IS_PRIMITIVE(root)) return prim_distance<COUNT>(S, root, ld4(S.nodes + FT_WORD_OFF(root)), p, acc);
     Frame stack[FT_MAX_DEPTH];
-    int sp = 0;
+    Frame top{0u, 0u, 0.f, 0.f};
+    int depth = 0;  // open composite frames; frames 0..depth-2 are in stack[], frame depth-1 is `top`
     uint32_t cur = root;
     float val = 0.f;
+    bool have_val = false;
     for (;;) {
-        // ------------------------------------------------ descend: evaluate `cur`
-        bool have_val = false;
-        while (!have_val) {
+        if (!have_val) {
             const uint32_t kind = FT_WORD_KIND(cur), off = FT_WORD_OFF(cur);
             if (kind < 8u) {
                 val = prim_distance<COUNT>(S, cur, ld4(S.nodes + off), p, acc);
                 have_val = true;
-            } else if (kind == FT_K_UNION) {  // SdfForm.fs:22-34
-                uint32_t i;
-                float dtc;
-                grid_cell<COUNT>(S, off, p, i, dtc, acc);
-                const Entry e0 = ld_entry(S, i);
-                const uint32_t first = e0.word();
-                if (FT_IS_PRIMITIVE(first)) {
-                    float m = prim_distance<COUNT>(S, first, e0.bound(), p, acc);  // :26
-                    i++;
-                    uint32_t child;
-                    if (union_scan<COUNT>(S, p, dtc, i, m, child, acc)) {
-                        val = m;
-                        have_val = true;
-                    } else {
-                        stack[sp++] = Frame{cur, i, m, dtc};
-                        cur = child;
-                    }
-                } else {
-                    stack[sp++] = Frame{cur, i, __int_as_float(0x7f800000), dtc};
-                    cur = first;
+            } else {
+                if (depth > 0) stack[depth - 1] = top;
+                depth++;
+                const float4 h = ld4(S.nodes + off + 1);
+                if (kind == FT_K_UNION) {  // SdfForm.fs:22-34
+                    uint32_t begin;
+                    float dtc;
+                    grid_cell<COUNT>(S, off, p, begin, dtc, acc);
+                    top = Frame{cur, begin - 1u, __int_as_float(0x7f800000), dtc};
+                    val = __int_as_float(0x7f800000);  // feed(+inf): the scan starts at the first entry
+                    have_val = true;
+                } else if (kind == FT_K_SUBTRACT) {  // SdfForm.fs:45-47
+                    top = Frame{cur, 0u, 0.f, 0.f};
+                    cur = __float_as_uint(h.x);
+                } else if (kind == FT_K_INTERSECT) {  // SdfForm.fs:58-64
+                    top = Frame{cur, 0u, 0.f, 0.f};
+                    cur = __ldg(S.links + __float_as_uint(h.y));
+                } else {  // FT_K_SMOOTH  SdfForm.fs:75-82
+                    top = Frame{cur, 0u, 0.f, 0.f};
+                    cur = __ldg(S.links + __float_as_uint(h.w));
                 }
-            } else if (kind == FT_K_SUBTRACT) {  // SdfForm.fs:45-47
-                const float4 h = ld4(S.nodes + off + 1);
-                stack[sp++] = Frame{cur, 0u, 0.f, 0.f};
-                cur = __float_as_uint(h.x);
-            } else if (kind == FT_K_INTERSECT) {  // SdfForm.fs:58-64
-                const float4 h = ld4(S.nodes + off + 1);
-                stack[sp++] = Frame{cur, 0u, 0.f, 0.f};
-                cur = __ldg(S.links + __float_as_uint(h.y));
-            } else {  // FT_K_SMOOTH  SdfForm.fs:75-82
-                const float4 h = ld4(S.nodes + off + 1);
-                stack[sp++] = Frame{cur, 0u, 0.f, 0.f};
-                cur = __ldg(S.links + __float_as_uint(h.w));
             }
-        }
-        // ------------------------------------------------ ascend: feed `val` to the enclosing composites
-        bool descend = false;
-        while (!descend) {
-            if (sp == 0) return val;
-            Frame &f = stack[sp - 1];
-            const uint32_t kind = FT_WORD_KIND(f.word), off = FT_WORD_OFF(f.word);
+        } else {
+            if (depth == 0) return val;
+            const uint32_t kind = FT_WORD_KIND(top.word), off = FT_WORD_OFF(top.word);
+            bool closed = false;
             if (kind == FT_K_UNION) {
-                float m = fminf(f.acc, val);  // :33  (first child: acc = +inf)
+                float m = fminf(top.acc, val);  // SdfForm.fs:33
                 add_flops<COUNT>(acc, FLOPS_MINMAX);
-                uint32_t i = f.idx + 1, child;
-                if (union_scan<COUNT>(S, p, f.aux, i, m, child, acc)) {
+                uint32_t i = top.idx + 1u, child;
+                if (union_scan<COUNT>(S, p, top.aux, i, m, child, acc)) {
                     val = m;
-                    sp--;
+                    closed = true;
                 } else {
-                    f.idx = i;
-                    f.acc = m;
+                    top.idx = i;
+                    top.acc = m;
                     cur = child;
-                    descend = true;
+                    have_val = false;
                 }
             } else if (kind == FT_K_SUBTRACT) {
                 const float4 h = ld4(S.nodes + off + 1);
-                if (f.idx == 0u) {
-                    f.idx = 1u;
-                    f.acc = val;  // a.Distance position
+                if (top.idx == 0u) {
+                    top.idx = 1u;
+                    top.acc = val;  // a.Distance position
                     cur = __float_as_uint(h.y);
-                    descend = true;
+                    have_val = false;
                 } else {
-                    val = fmaxf(-val, f.acc);  // MathF.Max(-(b p), a p)
+                    val = fmaxf(-val, top.acc);  // MathF.Max(-(b p), a p)
                     add_flops<COUNT>(acc, 2);
-                    sp--;
+                    closed = true;
                 }
             } else if (kind == FT_K_INTERSECT) {
                 const float4 h = ld4(S.nodes + off + 1);
                 const uint32_t n = __float_as_uint(h.x), base = __float_as_uint(h.y);
-                float mx = (f.idx == 0u) ? val : fmaxf(f.acc, val);  // :59 / :63
-                uint32_t i = f.idx + 1;
-                bool done = true;
+                float mx = (top.idx == 0u) ? val : fmaxf(top.acc, val);  // :59 / :63
+                uint32_t i = top.idx + 1u;
+                closed = true;
                 for (; i < n; i++) {
                     const uint32_t child = __ldg(S.links + base + i);
                     const float4 b0 = ld4(S.nodes + FT_WORD_OFF(child));
@@ -280,43 +280,102 @@ __device__ __forceinline__ float eval_form(const DevScene &S, uint32_t root, V3 
                         if (FT_WORD_KIND(child) == FT_K_SPHERE) {
                             mx = fmaxf(mx, dc - b0.w);
                             add_flops<COUNT>(acc, 2);
-                        } else if (FT_IS_PRIMITIVE(child)) {
-                            mx = fmaxf(mx, prim_distance<COUNT>(S, child, b0, p, acc));
-                            add_flops<COUNT>(acc, FLOPS_MINMAX);
                         } else {
-                            f.idx = i;
-                            f.acc = mx;
+                            top.idx = i;
+                            top.acc = mx;
                             cur = child;
-                            done = false;
+                            have_val = false;
+                            closed = false;
                             break;
                         }
                     }
                 }
-                if (done) {
-                    val = mx;
-                    sp--;
-                } else {
-                    descend = true;
-                }
+                if (closed) val = mx;
             } else {  // smooth
                 const float4 h = ld4(S.nodes + off + 1);
                 const uint32_t n = __float_as_uint(h.z), base = __float_as_uint(h.w);
-                const float sum = f.acc + expf(h.y * val);  // :80
+                const float sum = top.acc + expf(h.y * val);  // :80
                 add_flops<COUNT>(acc, FLOPS_SMOOTH_TERM);
-                const uint32_t i = f.idx + 1;
+                const uint32_t i = top.idx + 1u;
                 if (i < n) {
-                    f.idx = i;
-                    f.acc = sum;
+                    top.idx = i;
+                    top.acc = sum;
                     cur = __ldg(S.links + base + i);
-                    descend = true;
+                    have_val = false;
                 } else {
                     val = -logf(sum) * h.x;  // :82
                     add_flops<COUNT>(acc, 3);
-                    sp--;
+                    closed = true;
                 }
+            }
+            if (closed) {
+                depth--;
+                if (depth > 0) top = stack[depth - 1];
             }
         }
     }
+}
+
+// ---- specialised evaluator for chain-shaped root forms (device_scene.h "Chain program"):
+//   v = U(p)  (SdfForm.fs:22-34),  then  v = op_k(v)  for the intersect / subtract operations above U.
+// Bit-identical to eval_form on such scenes; it only drops the interpreter's dispatch.  The candidate loop is
+// "scan until a child must be evaluated, converge, evaluate": lanes share the primitive-evaluation code.
+template <bool COUNT>
+__device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
+    uint32_t i;
+    float dtc;
+    grid_cell<COUNT>(S, S.chain_union, p, i, dtc, acc);
+    float m = __int_as_float(0x7f800000);  // +inf passes both tests: the first entry is evaluated unconditionally (:26)
+    for (;;) {
+        uint32_t w = 0u;
+        float4 b0{0.f, 0.f, 0.f, 0.f};
+        bool need = false;
+        Entry e0 = ld_entry(S, i);
+        for (;;) {  // scan (SdfForm.fs:27-33); spheres are resolved in place, their Distance is the bound test's value
+            const Entry e1 = ld_entry(S, i + 1);
+            add_flops<COUNT>(acc, FLOPS_LB_TEST);
+            if (!(m > e0.lb() - dtc)) break;
+            float bd;
+            add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
+            if (bound_test(m, e0.bound(), p, bd)) {
+                if (FT_WORD_KIND(e0.word()) == FT_K_SPHERE) {
+                    m = bd;
+                    add_flops<COUNT>(acc, FLOPS_MINMAX);
+                } else {
+                    need = true;
+                    w = e0.word();
+                    b0 = e0.bound();
+                    break;
+                }
+            }
+            e0 = e1;
+            i++;
+        }
+        if (!need) break;
+        m = fminf(m, prim_distance<COUNT>(S, w, b0, p, acc));  // SdfForm.fs:33
+        add_flops<COUNT>(acc, FLOPS_MINMAX);
+        i++;
+    }
+    float v = m;
+    for (int k = 0; k < S.chain_n_ops; k++) {
+        const uint32_t op = __ldg(S.links + S.chain_ops + 2 * k), w = __ldg(S.links + S.chain_ops + 2 * k + 1);
+        const float4 b0 = ld4(S.nodes + FT_WORD_OFF(w));
+        if (op == FT_OP_INTERSECT) {
+            const float dc = distance(xyz(b0), p);
+            add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
+            if (v < dc + b0.w) {  // SdfForm.fs:62
+                const float dd = (FT_WORD_KIND(w) == FT_K_SPHERE) ? dc - b0.w : prim_distance<COUNT>(S, w, b0, p, acc);
+                v = fmaxf(v, dd);
+                add_flops<COUNT>(acc, 2);
+            }
+        } else {
+            const float dd = (FT_WORD_KIND(w) == FT_K_SPHERE) ? distance(xyz(b0), p) - b0.w
+                                                              : prim_distance<COUNT>(S, w, b0, p, acc);
+            v = fmaxf(-dd, v);  // SdfForm.fs:45-47
+            add_flops<COUNT>(acc, 2);
+        }
+    }
+    return v;
 }
 
 // out-of-line copy for the rare callers (composite children inside the material arg-min)
@@ -342,8 +401,7 @@ __device__ int material_leaf(const DevScene &S, V3 p, Acc &acc) {
         uint32_t best = begin;
         const Entry e0 = ld_entry(S, begin);
         const uint32_t w0 = e0.word();
-        float m = FT_IS_PRIMITIVE(w0) ? prim_distance<COUNT>(S, w0, e0.bound(), p, acc)
-                                      : eval_form_call<COUNT>(S, w0, p, acc);  // :30
+        float m = eval_form_call<COUNT>(S, w0, p, acc);  // :30
         // the reference's loop starts again at item 0 (:34); re-testing it cannot change min or material
         for (uint32_t i = begin + 1;; i++) {
             const Entry e = ld_entry(S, i);
@@ -354,9 +412,7 @@ __device__ int material_leaf(const DevScene &S, V3 p, Acc &acc) {
             float bd;
             add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
             if (bound_test(m, b0, p, bd)) {
-                const float dd = (FT_WORD_KIND(w) == FT_K_SPHERE) ? bd
-                                 : FT_IS_PRIMITIVE(w)              ? prim_distance<COUNT>(S, w, b0, p, acc)
-                                                                   : eval_form_call<COUNT>(S, w, p, acc);
+                const float dd = (FT_WORD_KIND(w) == FT_K_SPHERE) ? bd : eval_form_call<COUNT>(S, w, p, acc);
                 if (dd < m) {  // :41-43
                     m = dd;
                     best = i;

@@ -128,7 +128,8 @@ struct RaysJob {
 
 // ESCAPE: resolve rays by the escape proof (identical colours / leaf / shadow mask; the step counters then
 // count only the evaluations actually performed, so it is off when per-ray step counts are requested).
-template <bool COUNT, bool ESCAPE, class Job>
+// CHAIN: the root form is a chain program (eval_chain) instead of a generic tree (eval_form).
+template <bool COUNT, bool ESCAPE, bool CHAIN, class Job>
 __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_constant__ DevScene S, const __grid_constant__ Job job,
                                                      unsigned long long *__restrict__ work_counter,
                                                      unsigned long long *__restrict__ stats) {
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         const unsigned m_long = __ballot_sync(FULL, wants && is_long), m_short = __ballot_sync(FULL, wants && !is_long);
         const bool run_long = m_short == 0u || __popc(m_long) >= FT_LONG_BATCH;
         if (wants && is_long == run_long) {
-            const float dist = eval_form<COUNT>(S, S.root_word, p, acc);
+            const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc) : eval_form<COUNT>(S, S.root_word, p, acc);
             if (phase <= PH_SHADOW) {  // SdfForm.fs:97-104
                 steps++;
                 if (COUNT) acc.steps++;

@@ -194,3 +194,64 @@ def test_image_render_mirror_and_single_ray_closure():
     assert np.array_equal(bits(img), bits(ref["rgb"]))
     ray = ft.Ray(Origin=(0, 0, -10), Direction=(0, 0, 1), Length=30.0, Epsilon=0.01)
     assert bits(np.array(trace(ray), np.float32)).tolist() == bits(orc.trace_rays(ray.as_row())["rgb"][0]).tolist()
+
+
+def _nested_scene():
+    from fraytracer_b200 import SdfForm, SdfObject, SdfScene
+
+    P = SdfForm.Primitive
+    b = scenes.SceneBuilder(seed=36)
+    inner1 = SdfObject.union([b.randomSphere() for _ in range(7)])
+    inner2 = SdfObject.union([b.randomCapsule() for _ in range(9)] + [b.randomTriangle() for _ in range(5)])
+    outer = SdfObject.union([inner1, inner2, b.randomTorus(), b.randomTorus()])
+    carved = SdfObject.subtract(SdfObject.intersect(outer, [P.sphere(Center=(0, 0, 0), Radius=3.0)]),
+                                SdfForm.union([P.sphere(Center=(1, 1, 1), Radius=1.0), P.sphere(Center=(-1, 1, 0), Radius=0.7)]))
+    return SdfScene(Object=carved, BackgroundColor=(0.05, 0.1, 0.2), Lights=scenes.default_lights())
+
+
+def test_generic_interpreter_nested_composites_bit_exact():
+    """nested unions, a union as the subtracted operand: not a chain program, runs the generic interpreter"""
+    scene = _nested_scene()
+    cam = scenes.default_camera()
+    tracer = ft.SceneTracer(scene, device=0)
+    assert tracer.info()["n_grids"] == 4
+    rgb, leaf, _ = tracer.render(cam, ft.ImageSize(160, 120), 0.01, 30.0, want_leaf=True)
+    ref = O.OracleScene(tracer.description).render(cam, 160, 120, 0.01, 30.0)
+    assert np.array_equal(leaf, ref["leaf"]) and np.array_equal(bits(rgb), bits(ref["rgb"]))
+    assert len(np.unique(leaf)) > 10
+
+
+def test_union_smooth_within_tolerance():
+    """SdfForm.unionSmooth uses MathF.Exp/Log (C runtime, not bit-reproducible): tolerance row.  Distances agree
+    to 2e-6 absolute + 2e-5 relative with the oracle (glibc expf/logf vs CUDA expf/logf)."""
+    from fraytracer_b200 import SdfForm, SdfMaterial, SdfObject, SdfScene
+
+    P = SdfForm.Primitive
+    forms = [P.sphere(Center=(0, 0, 0), Radius=1.0), P.sphere(Center=(1.5, 0, 0), Radius=0.8),
+             P.torus(Center=(0, 1.5, 0), Normal=(0, 1, 0.2), MajorRadius=1.0, MinorRadius=0.25),
+             P.capsule(From=(-1, -1, 0), To=(1, -1.5, 0.5), Radius=0.3)]
+    obj = SdfObject.create(SdfMaterial.createSolid((0.8, 0.6, 0.4)), SdfForm.unionSmooth(0.25, forms))
+    scene = SdfScene(Object=obj, BackgroundColor=(0.1, 0.1, 0.1), Lights=scenes.default_lights())
+    tracer = ft.SceneTracer(scene, device=0)
+    orc = O.OracleScene(tracer.description)
+    pts = (np.random.default_rng(2).normal(size=(20000, 3)) * 2).astype(np.float32)
+    assert np.allclose(tracer.distance(pts), orc.distance(pts), rtol=2e-5, atol=2e-6)
+    cam = scenes.default_camera()
+    rgb, leaf, _ = tracer.render(cam, ft.ImageSize(96, 96), 0.01, 30.0, want_leaf=True)
+    ref = orc.render(cam, 96, 96, 0.01, 30.0)
+    assert (leaf != ref["leaf"]).mean() < 0.01  # silhouette pixels only
+    same = (leaf == ref["leaf"])
+    rel = np.abs(rgb - ref["rgb"])[same] / np.maximum(np.abs(ref["rgb"])[same], 1e-3)
+    assert np.percentile(rel, 99) < 2e-2
+
+
+def test_chain_program_equals_generic_interpreter(monkeypatch):
+    for w in (scenes.default_scene(), scenes.mixed_scene()):
+        size = ft.ImageSize(240, 135)
+        chain = ft.SceneTracer(w.scene, device=0)
+        monkeypatch.setenv("FT_NO_CHAIN", "1")
+        generic = ft.SceneTracer(w.scene, device=0)
+        monkeypatch.delenv("FT_NO_CHAIN")
+        a, la, _ = chain.render(w.camera, size, w.epsilon, w.length, want_leaf=True)
+        b, lb, _ = generic.render(w.camera, size, w.epsilon, w.length, want_leaf=True)
+        assert np.array_equal(bits(a), bits(b)) and np.array_equal(la, lb)
