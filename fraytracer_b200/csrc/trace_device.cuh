@@ -330,27 +330,35 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
         uint32_t w = 0u;
         float4 b0{0.f, 0.f, 0.f, 0.f};
         bool need = false;
+        // scan (SdfForm.fs:27-33); spheres are resolved in place (their Distance is the bound test's value);
+        // two records in flight, ping-pong, so that the prefetch costs no register rotation
+#define FT_CHAIN_ONE(E)                                                       \
+    {                                                                         \
+        add_flops<COUNT>(acc, FLOPS_LB_TEST);                                 \
+        if (!(m > (E).lb() - dtc)) break;                                     \
+        float bd;                                                             \
+        add_flops<COUNT>(acc, FLOPS_BOUND_TEST);                              \
+        if (bound_test(m, (E).bound(), p, bd)) {                              \
+            if (FT_WORD_KIND((E).word()) == FT_K_SPHERE) {                    \
+                m = bd;                                                       \
+                add_flops<COUNT>(acc, FLOPS_MINMAX);                          \
+            } else {                                                          \
+                need = true;                                                  \
+                w = (E).word();                                               \
+                b0 = (E).bound();                                             \
+                break;                                                        \
+            }                                                                 \
+        }                                                                     \
+        i++;                                                                  \
+    }
         Entry e0 = ld_entry(S, i);
-        for (;;) {  // scan (SdfForm.fs:27-33); spheres are resolved in place, their Distance is the bound test's value
+        for (;;) {
             const Entry e1 = ld_entry(S, i + 1);
-            add_flops<COUNT>(acc, FLOPS_LB_TEST);
-            if (!(m > e0.lb() - dtc)) break;
-            float bd;
-            add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
-            if (bound_test(m, e0.bound(), p, bd)) {
-                if (FT_WORD_KIND(e0.word()) == FT_K_SPHERE) {
-                    m = bd;
-                    add_flops<COUNT>(acc, FLOPS_MINMAX);
-                } else {
-                    need = true;
-                    w = e0.word();
-                    b0 = e0.bound();
-                    break;
-                }
-            }
-            e0 = e1;
-            i++;
+            FT_CHAIN_ONE(e0)
+            e0 = ld_entry(S, i + 1);
+            FT_CHAIN_ONE(e1)
         }
+#undef FT_CHAIN_ONE
         if (!need) break;
         m = fminf(m, prim_distance<COUNT>(S, w, b0, p, acc));  // SdfForm.fs:33
         add_flops<COUNT>(acc, FLOPS_MINMAX);
