@@ -46,7 +46,7 @@ cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderP
     job.P = P;
     job.out_rgb = out_rgb;
     job.out_leaf = out_leaf;
-    job.n_items = (long long)((P.local_cols + 3) / 4) * ((P.height + 7) / 8) * 32;
+    job.n_items = (long long)((P.local_cols + FT_TILE_W - 1) / FT_TILE_W) * ((P.height + FT_TILE_H - 1) / FT_TILE_H) * 32;
     if (job.n_items <= 0) return cudaSuccess;
     unsigned grid = 1;
     cudaError_t e;

@@ -18,11 +18,15 @@ namespace FT_NS {
 #define FT_MINB 8  // <= 64 registers: 32 resident warps per SM (measured faster than 96 regs without spills)
 #endif
 constexpr int MB = 128;             // threads per CTA
+#ifndef FT_TILE_W
+#define FT_TILE_W 4  // pixel tile of one warp: FT_TILE_W (x) by FT_TILE_H (y), 32 pixels
+#define FT_TILE_H 8
+#endif
 #ifndef FT_REFILL_MIN
 #define FT_REFILL_MIN 32  // measured: whole tiles in lockstep beat per-lane refill by 1.5-2.9x (coherent cells and trip counts)
 #endif
 #ifndef FT_LONG_BATCH
-#define FT_LONG_BATCH 16
+#define FT_LONG_BATCH 1  // run the long class as soon as any lane has one (measured best with whole-tile lockstep)
 #endif
 constexpr int FT_CHUNK = 32;        // work items per global-counter grab (one tile of 4x8 pixels)
 
@@ -57,10 +61,10 @@ struct RenderJob {
                                          int &steps) const {
         const long long tile = i >> 5;
         const int lane = (int)(i & 31);
-        const int tiles_y = (P.height + 7) >> 3;
+        const int tiles_y = (P.height + FT_TILE_H - 1) / FT_TILE_H;
         const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
-        const int xl = tx * 4 + (lane >> 3);
-        const int y = ty * 8 + (lane & 7);
+        const int xl = tx * FT_TILE_W + lane / FT_TILE_H;
+        const int y = ty * FT_TILE_H + lane % FT_TILE_H;
         const int strip = xl / P.strip_width;
         const int x = P.x_offset + (strip * P.world + P.rank) * P.strip_width + (xl - strip * P.strip_width);
         if (xl >= P.local_cols || y >= P.height) return false;
