@@ -132,17 +132,19 @@ __device__ __forceinline__ Entry ld_entry(const DevScene &S, uint32_t i) {
 }
 
 // ---- the second pruning test, SdfForm.fs:31 / SdfObject.fs:38:  min > Vector3.Distance(C, p) - R.
-// s = |C - p|^2 is formed exactly like the reference; the root is only taken when the outcome is open:
-//   m + R <= 0              =>  sqrt(s) - R >= -R >= m          =>  false
-//   s > (m+R)^2 (1 + 2^-12)  =>  fl(sqrt(s)) > m + R (the 2^-13 margin dwarfs the 3 roundings involved)
-//                            =>  fl(sqrt(s)) - R > m, and rounding is monotone  =>  false
-// Otherwise bd = fl(fl(sqrt(s)) - R) is computed as the reference does and compared.  `bd` is only valid
-// when the function returns true.  NaNs fall through to the exact path (all comparisons false).
+// s = |C - p|^2 is formed exactly like the reference; the root is only taken when the outcome is open.
+// With u = max(m + R, 1e-15):  s > u^2 (1 + 2^-12)  implies  q = fl(sqrt(s)) > m + R  (u^2 >= 1e-30 is a normal
+// float, so the 2^-13 margin on the root dwarfs the roundings of u, u^2, the constant product and q; when
+// m + R < 1e-15, q > 1e-15 > m + R directly), hence q - R > m as reals and, rounding being monotone,
+// fl(q - R) >= m: the reference's test is false.  NaN in m or R lands here too (fmaxf drops it) and the
+// reference's comparison with NaN is false as well; NaN in s fails `s > ..` and takes the exact path.
+// Otherwise bd = fl(fl(sqrt(s)) - R) is computed and compared as the reference does.  `bd` is only valid when
+// the function returns true.
 __device__ __forceinline__ bool bound_test(float m, float4 b0, V3 p, float &bd) {
     const V3 dl = xyz(b0) - p;
     const float s = dot(dl, dl);
-    const float u = m + b0.w;
-    if (u <= 0.0f || s > (u * u) * 1.000244140625f) return false;
+    const float u = fmaxf(m + b0.w, 1e-15f);
+    if (s > (u * u) * 1.000244140625f) return false;
     bd = sqrtf(s) - b0.w;
     return m > bd;
 }
