@@ -255,3 +255,51 @@ def test_chain_program_equals_generic_interpreter(monkeypatch):
         a, la, _ = chain.render(w.camera, size, w.epsilon, w.length, want_leaf=True)
         b, lb, _ = generic.render(w.camera, size, w.epsilon, w.length, want_leaf=True)
         assert np.array_equal(bits(a), bits(b)) and np.array_equal(la, lb)
+
+
+@pytest.mark.parametrize("make,stride", [(scenes.default_scene, 25), (scenes.spheres_capsules_scene, 48)])
+def test_full_size_frames_against_oracle_columns(make, stride):
+    """BASELINE.json's full frame sizes (config 1: 1000x1000, config 2: 1920x1080): every `stride`-th column of the
+    GPU frame must equal the oracle bit for bit (the oracle finishes these columns in seconds)."""
+    w = make()
+    X, Y = w.size.X, w.size.Y
+    tracer = ft.SceneTracer(w.scene, device=0)
+    rgb, leaf, stats = tracer.render(w.camera, w.size, w.epsilon, w.length, want_leaf=True)
+    ref = O.OracleScene(tracer.description).render(w.camera, X, Y, w.epsilon, w.length, x_stride=stride)
+    cols = np.arange(0, X, stride)
+    assert np.array_equal(bits(rgb[cols]), bits(ref["rgb"][cols]))
+    assert np.array_equal(leaf[cols], ref["leaf"][cols])
+    assert stats["capped_rays"] == 0 and stats["primary_rays"] == X * Y
+
+
+def test_full_size_properties_config5_4k():
+    """size-independent properties at a size the oracle cannot cover: (a) the frame is independent of how it is cut
+    (one launch, two host bands, 8-column strips of 4 'ranks'); (b) re-rendering is idempotent; (c) the stats add up."""
+    import ctypes as C
+
+    import torch
+
+    from fraytracer_b200 import _abi as A
+    from fraytracer_b200.distributed import strip_layout
+
+    w = scenes.mixed_scene(width=3840, height=2160)
+    X, Y = w.size.X, w.size.Y
+    tracer = ft.SceneTracer(w.scene, device=0)
+    a, la, sa = tracer.render(w.camera, w.size, w.epsilon, w.length, want_leaf=True)
+    b, lb, sb = tracer.render(w.camera, w.size, w.epsilon, w.length, want_leaf=True)
+    assert np.array_equal(bits(a), bits(b)) and np.array_equal(la, lb)
+    assert sa["primary_hits"] == int((la >= 0).sum()) == sb["primary_hits"]
+    assert (bits(a[la < 0]) == bits(np.float32(0.1)).item()).all()  # misses carry the background colour exactly
+    world, sw = 4, 8
+    spr, _ = strip_layout(X, Y, sw, world)
+    gathered = torch.empty((world, spr * sw, Y, 3), dtype=torch.float32, device="cuda:0")
+    hits = 0
+    for r in range(world):
+        st = tracer.render_device(w.camera, w.size, w.epsilon, w.length, gathered[r].data_ptr(), strip_width=sw,
+                                  rank=r, world=world, stream=torch.cuda.current_stream().cuda_stream, want_stats=True)
+        hits += st["primary_hits"]
+    final = torch.empty((X, Y, 3), dtype=torch.float32, device="cuda:0")
+    A.check(tracer.lib.ft_deinterleave_device(C.c_void_p(gathered.data_ptr()), X, Y, sw, world, 3,
+                                              C.c_void_p(final.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(final.cpu().numpy()), bits(a)) and hits == sa["primary_hits"]
