@@ -116,6 +116,7 @@ EXPORTS = [
     "ft_scene_grid_count", "ft_scene_grid_info", "ft_scene_grid_read",
     "ft_render", "ft_render_device", "ft_strip_layout", "ft_deinterleave_device",
     "ft_trace_rays", "ft_distance",
+    "ft_image_max_device", "ft_tonemap_device", "ft_to_bitmap", "ft_save_bitmap",
     "ft_host_register", "ft_host_unregister", "ft_host_alloc", "ft_host_free",
     "ft_measure_fp32_peak",
 ]
@@ -163,6 +164,10 @@ def load_library(path: str | None = None):
         "ft_deinterleave_device": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
         "ft_trace_rays": (C.c_int, [vp, i64, vp, u32, vp, vp, vp, vp, P(ft_render_stats)]),
         "ft_distance": (C.c_int, [vp, i64, vp, u32, vp]),
+        "ft_image_max_device": (C.c_int, [vp, i64, vp, vp]),
+        "ft_tonemap_device": (C.c_int, [vp, i32, i32, f32, vp, f32, C.c_uint64, vp, i32, vp]),
+        "ft_to_bitmap": (C.c_int, [C.c_int, vp, i32, i32, f32, C.c_uint64, vp, i32]),
+        "ft_save_bitmap": (C.c_int, [C.c_char_p, vp, i32, i32, i32]),
         "ft_host_register": (C.c_int, [vp, i64]),
         "ft_host_unregister": (C.c_int, [vp]),
         "ft_host_alloc": (C.c_int, [P(vp), i64]),

@@ -524,3 +524,22 @@ class Image:
                             "Ray -> FColor closures cannot run on the device (FT_ERR_UNSUPPORTED_NODE)")
         out, _, _ = trace.render(camera, imageSize, epsilon, length)
         return out
+
+    @staticmethod
+    def toBitmap(gamma: float, seed: int, image: np.ndarray, device: int = 0) -> np.ndarray:
+        """Image.toColors gamma rng image |> Image.toBitmap (Image.fs:37-72) on the GPU: uint8 [Y, X, 3], top-down
+        B,G,R scanlines in the reference's pixel order.  `seed` keys the deterministic Philox dither that replaces
+        the reference's shared (racy) System.Random."""
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        X, Y = image.shape[0], image.shape[1]
+        out = np.zeros((Y, X, 3), np.uint8)
+        A.check(A.load_library().ft_to_bitmap(int(device), _ptr(image), X, Y, C.c_float(gamma), C.c_uint64(seed),
+                                              _ptr(out), 3 * X))
+        return out
+
+    @staticmethod
+    def saveBitmap(path: str, bitmap: np.ndarray):
+        """Image.saveBitmap path (Image.fs:87-90): 24-bit BMP from the scanlines of Image.toBitmap"""
+        bitmap = np.ascontiguousarray(bitmap, dtype=np.uint8)
+        Y, X = bitmap.shape[0], bitmap.shape[1]
+        A.check(A.load_library().ft_save_bitmap(str(path).encode(), _ptr(bitmap), X, Y, 3 * X))

@@ -592,6 +592,55 @@ FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint3
     return FT_OK;
 }
 
+FT_API int ft_image_max_device(const float *d_rgb, int64_t n_floats, float *d_max, void *stream) {
+    if (!d_rgb || !d_max || n_floats < 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    cudaError_t e = launch_image_max(d_rgb, n_floats, d_max, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "image max kernel launch");
+    return FT_OK;
+}
+
+FT_API int ft_tonemap_device(const float *d_rgb, int32_t width, int32_t height, float gamma, const float *d_max,
+                             float max_value, uint64_t seed, uint8_t *d_out_bgr, int32_t stride, void *stream) {
+    if (!d_rgb || !d_out_bgr || width <= 0 || height <= 0 || stride < 3 * width || !(gamma > 0.0f))
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    cudaError_t e = launch_tonemap(d_rgb, width, height, gamma, d_max, max_value, seed, d_out_bgr, stride, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tonemap kernel launch");
+    return FT_OK;
+}
+
+FT_API int ft_to_bitmap(int device, const float *rgb, int32_t width, int32_t height, float gamma, uint64_t seed,
+                        uint8_t *out_bgr, int32_t stride) {
+    if (!rgb || !out_bgr || width <= 0 || height <= 0 || stride < 3 * width || !(gamma > 0.0f))
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+        return fail(FT_ERR_NO_DEVICE, "no CUDA device available; fraytracer_b200 has no CPU fallback");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    const size_t n = (size_t)width * height * 3, out_bytes = (size_t)stride * height;
+    float *d_rgb = nullptr, *d_max = nullptr;
+    uint8_t *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_rgb, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_max, sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_bytes);
+    if (e == cudaSuccess) e = cudaMemset(d_out, 0, out_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(d_rgb, rgb, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_image_max(d_rgb, (long long)n, d_max, nullptr);
+    if (e == cudaSuccess) e = launch_tonemap(d_rgb, width, height, gamma, d_max, 0.f, seed, d_out, stride, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out_bgr, d_out, out_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_rgb);
+    cudaFree(d_max);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "ft_to_bitmap");
+    return FT_OK;
+}
+
+FT_API int ft_save_bitmap(const char *path, const uint8_t *bgr, int32_t width, int32_t height, int32_t stride) {
+    if (!path || !bgr || width <= 0 || height <= 0 || stride < 3 * width) return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    if (write_bmp_file(path, bgr, width, height, stride) != 0) return fail(FT_ERR_INVALID_ARGUMENT, std::string("cannot write ") + path);
+    return FT_OK;
+}
+
 FT_API int ft_host_register(void *ptr, int64_t bytes) {
     if (!ptr || bytes <= 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
     CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));

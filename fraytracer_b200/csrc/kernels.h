@@ -40,3 +40,9 @@ FT_DECLARE_LAUNCHERS(ft_fast)
 cudaError_t launch_deinterleave(const float *gathered, int width, int height, int strip_width, int world, int channels,
                                 float *out, cudaStream_t stream);
 cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate);
+
+// post_kernels.cu
+cudaError_t launch_image_max(const float *rgb, long long n_floats, float *d_max, cudaStream_t stream);
+cudaError_t launch_tonemap(const float *rgb, int X, int Y, float gamma, const float *d_max, float max_value,
+                           unsigned long long seed, unsigned char *out, int stride, cudaStream_t stream);
+int write_bmp_file(const char *path, const unsigned char *bgr, int width, int height, int stride);

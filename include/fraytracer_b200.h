@@ -298,6 +298,24 @@ FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_
 FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint32_t flags,
                        float *out_distance);
 
+/* ---- post-process: Image.toColors / toBitmap / saveBitmap (Image.fs:37-90) -- */
+/* max over the n_floats values of an FColor image (Array2D.Parallel.maxWith FColor.getMaxColor, Image.fs:40-42);
+ * d_max is one DEVICE float.  With several GPUs, all-reduce(max) it before ft_tonemap_device.               */
+FT_API int ft_image_max_device(const float *d_rgb, int64_t n_floats, float *d_max, void *stream);
+/* Image.toColors gamma rng image + Image.toBitmap's pixel order, on the device.  d_rgb is FColor[X,Y]
+ * (x-major).  Output: top-down 24-bit B,G,R scanlines of `stride` bytes; scanline r, column c holds the colour
+ * of image[X-1-c, r] (the reference's Array.rev undoes its own y flip and mirrors x, Image.fs:66-72).
+ * The maximum is read from d_max when non-NULL, else max_value is used; Max(0.01, .) is applied as Image.fs:43.
+ * The reference's dither comes from a System.Random shared by a parallel map (a race: not reproducible);
+ * here it is Philox4x32-10(seed, pixel index), deterministic.                                               */
+FT_API int ft_tonemap_device(const float *d_rgb, int32_t width, int32_t height, float gamma, const float *d_max,
+                             float max_value, uint64_t seed, uint8_t *d_out_bgr, int32_t stride, void *stream);
+/* host-pointer convenience: upload FColor[X,Y], max, tone map, download the scanlines (device ordinal given) */
+FT_API int ft_to_bitmap(int device, const float *rgb, int32_t width, int32_t height, float gamma, uint64_t seed,
+                        uint8_t *out_bgr, int32_t stride);
+/* Image.saveBitmap path (Image.fs:87-90): 24-bit BMP from top-down B,G,R scanlines (host pointers, no GPU)  */
+FT_API int ft_save_bitmap(const char *path, const uint8_t *bgr, int32_t width, int32_t height, int32_t stride);
+
 /* ---- host memory helpers ------------------------------------------------- */
 FT_API int ft_host_register(void *ptr, int64_t bytes);
 FT_API int ft_host_unregister(void *ptr);

@@ -1147,3 +1147,50 @@ FTO_API int fto_root_boundary(const fto_scene *s, float out[4]) {
     out[0] = b.c.x; out[1] = b.c.y; out[2] = b.c.z; out[3] = b.r;
     return FT_OK;
 }
+
+/* ------------------------------------------------------------------------ */
+/* Post-process: Image.toColors + Image.toBitmap (Image.fs:37-72, FColor.fs:43-58) */
+/* ------------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al. SC'11): the deterministic replacement, shared with the product by
+ * specification, for the reference's racy shared System.Random dither (Image.fs:45-50).          */
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+FTO_API void fto_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    philox4x32_10(c, key[0], key[1]);
+    memcpy(out, c, sizeof(c));
+}
+static unsigned char to_byte(float c, float inv_gamma, float mx, uint32_t bits) {
+    float v = powf(c / mx, inv_gamma);                             /* FColor.fs:50-55 MathF.Pow */
+    float u = (float)((double)bits * (1.0 / 4294967296.0));        /* range_01 */
+    float r = rintf(v * 254.5f + u);                               /* FColor.fs:44 MathF.Round (half to even) */
+    int k = (int)r;
+    k = k < 255 ? k : 255;
+    return (unsigned char)(k < 0 ? 0 : k);
+}
+/* rgb: FColor[X,Y] x-major.  out: top-down B,G,R scanlines; scanline r, column c = image[X-1-c, r]
+ * (Image.fs:66-72: y flip, then Array.rev).                                                       */
+FTO_API float fto_to_bitmap(const float *rgb, int X, int Y, float gamma, uint64_t seed, unsigned char *out, int stride) {
+    float mx = rgb[0];
+    for (int64_t i = 1; i < (int64_t)X * Y * 3; i++) if (rgb[i] > mx) mx = rgb[i]; /* Image.fs:40-42 */
+    float raw = mx;
+    mx = net_max(0.01f, mx);                                                          /* Image.fs:43 */
+    float inv_gamma = 1.0f / gamma;                                                   /* Image.fs:38 */
+    for (int x = 0; x < X; x++)
+        for (int y = 0; y < Y; y++) {
+            int64_t idx = (int64_t)x * Y + y;
+            uint32_t c[4] = {(uint32_t)idx, (uint32_t)((uint64_t)idx >> 32), 0u, 0u};
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            unsigned char *p = out + (int64_t)y * stride + 3 * (int64_t)(X - 1 - x);
+            p[2] = to_byte(rgb[3 * idx], inv_gamma, mx, c[0]);
+            p[1] = to_byte(rgb[3 * idx + 1], inv_gamma, mx, c[1]);
+            p[0] = to_byte(rgb[3 * idx + 2], inv_gamma, mx, c[2]);
+        }
+    return raw;
+}

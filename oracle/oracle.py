@@ -72,6 +72,9 @@ def lib():
         L.fto_form_distance.argtypes = [vp, C.c_int, i64, vp, vp]
         L.fto_form_boundary.argtypes = [vp, C.c_int, vp]
         L.fto_root_boundary.argtypes = [vp, vp]
+        L.fto_philox4x32_10.argtypes = [vp, vp, vp]
+        L.fto_to_bitmap.restype = f32
+        L.fto_to_bitmap.argtypes = [vp, C.c_int, C.c_int, f32, C.c_uint64, vp, C.c_int]
         _lib = L
     return _lib
 
@@ -210,3 +213,20 @@ class OracleScene:
         out = np.empty(4, np.float32)
         lib().fto_root_boundary(self.h, _ptr(out))
         return out
+
+
+def philox4x32_10(ctr, key):
+    c = np.array(ctr, np.uint32)
+    k = np.array(key, np.uint32)
+    out = np.zeros(4, np.uint32)
+    lib().fto_philox4x32_10(_ptr(c), _ptr(k), _ptr(out))
+    return out
+
+
+def to_bitmap(rgb, gamma, seed):
+    """Image.toColors + toBitmap pixel order: returns (uint8 [Y, X, 3] top-down B,G,R scanlines, raw max)"""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    X, Y = rgb.shape[0], rgb.shape[1]
+    out = np.zeros((Y, X, 3), np.uint8)
+    mx = lib().fto_to_bitmap(_ptr(rgb), X, Y, C.c_float(gamma), C.c_uint64(seed), _ptr(out), 3 * X)
+    return out, float(mx)
