@@ -61,54 +61,67 @@ def workload(name: str, world: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML from a thread DURING the timed region (every ~5 ms);
+    the same quantities `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu: int):
-        self.proc = None
+        import threading
+
+        self.rows, self.stop_flag, self.error = [], False, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            pass
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = gpu
+            if vis:  # map the CUDA ordinal to the NVML index
+                tok = vis.split(",")[gpu].strip()
+                if tok.isdigit():
+                    index = int(tok)
+                else:
+                    uuid = tok
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid) if uuid else \
+                pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.error = f"NVML unavailable: {e}"
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001  older bindings
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), mhz, mask))
+            except Exception as e:  # noqa: BLE001
+                self.error = str(e)
+                return
+            time.sleep(0.005)
 
     def stop(self, t_begin=None, t_end=None):
-        """samples whose nvidia-smi timestamp falls into [t_begin, t_end] (time.time()); the sampler is started
-        before the warm-up so that it is already looping when the timed region begins"""
-        import datetime
-
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        rows = []
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(f[1]), float(f[2]), f[4:8]))
-            except ValueError:
-                continue
-        inside = [r for r in rows if t_begin is None or (t_begin - 0.02 <= r[0] <= t_end + 0.02)]
+        if self.error and not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.error], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        inside = [r for r in self.rows if t_begin is None or t_begin <= r[0] <= t_end]
         window = "timed region"
-        if not inside:  # region shorter than the sampling period: fall back to every sample of the run
-            inside, window = rows, "whole run (timed region shorter than the sampling period)"
-        sm, mx, reasons = [r[1] for r in inside], [r[2] for r in inside], set()
+        if not inside:
+            inside, window = self.rows, "whole run (no sample fell into the timed region)"
+        mask = 0
         for r in inside:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+            mask |= r[2]
+        return {"sm_mhz": statistics.median([r[1] for r in inside]) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(v for k, v in self.REASONS.items() if mask & k), "samples": len(inside),
+                "window": window}
 
 
 def cpu_sample(orc, w, budget_s: float, threads: int):
@@ -203,7 +216,8 @@ def bench_b200(args):
         return float(t.item())
 
     # ---- work of one step (deterministic): rays and algorithmic flops of this rank's strips
-    buf = renderer.local if world > 1 else renderer.final
+    spr_floats = ft.distributed.strip_layout(X, Y, 8, world)[1]
+    buf = torch.empty(spr_floats, dtype=torch.float32, device=dev) if world > 1 else renderer.final
     st = tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(),
                               stream=torch.cuda.current_stream().cuda_stream, flags=flags | A.FT_FLAG_COUNTERS,
                               strip_width=8, rank=rank, world=world, want_stats=True)
@@ -221,21 +235,26 @@ def bench_b200(args):
 
     def one_step(timed):
         flush.zero_()
-        stream = torch.cuda.current_stream().cuda_stream
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
         e0.record()
-        if world == 1:
-            renderer.render(w.camera, w.epsilon, w.length, flags)
-            e1.record()
-        else:
-            tracer.render_device(w.camera, w.size, w.epsilon, w.length, renderer.local.data_ptr(), stream=stream,
-                                 flags=flags, strip_width=8, rank=rank, world=world)
-            e1.record()
-            dist.all_gather_into_tensor(renderer.gathered.view(-1, Y, 3), renderer.local)
-            A.check(lib.ft_deinterleave_device(C.c_void_p(renderer.gathered.data_ptr()), X, Y, 8, world, 3,
-                                               C.c_void_p(renderer.final.data_ptr()), C.c_void_p(stream) if stream else None))
+        renderer.render(w.camera, w.epsilon, w.length, flags)  # N > 1: chunked render, async all-gather, de-interleave
         e2.record()
-        return (e0, e1, e2) if timed else None
+        return (e0, e2, e2) if timed else None
+
+    # duration of the dominant kernel alone (all strips of this rank in one launch), for the roofline
+    kern_events = []
+    for it in range(6):
+        flush.zero_()
+        k0, k1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        k0.record()
+        tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(),
+                             stream=torch.cuda.current_stream().cuda_stream, flags=flags, strip_width=8, rank=rank,
+                             world=world)
+        k1.record()
+        if it >= 3:
+            kern_events.append((k0, k1))
+    torch.cuda.synchronize()
+    kern_ms = sum(x.elapsed_time(y) for x, y in kern_events) / len(kern_events)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
@@ -246,7 +265,6 @@ def bench_b200(args):
     barrier()
     t_end = time.time()
     step_ms = sum(e0.elapsed_time(e2) for e0, _, e2 in events)
-    kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in events) / args.steps
     clocks = sampler.stop(t_begin, t_end) if sampler else None
     step_ms = allreduce(step_ms, dist.ReduceOp.MAX if world > 1 else None)
     ms_per_step = step_ms / args.steps
@@ -287,7 +305,7 @@ def bench_b200(args):
         e2e_s = allreduce(e2e_s, dist.ReduceOp.MAX)
         checksum = float(pinned[::97, ::89].sum()) if rank == 0 else 0.0
         h2d = C.sizeof(A.ft_camera) + 16
-        e2e_launches = 2
+        e2e_launches = renderer.launches_per_frame
     e2e_value = total_rays * args.steps / e2e_s / 1e6
 
     if rank == 0:

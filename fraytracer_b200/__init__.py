@@ -5,6 +5,7 @@ include/fraytracer_b200.h).  This package is the thin host-side mirror of the re
 API over that ABI.  There is no CPU fallback.
 """
 from ._abi import (FT_FLAG_COUNTERS, FT_FLAG_DEFAULT, FT_FLAG_FAST_MATH, FrayTracerError, load_library)
+from . import distributed  # noqa: F401
 from .api import (Camera, FColor, Image, ImageSize, Lens, Ray, SceneDescription, SceneTracer, SdfForm,
                   SdfLight, SdfMaterial, SdfObject, SdfScene)
 

@@ -114,7 +114,8 @@ EXPORTS = [
     "ft_abi_version", "ft_last_error", "ft_device_count", "ft_lens_create", "ft_camera_look_at",
     "ft_scene_create", "ft_scene_destroy", "ft_scene_info_get", "ft_scene_set_step_cap",
     "ft_scene_grid_count", "ft_scene_grid_info", "ft_scene_grid_read",
-    "ft_render", "ft_render_device", "ft_strip_layout", "ft_deinterleave_device",
+    "ft_render", "ft_render_device", "ft_render_strips_device", "ft_strip_layout", "ft_deinterleave_device",
+    "ft_deinterleave_strips_device",
     "ft_trace_rays", "ft_distance",
     "ft_image_max_device", "ft_tonemap_device", "ft_to_bitmap", "ft_save_bitmap",
     "ft_host_register", "ft_host_unregister", "ft_host_alloc", "ft_host_free",
@@ -160,6 +161,9 @@ def load_library(path: str | None = None):
         "ft_render": (C.c_int, [vp, P(ft_camera), i32, i32, f32, f32, u32, vp, vp, P(ft_render_stats)]),
         "ft_render_device": (C.c_int, [vp, P(ft_camera), i32, i32, f32, f32, u32, i32, i32, i32, vp, vp, vp,
                                        P(ft_render_stats)]),
+        "ft_render_strips_device": (C.c_int, [vp, P(ft_camera), i32, i32, f32, f32, u32, i32, i32, i32, i32, i32, vp, vp,
+                                              vp, P(ft_render_stats)]),
+        "ft_deinterleave_strips_device": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
         "ft_strip_layout": (C.c_int, [i32, i32, i32, i32, P(i32), P(i64)]),
         "ft_deinterleave_device": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
         "ft_trace_rays": (C.c_int, [vp, i64, vp, u32, vp, vp, vp, vp, P(ft_render_stats)]),

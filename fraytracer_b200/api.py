@@ -476,17 +476,20 @@ class SceneTracer:
 
     def render_device(self, camera: Camera, size: ImageSize, epsilon: float, length: float, d_out_rgb: int,
                       d_out_leaf: int = 0, stream: int = 0, flags: int = 0, strip_width: int = 8,
-                      rank: int = 0, world: int = 1, want_stats: bool = False):
+                      rank: int = 0, world: int = 1, want_stats: bool = False, first_local_strip: int = 0,
+                      n_local_strips: int = -1):
         """Asynchronous render into device memory (raw pointers, e.g. torch `data_ptr()`).
-        want_stats=True synchronises the stream and returns the counters of this launch."""
+        want_stats=True synchronises the stream and returns the counters of this launch.
+        first_local_strip / n_local_strips render only a range of the rank's strips (d_out_rgb then points at
+        that range's first column)."""
         cam = camera.to_c()
         stats = A.ft_render_stats() if want_stats else None
-        A.check(self.lib.ft_render_device(self.handle, C.byref(cam), int(size.X), int(size.Y),
-                                          C.c_float(epsilon), C.c_float(length), int(flags), int(strip_width),
-                                          int(rank), int(world), C.c_void_p(d_out_rgb),
-                                          C.c_void_p(d_out_leaf) if d_out_leaf else None,
-                                          C.c_void_p(stream) if stream else None,
-                                          C.byref(stats) if want_stats else None))
+        A.check(self.lib.ft_render_strips_device(self.handle, C.byref(cam), int(size.X), int(size.Y),
+                                                 C.c_float(epsilon), C.c_float(length), int(flags), int(strip_width),
+                                                 int(rank), int(world), int(first_local_strip), int(n_local_strips),
+                                                 C.c_void_p(d_out_rgb), C.c_void_p(d_out_leaf) if d_out_leaf else None,
+                                                 C.c_void_p(stream) if stream else None,
+                                                 C.byref(stats) if want_stats else None))
         return stats.as_dict() if want_stats else None
 
     def trace_rays(self, rays: np.ndarray, flags: int = 0):

@@ -156,6 +156,7 @@ RenderParams make_params(int width, int height, float eps, float length, int str
     P.rank = rank;
     P.world = world;
     P.x_offset = 0;
+    P.xl_begin = 0;
     const int strips = (width + strip_width - 1) / strip_width;
     const int spr = (strips + world - 1) / world;
     P.local_cols = world == 1 ? width : spr * strip_width;
@@ -402,6 +403,14 @@ FT_API int ft_strip_layout(int32_t width, int32_t height, int32_t strip_width, i
 FT_API int ft_render_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
                             float length, uint32_t flags, int32_t strip_width, int32_t rank, int32_t world,
                             float *d_out_rgb, int32_t *d_out_leaf, void *stream, ft_render_stats *stats) {
+    return ft_render_strips_device(scene, camera, width, height, epsilon, length, flags, strip_width, rank, world, 0, -1,
+                                   d_out_rgb, d_out_leaf, stream, stats);
+}
+
+FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                                   float length, uint32_t flags, int32_t strip_width, int32_t rank, int32_t world,
+                                   int32_t first_local_strip, int32_t n_local_strips, float *d_out_rgb,
+                                   int32_t *d_out_leaf, void *stream, ft_render_stats *stats) {
     if (!scene || !camera || !d_out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
     if (width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || rank < 0 || rank >= world)
         return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size or strip partition");
@@ -414,7 +423,18 @@ FT_API int ft_render_device(ft_scene *scene, const ft_camera *camera, int32_t wi
     if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
     cudaStream_t s = (cudaStream_t)stream;
     const bool count = (flags & FT_FLAG_COUNTERS) != 0;
-    const RenderParams P = make_params(width, height, epsilon, length, strip_width, rank, world);
+    RenderParams P = make_params(width, height, epsilon, length, strip_width, rank, world);
+    if (n_local_strips >= 0) {  // a range of this rank's local strips
+        const int spr = (((width + strip_width - 1) / strip_width) + world - 1) / world;
+        if (first_local_strip < 0 || first_local_strip + n_local_strips > spr)
+            return fail(FT_ERR_INVALID_ARGUMENT, "local strip range out of bounds");
+        if (world == 1 && (first_local_strip + n_local_strips) * strip_width > width)
+            P.local_cols = width - first_local_strip * strip_width;  // the plain FColor[X,Y] has no padding columns
+        else
+            P.local_cols = n_local_strips * strip_width;
+        P.xl_begin = first_local_strip * strip_width;
+        if (P.local_cols <= 0) return FT_OK;
+    }
     if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     unsigned long long *wc;
     CU(fresh_counter(scene, s, &wc));
@@ -428,7 +448,7 @@ FT_API int ft_render_device(ft_scene *scene, const ft_camera *camera, int32_t wi
         CU(cudaStreamSynchronize(s));
         sum_stats(scene->h_stats, stats);
         long long owned = 0;
-        for (int xl = 0; xl < P.local_cols; xl++) {
+        for (int xl = P.xl_begin; xl < P.xl_begin + P.local_cols; xl++) {
             const int strip = xl / strip_width;
             const int x = (strip * world + rank) * strip_width + (xl - strip * strip_width);
             owned += x < width;
@@ -514,9 +534,19 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
 
 FT_API int ft_deinterleave_device(const float *d_gathered, int32_t width, int32_t height, int32_t strip_width,
                                   int32_t world, int32_t channels, float *d_out, void *stream) {
-    if (!d_gathered || !d_out || width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || channels <= 0)
+    if (width <= 0 || strip_width <= 0 || world <= 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    const int spr = (((width + strip_width - 1) / strip_width) + world - 1) / world;
+    return ft_deinterleave_strips_device(d_gathered, width, height, strip_width, world, channels, 0, spr, d_out, stream);
+}
+
+FT_API int ft_deinterleave_strips_device(const float *d_gathered, int32_t width, int32_t height, int32_t strip_width,
+                                         int32_t world, int32_t channels, int32_t first_local_strip,
+                                         int32_t n_local_strips, float *d_out, void *stream) {
+    if (!d_gathered || !d_out || width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || channels <= 0 ||
+        first_local_strip < 0 || n_local_strips < 0)
         return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
-    cudaError_t e = launch_deinterleave(d_gathered, width, height, strip_width, world, channels, d_out, (cudaStream_t)stream);
+    cudaError_t e = launch_deinterleave(d_gathered, width, height, strip_width, world, channels, first_local_strip,
+                                        n_local_strips, d_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "deinterleave kernel launch");
     return FT_OK;
 }

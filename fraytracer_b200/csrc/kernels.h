@@ -19,6 +19,7 @@ struct RenderParams {
     int local_cols;      // columns of this rank's compact buffer
     int strip_width, rank, world;
     int x_offset;        // image column of compact column 0 (band rendering)
+    int xl_begin;        // first compact column (in the rank's strip space) this launch renders; out_rgb starts there
     float epsilon, length, max_size;
 };
 
@@ -38,7 +39,7 @@ FT_DECLARE_LAUNCHERS(ft_fast)
 
 // util_kernels.cu
 cudaError_t launch_deinterleave(const float *gathered, int width, int height, int strip_width, int world, int channels,
-                                float *out, cudaStream_t stream);
+                                int first_local_strip, int n_local_strips, float *out, cudaStream_t stream);
 cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate);
 
 // post_kernels.cu

@@ -63,12 +63,13 @@ struct RenderJob {
         const int lane = (int)(i & 31);
         const int tiles_y = (P.height + FT_TILE_H - 1) / FT_TILE_H;
         const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
-        const int xl = tx * FT_TILE_W + lane / FT_TILE_H;
+        const int xc = tx * FT_TILE_W + lane / FT_TILE_H;  // column inside this launch's buffer
+        const int xl = P.xl_begin + xc;                    // column in the rank's compact strip space
         const int y = ty * FT_TILE_H + lane % FT_TILE_H;
         const int strip = xl / P.strip_width;
         const int x = P.x_offset + (strip * P.world + P.rank) * P.strip_width + (xl - strip * P.strip_width);
-        if (xl >= P.local_cols || y >= P.height) return false;
-        slot = (long long)xl * P.height + y;
+        if (xc >= P.local_cols || y >= P.height) return false;
+        slot = (long long)xc * P.height + y;
         if (x >= P.width) {  // padding column of a strip buffer: defined contents for the all-gather
             out_rgb[3 * slot + 0] = 0.f;
             out_rgb[3 * slot + 1] = 0.f;

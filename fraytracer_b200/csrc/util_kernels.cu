@@ -1,33 +1,35 @@
 // util_kernels.cu -- strip de-interleave after the multi-GPU all-gather, and the FP32 peak probe.
 #include "kernels.h"
 
-// gathered: [world][strips_per_rank][strip_width][height][channels]  ->  out: [width][height][channels]
-// (x-major FColor[X,Y]).  One thread per output scalar; consecutive threads write consecutive addresses.
+// gathered: [world][n_local_strips][strip_width][height][channels], holding local strips
+// first_local_strip .. first_local_strip + n_local_strips - 1 of every rank  ->  out: [width][height][channels]
+// (x-major FColor[X,Y]).  One thread per SOURCE scalar: a strip column is contiguous on both sides, so reads and
+// writes are coalesced.  Padding columns (image column >= width) are dropped.
 __global__ void __launch_bounds__(256) deinterleave_kernel(const float *__restrict__ g, int width, int height,
                                                            int strip_width, int world, int channels,
-                                                           int strips_per_rank, float *__restrict__ out) {
+                                                           int first_local_strip, int n_local_strips,
+                                                           float *__restrict__ out) {
     const long long col_elems = (long long)height * channels;
-    const long long total = (long long)width * col_elems;
+    const long long cols_per_rank = (long long)n_local_strips * strip_width;
+    const long long total = (long long)world * cols_per_rank * col_elems;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(i / col_elems);
-        const long long rem = i - (long long)x * col_elems;
-        const int strip = x / strip_width, within = x - strip * strip_width;
-        const int rank = strip % world, local = strip / world;
-        const long long src = (((long long)rank * strips_per_rank + local) * strip_width + within) * col_elems + rem;
-        out[i] = __ldg(g + src);
+        const long long col = i / col_elems, rem = i - col * col_elems;
+        const int rank = (int)(col / cols_per_rank);
+        const int lc = (int)(col - (long long)rank * cols_per_rank);
+        const int local = lc / strip_width, within = lc - local * strip_width;
+        const long long x = ((long long)(first_local_strip + local) * world + rank) * strip_width + within;
+        if (x < width) out[x * col_elems + rem] = __ldg(g + i);
     }
 }
 
 cudaError_t launch_deinterleave(const float *gathered, int width, int height, int strip_width, int world, int channels,
-                                float *out, cudaStream_t stream) {
-    const int strips = (width + strip_width - 1) / strip_width;
-    const int strips_per_rank = (strips + world - 1) / world;
-    const long long total = (long long)width * height * channels;
+                                int first_local_strip, int n_local_strips, float *out, cudaStream_t stream) {
+    const long long total = (long long)world * n_local_strips * strip_width * height * channels;
     if (total <= 0) return cudaSuccess;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     deinterleave_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gathered, width, height, strip_width, world, channels,
-                                                              strips_per_rank, out);
+                                                              first_local_strip, n_local_strips, out);
     return cudaGetLastError();
 }
 

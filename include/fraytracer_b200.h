@@ -275,6 +275,14 @@ FT_API int ft_render_device(ft_scene *scene, const ft_camera *camera, int32_t wi
                             int32_t rank, int32_t world, float *d_out_rgb, int32_t *d_out_leaf,
                             void *stream, ft_render_stats *stats);
 
+/* Same for a RANGE of the rank's local strips [first_local_strip, first_local_strip + n_local_strips):
+ * d_out_rgb / d_out_leaf point at the first column of that range (a chunk of the compact buffer).  Lets a rank
+ * render in chunks so that the all-gather of chunk k overlaps the rendering of chunk k+1.                  */
+FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
+                                   float epsilon, float length, uint32_t flags, int32_t strip_width, int32_t rank,
+                                   int32_t world, int32_t first_local_strip, int32_t n_local_strips,
+                                   float *d_out_rgb, int32_t *d_out_leaf, void *stream, ft_render_stats *stats);
+
 /* number of strips and of floats in the compact per-rank buffer above       */
 FT_API int ft_strip_layout(int32_t width, int32_t height, int32_t strip_width, int32_t world,
                            int32_t *strips_per_rank, int64_t *floats_per_rank);
@@ -284,6 +292,12 @@ FT_API int ft_strip_layout(int32_t width, int32_t height, int32_t strip_width, i
 FT_API int ft_deinterleave_device(const float *d_gathered, int32_t width, int32_t height,
                                   int32_t strip_width, int32_t world, int32_t channels,
                                   float *d_out, void *stream);
+
+/* the same for an all-gathered chunk [world][n_local_strips][strip_width][height][channels] that holds local
+ * strips first_local_strip .. of every rank                                                                 */
+FT_API int ft_deinterleave_strips_device(const float *d_gathered, int32_t width, int32_t height, int32_t strip_width,
+                                         int32_t world, int32_t channels, int32_t first_local_strip,
+                                         int32_t n_local_strips, float *d_out, void *stream);
 
 /* Batched SdfScene.trace scene ray (SdfScene.fs:7-28) for arbitrary rays.
  * HOST pointers; every output is optional.  out_leaf: as above.  out_steps:

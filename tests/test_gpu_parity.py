@@ -110,6 +110,21 @@ def test_strip_partition_gather_equals_single_render():
         torch.cuda.synchronize()
         assert not torch.isnan(gathered).any()  # padding columns are written too
         assert np.array_equal(bits(final.cpu().numpy()), bits(full))
+        # the same in two chunks of local strips (what DistributedRenderer overlaps with the all-gather)
+        final2 = torch.full((X, Y, 3), float("nan"), dtype=torch.float32, device="cuda:0")
+        edges = [0, spr // 2, spr]
+        for first, n in ((edges[0], edges[1] - edges[0]), (edges[1], edges[2] - edges[1])):
+            if n == 0:
+                continue
+            chunk = torch.full((world, n * sw, Y, 3), float("nan"), dtype=torch.float32, device="cuda:0")
+            for r in range(world):
+                tracer.render_device(w.camera, size, w.epsilon, w.length, chunk[r].data_ptr(), strip_width=sw, rank=r,
+                                     world=world, first_local_strip=first, n_local_strips=n,
+                                     stream=torch.cuda.current_stream().cuda_stream)
+            A.check(tracer.lib.ft_deinterleave_strips_device(C.c_void_p(chunk.data_ptr()), X, Y, sw, world, 3, first, n,
+                                                             C.c_void_p(final2.data_ptr()), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(final2.cpu().numpy()), bits(full))
 
 
 def test_fast_math_mode_within_tolerance():
