@@ -89,7 +89,8 @@ class ft_ray(C.Structure):
 class ft_scene_info(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_primitives", C.c_int32), ("n_grids", C.c_int32),
                 ("max_depth", C.c_int32), ("n_cells", C.c_int64), ("n_entries", C.c_int64),
-                ("device_bytes", C.c_int64), ("device", C.c_int32), ("sm_count", C.c_int32)]
+                ("device_bytes", C.c_int64), ("device", C.c_int32), ("sm_count", C.c_int32),
+                ("grids_built_on_gpu", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ft_grid_info(C.Structure):

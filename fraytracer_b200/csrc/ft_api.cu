@@ -201,8 +201,20 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
     if (!s) return fail(FT_ERR_OUT_OF_MEMORY, "host allocation failed");
     std::string err;
     int st;
+    // Spatial lookups are built on the device once they are large (>= 2^24 cell x child pair tests; the host build
+    // of the reference's 1024-primitive scenes takes ~10 ms).  FT_GRID_BUILD=gpu|cpu forces either (tests).
+    ftc::GridBuildFn grid_fn = nullptr;
+    long long gpu_min_pairs = 1ll << 24;
+    if (device != FT_DEVICE_NONE) {
+        int nd = 0;
+        if (cudaGetDeviceCount(&nd) == cudaSuccess && device >= 0 && device < nd) grid_fn = ftc::gpu_grid_build;
+    }
+    if (const char *gb = getenv("FT_GRID_BUILD")) {
+        if (!strcmp(gb, "cpu")) grid_fn = nullptr;
+        else if (!strcmp(gb, "gpu")) gpu_min_pairs = 0;
+    }
     try {
-        st = ftc::compile_scene(desc, &s->host, &err);
+        st = ftc::compile_scene(desc, &s->host, &err, grid_fn, (void *)(intptr_t)device, gpu_min_pairs);
     } catch (const std::bad_alloc &) {
         delete s;
         return fail(FT_ERR_OUT_OF_MEMORY, "host allocation failed while compiling the scene");
@@ -315,6 +327,7 @@ FT_API int ft_scene_info_get(const ft_scene *scene, ft_scene_info *out) {
         out->n_entries += g.n_entries;
     }
     out->device_bytes = scene->device_bytes;
+    out->grids_built_on_gpu = h.grids_built_on_gpu;
     out->device = scene->device;
     out->sm_count = scene->sm_count;
     return FT_OK;

@@ -8,6 +8,7 @@
 #include <limits>
 #include <thread>
 
+#include "dotnet_sort.h"
 #include "ft_math.h"
 
 namespace ftc {
@@ -51,100 +52,9 @@ Bnd bnd_intersection(const Bnd &a, const Bnd &b) {
     return Bnd{(a2 + b2) * 0.5f, sqrtf(4.0f * d2 * aR2 - (d2 - bR2 + aR2)) / (2.0f * dist)};
 }
 
-// ---- Array.sortInPlaceBy (SdfBoundary.fs:267-268) = .NET 6 Array.Sort(keys, items): float keys,
-// NaNs moved to the front, then introsort (insertion sort <= 16, median-of-three partition,
-// heapsort at depth 2*(log2 n + 1)).  Not stable: ties keep this algorithm's order.
-struct KeyItem {
-    float key;
-    int32_t item;
-};
-struct DotNetSort {
-    static void swap_if_greater(KeyItem *a, int i, int j) {
-        if (a[i].key > a[j].key) std::swap(a[i], a[j]);
-    }
-    static void insertion(KeyItem *a, int n) {
-        for (int i = 0; i < n - 1; i++) {
-            KeyItem t = a[i + 1];
-            int j = i;
-            while (j >= 0 && t.key < a[j].key) {
-                a[j + 1] = a[j];
-                j--;
-            }
-            a[j + 1] = t;
-        }
-    }
-    static void down_heap(KeyItem *a, int i, int n) {
-        KeyItem d = a[i - 1];
-        while (i <= n >> 1) {
-            int child = 2 * i;
-            if (child < n && a[child - 1].key < a[child].key) child++;
-            if (!(d.key < a[child - 1].key)) break;
-            a[i - 1] = a[child - 1];
-            i = child;
-        }
-        a[i - 1] = d;
-    }
-    static void heap(KeyItem *a, int n) {
-        for (int i = n >> 1; i >= 1; i--) down_heap(a, i, n);
-        for (int i = n; i > 1; i--) {
-            std::swap(a[0], a[i - 1]);
-            down_heap(a, 1, i - 1);
-        }
-    }
-    static int partition(KeyItem *a, int n) {
-        int hi = n - 1, mid = hi >> 1;
-        swap_if_greater(a, 0, mid);
-        swap_if_greater(a, 0, hi);
-        swap_if_greater(a, mid, hi);
-        float pivot = a[mid].key;
-        std::swap(a[mid], a[hi - 1]);
-        int left = 0, right = hi - 1;
-        while (left < right) {
-            while (pivot > a[++left].key) {}
-            while (pivot < a[--right].key) {}
-            if (left >= right) break;
-            std::swap(a[left], a[right]);
-        }
-        if (left != hi - 1) std::swap(a[left], a[hi - 1]);
-        return left;
-    }
-    static void intro(KeyItem *a, int n, int depth) {
-        int size = n;
-        while (size > 1) {
-            if (size <= 16) {
-                if (size == 2) {
-                    swap_if_greater(a, 0, 1);
-                } else if (size == 3) {
-                    swap_if_greater(a, 0, 1);
-                    swap_if_greater(a, 0, 2);
-                    swap_if_greater(a, 1, 2);
-                } else {
-                    insertion(a, size);
-                }
-                return;
-            }
-            if (depth == 0) {
-                heap(a, size);
-                return;
-            }
-            depth--;
-            int p = partition(a, size);
-            intro(a + p + 1, size - (p + 1), depth);
-            size = p;
-        }
-    }
-    static void sort(KeyItem *a, int n) {
-        if (n < 2) return;
-        int left = 0;
-        for (int i = 0; i < n; i++)
-            if (std::isnan(a[i].key)) std::swap(a[left++], a[i]);
-        if (left == n) return;
-        a += left;
-        n -= left;
-        int lg = 0;
-        for (unsigned v = (unsigned)n; v >>= 1;) lg++;
-        intro(a, n, 2 * (lg + 1));
-    }
+using ftsort::KeyItem;
+struct DotNetSort {  // see dotnet_sort.h
+    static void sort(KeyItem *a, int n) { ftsort::sort(a, n); }
 };
 
 struct FormNode {
@@ -184,7 +94,8 @@ inline float4 f4(V3 v, float w) { return float4{v.x, v.y, v.z, w}; }
 
 class Compiler {
    public:
-    Compiler(const ft_scene_desc *d, CompiledScene *out) : d_(d), out_(out) {}
+    Compiler(const ft_scene_desc *d, CompiledScene *out, GridBuildFn fn, void *ctx, long long min_pairs)
+        : d_(d), out_(out), grid_fn_(fn), grid_ctx_(ctx), gpu_min_pairs_(min_pairs) {}
 
     int run(std::string *err) {
         int st = validate();
@@ -197,6 +108,9 @@ class Compiler {
    private:
     const ft_scene_desc *d_;
     CompiledScene *out_;
+    GridBuildFn grid_fn_;
+    void *grid_ctx_;
+    long long gpu_min_pairs_;
     std::string err_;
     std::vector<FormNode> nodes_;
     std::vector<ObjNode> objs_;
@@ -280,10 +194,38 @@ class Compiler {
                     }
             }
         };
+        bool on_gpu = false;
+        if (grid_fn_ && (long long)g.n_cells * n >= gpu_min_pairs_) {  // device build: bit-identical lists (grid_build.cu)
+            std::vector<float> flat((size_t)4 * n);
+            for (int i = 0; i < n; i++) {
+                flat[4 * (size_t)i] = b[(size_t)i].c.x; flat[4 * (size_t)i + 1] = b[(size_t)i].c.y;
+                flat[4 * (size_t)i + 2] = b[(size_t)i].c.z; flat[4 * (size_t)i + 3] = b[(size_t)i].r;
+            }
+            GridBuildJob job;
+            job.bounds = flat.data(); job.n = n; job.cx = cx; job.cy = cy; job.cz = cz;
+            job.amin[0] = amin.x; job.amin[1] = amin.y; job.amin[2] = amin.z;
+            job.cell[0] = cell.x; job.cell[1] = cell.y; job.cell[2] = cell.z;
+            job.half[0] = half.x; job.half[1] = half.y; job.half[2] = half.z;
+            job.half_len = half_len;
+            GridBuildResult res;
+            std::string gerr;
+            const int st = grid_fn_(grid_ctx_, job, &res, &gerr);
+            if (st != FT_OK) return fail(st, gerr);
+            for (int64_t c = 0; c < g.n_cells; c++) {
+                centers[(size_t)c] = v3(res.centers[3 * (size_t)c], res.centers[3 * (size_t)c + 1], res.centers[3 * (size_t)c + 2]);
+                const GridKeyItem *e = res.entries.data() + res.begin[(size_t)c];
+                const size_t k = (size_t)(res.begin[(size_t)c + 1] - res.begin[(size_t)c]);
+                lists[(size_t)c].resize(k);
+                for (size_t i = 0; i < k; i++) lists[(size_t)c][i] = KeyItem{e[i].key, e[i].item};
+            }
+            on_gpu = true;
+            out_->grids_built_on_gpu++;
+        }
         unsigned hw = std::thread::hardware_concurrency();
         int nthreads = (int)std::min<unsigned>(hw ? hw : 1, 16);
         if ((int64_t)g.n_cells * n < (1 << 18)) nthreads = 1;
-        if (nthreads <= 1) {
+        if (on_gpu) {
+        } else if (nthreads <= 1) {
             work();
         } else {
             std::vector<std::thread> th;
@@ -810,8 +752,9 @@ class Compiler {
 
 }  // namespace
 
-int compile_scene(const ft_scene_desc *desc, CompiledScene *out, std::string *err) {
-    Compiler c(desc, out);
+int compile_scene(const ft_scene_desc *desc, CompiledScene *out, std::string *err, GridBuildFn grid_fn, void *grid_ctx,
+                  long long gpu_min_pairs) {
+    Compiler c(desc, out, grid_fn, grid_ctx, gpu_min_pairs);
     return c.run(err);
 }
 

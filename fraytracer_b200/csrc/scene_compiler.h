@@ -46,10 +46,31 @@ struct CompiledScene {
     int32_t chain_valid = 0, chain_n_ops = 0;
     uint32_t chain_union = 0, chain_ops = 0;
     int32_t n_nodes = 0, n_primitives = 0, max_depth = 0;
+    int32_t grids_built_on_gpu = 0;
 };
 
-// Returns FT_OK or an FT_ERR_* code with a message in `err`.
-int compile_scene(const ft_scene_desc *desc, CompiledScene *out, std::string *err);
+// Optional device backend for SdfBoundary.buildSpatialLookup (grid_build.cu): same lists, built on the GPU.
+struct GridBuildJob {
+    const float *bounds;  // n x {cx, cy, cz, r}
+    int n, cx, cy, cz;
+    float amin[3], cell[3], half[3], half_len;
+};
+struct GridKeyItem {
+    float key;
+    int32_t item;
+};
+struct GridBuildResult {
+    std::vector<float> centers;        // 3 per cell
+    std::vector<long long> begin;      // n_cells + 1
+    std::vector<GridKeyItem> entries;  // per cell: sorted {LowerBound, child position}
+};
+typedef int (*GridBuildFn)(void *ctx, const GridBuildJob &job, GridBuildResult *res, std::string *err);
+int gpu_grid_build(void *ctx /* (void*)(intptr_t)device */, const GridBuildJob &job, GridBuildResult *res, std::string *err);
+
+// Returns FT_OK or an FT_ERR_* code with a message in `err`.  Grids with at least `gpu_min_pairs` (cells x children)
+// pair tests are built by `grid_fn` when it is given.
+int compile_scene(const ft_scene_desc *desc, CompiledScene *out, std::string *err, GridBuildFn grid_fn = nullptr,
+                  void *grid_ctx = nullptr, long long gpu_min_pairs = 0);
 
 // Lens.create / Camera.lookAt (Camera.fs:10-14, 33-42)
 float lens_create(float field_of_view);

@@ -177,6 +177,8 @@ typedef struct ft_scene_info {
     int64_t device_bytes;    /* resident scene bytes in HBM                    */
     int32_t device;          /* CUDA ordinal                                   */
     int32_t sm_count;
+    int32_t grids_built_on_gpu; /* spatial lookups built by the device backend  */
+    int32_t reserved;
 } ft_scene_info;
 
 /* per-grid introspection (tests compare this against the oracle's grid) */
