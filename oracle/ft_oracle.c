@@ -295,6 +295,7 @@ typedef struct grid {
     int cx, cy, cz;
     gcell *cells; /* cells[(x*cy + y)*cz + z] as the .NET [,,] array */
     int64_t n_entries;
+    int64_t empty_cells;
 } grid;
 
 static grid *grid_build(const bnd *b, int n) {
@@ -341,6 +342,7 @@ static grid *grid_build(const bnd *b, int n) {
                 }
                 dotnet_sort_by_lower_bound(tmp, k); /* :267-268 */
                 gcell *c = &g->cells[((size_t)x * cy + y) * cz + z];
+                if (k == 0) g->empty_cells++; /* the reference would index Items.[0] of an empty array */
                 c->center = center;
                 c->n = k;
                 c->items = (gitem *)malloc(sizeof(gitem) * (size_t)(k > 0 ? k : 1));
@@ -713,6 +715,11 @@ static onode *make_composite(fto_scene *s, int kind, onode **kids, int n, float 
             nd->g = grid_build(bb, n); /* SdfForm.fs:19 */
             free(bb);
             add_grid(s, nd->g);
+            if (nd->g->empty_cells) {
+                set_err(err, errlen, "spatial lookup cell without candidates (non-finite boundary?): the reference "
+                                     "would throw IndexOutOfRangeException in SdfForm.union");
+                return NULL;
+            }
         } else {
             nd->r0 = strength;
             nd->r1 = -1.0f / strength; /* SdfForm.fs:75 */

@@ -1,0 +1,78 @@
+"""Randomised scenes (random composite trees: nested unions, subtract, intersect, smooth unions over the four
+primitives): the scene compiler against the oracle on the CPU, the kernels against the oracle on the GPU."""
+import numpy as np
+import pytest
+
+import fraytracer_b200 as ft
+from fraytracer_b200 import _abi as A
+from fraytracer_b200 import scenes
+from oracle import oracle as O
+
+from conftest import bits
+from fuzz_scenes import random_scene
+
+
+def build_both(scene, device):
+    """(tracer, oracle) or (None, None) when BOTH reject the scene for the same reason: the reference's
+    SdfBoundary.intersection radius formula (SdfBoundary.fs:48) yields NaN for some overlapping spheres, and a union
+    over such a child has empty lookup cells -- the reference itself would throw at trace time."""
+    desc = ft.SceneDescription(scene)
+    try:
+        orc = O.OracleScene(desc)
+    except ft.FrayTracerError as e:
+        assert "cell without candidates" in str(e)
+        with pytest.raises(ft.FrayTracerError, match="cell without candidates"):
+            ft.SceneTracer(scene, device=device)
+        return None, None
+    tr = ft.SceneTracer(scene, device=device)
+    return tr, O.OracleScene(tr.description)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_compiler_grids_equal_oracle(seed):
+    tr, orc = build_both(random_scene(seed, allow_smooth=True), A.FT_DEVICE_NONE)
+    if tr is None:
+        return
+    g1, g2 = tr.grids(), orc.grids()
+    assert len(g1) == len(g2)
+    for a, b in zip(g1, g2):
+        assert a["count"] == b["count"] and np.array_equal(a["item"], b["item"]) and np.array_equal(a["begin"], b["begin"])
+        assert np.array_equal(bits(a["lower_bound"]), bits(b["lower_bound"])) and np.array_equal(bits(a["centers"]), bits(b["centers"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_gpu_bit_exact(seed):
+    """no smooth unions (exp/log are not bit-reproducible across math libraries): everything must be bit-exact"""
+    cam = scenes.default_camera()
+    tracer, orc = build_both(random_scene(1000 + seed), 0)
+    if tracer is None:
+        return
+    rng = np.random.default_rng(seed)
+    pts = (rng.normal(size=(20000, 3)) * 2.5).astype(np.float32)
+    assert np.array_equal(bits(tracer.distance(pts)), bits(orc.distance(pts)))
+    X, Y = 96, 72
+    rgb, leaf, stats = tracer.render(cam, ft.ImageSize(X, Y), 0.01, 30.0, want_leaf=True)
+    ref = orc.render(cam, X, Y, 0.01, 30.0, counters=True)
+    assert np.array_equal(leaf, ref["leaf"]) and np.array_equal(bits(rgb), bits(ref["rgb"]))
+    assert stats["shadow_rays"] == ref["counters"]["shadow_rays"] and stats["capped_rays"] == 0
+    n = 3000
+    origin = (rng.normal(size=(n, 3)) * 5.0).astype(np.float32)
+    d = (rng.normal(size=(n, 3)) * 1.5 - origin).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([origin, d, np.full((n, 1), 20.0, np.float32), np.full((n, 1), 0.02, np.float32)], axis=1)
+    got, _ = tracer.trace_rays(rays)
+    want = orc.trace_rays(rays)
+    for k in ("leaf", "steps", "shadow"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(bits(got["rgb"]), bits(want["rgb"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_gpu_smooth_unions_within_tolerance(seed):
+    tracer, orc = build_both(random_scene(2000 + seed, allow_smooth=True), 0)
+    if tracer is None:
+        return
+    pts = (np.random.default_rng(seed).normal(size=(20000, 3)) * 2.5).astype(np.float32)
+    assert np.allclose(tracer.distance(pts), orc.distance(pts), rtol=5e-5, atol=5e-6)
