@@ -35,6 +35,8 @@ FT_FORM_INTERSECT = 18
 FT_FORM_UNION_SMOOTH = 19
 
 FT_MATERIAL_SOLID = 1
+FT_MATERIAL_GLASS = 2  # EXTENSION (no reference implementation): Cauchy glass, rgb = (A, B, unused)
+FT_SPECTRAL_MAX_LIGHTS = 8
 
 FT_OBJECT_LEAF = 1
 FT_OBJECT_UNION = 2
@@ -107,7 +109,7 @@ class ft_render_stats(C.Structure):
                 ("reserved", C.c_int32)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 # every symbol include/fraytracer_b200.h declares (tests check the library exports them all)
@@ -117,7 +119,7 @@ EXPORTS = [
     "ft_scene_grid_count", "ft_scene_grid_info", "ft_scene_grid_read",
     "ft_render", "ft_render_device", "ft_render_strips_device", "ft_strip_layout", "ft_deinterleave_device",
     "ft_deinterleave_strips_device",
-    "ft_trace_rays", "ft_distance",
+    "ft_trace_rays", "ft_distance", "ft_render_spectral",
     "ft_image_max_device", "ft_tonemap_device", "ft_to_bitmap", "ft_save_bitmap",
     "ft_host_register", "ft_host_unregister", "ft_host_alloc", "ft_host_free",
     "ft_measure_fp32_peak",
@@ -169,6 +171,8 @@ def load_library(path: str | None = None):
         "ft_deinterleave_device": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
         "ft_trace_rays": (C.c_int, [vp, i64, vp, u32, vp, vp, vp, vp, P(ft_render_stats)]),
         "ft_distance": (C.c_int, [vp, i64, vp, u32, vp]),
+        "ft_render_spectral": (C.c_int, [vp, P(ft_camera), i32, i32, f32, f32, i32, i32, C.c_uint64, vp,
+                                         P(ft_render_stats)]),
         "ft_image_max_device": (C.c_int, [vp, i64, vp, vp]),
         "ft_tonemap_device": (C.c_int, [vp, i32, i32, f32, vp, f32, C.c_uint64, vp, i32, vp]),
         "ft_to_bitmap": (C.c_int, [C.c_int, vp, i32, i32, f32, C.c_uint64, vp, i32]),

@@ -163,6 +163,12 @@ class SdfMaterial:
     def createSolid(color) -> "SdfMaterial":
         return SdfMaterial(A.FT_MATERIAL_SOLID, _vec3(color))
 
+    @staticmethod
+    def createGlass(cauchy_a: float, cauchy_b: float) -> "SdfMaterial":
+        """EXTENSION, not in the reference: dispersive glass with the Cauchy index
+        n(lambda) = A + B / lambda^2 (lambda in micrometres).  Only `SceneTracer.render_spectral` renders it."""
+        return SdfMaterial(A.FT_MATERIAL_GLASS, (cauchy_a, cauchy_b, 0.0))
+
 
 # --------------------------------------------------------------------------- SdfObject
 class SdfObject:
@@ -473,6 +479,23 @@ class SceneTracer:
         A.check(self.lib.ft_render(self.handle, C.byref(cam), X, Y, C.c_float(epsilon), C.c_float(length),
                                    int(flags), _ptr(out), _ptr(out_leaf), C.byref(stats)))
         return out, out_leaf, stats.as_dict()
+
+    def render_spectral(self, camera: Camera, size: ImageSize, epsilon: float, length: float, n_wavelengths: int = 16,
+                        max_bounces: int = 8, seed: int = 19, out: np.ndarray | None = None):
+        """EXTENSION (BASELINE config 3; no reference implementation): spectral ray-test with
+        dispersive glass, `n_wavelengths` frequencies per pixel.  Returns (float32 [X,Y,3], stats dict);
+        stats["shadow_rays"] counts every secondary ray (shadow rays + continuation segments), stats["reserved"]
+        the pixels whose primary ray hit glass."""
+        X, Y = int(size.X), int(size.Y)
+        if out is None:
+            out = np.empty((X, Y, 3), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == X * Y * 3
+        stats = A.ft_render_stats()
+        cam = camera.to_c()
+        A.check(self.lib.ft_render_spectral(self.handle, C.byref(cam), X, Y, C.c_float(epsilon), C.c_float(length),
+                                            int(n_wavelengths), int(max_bounces), C.c_uint64(seed), _ptr(out),
+                                            C.byref(stats)))
+        return out, stats.as_dict()
 
     def render_device(self, camera: Camera, size: ImageSize, epsilon: float, length: float, d_out_rgb: int,
                       d_out_leaf: int = 0, stream: int = 0, flags: int = 0, strip_width: int = 8,

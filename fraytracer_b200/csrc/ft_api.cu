@@ -12,6 +12,7 @@
 
 #include "kernels.h"
 #include "scene_compiler.h"
+#include "spectral.h"
 
 namespace {
 
@@ -83,6 +84,10 @@ struct ft_scene {
     // scratch for the host-pointer entry points, grown on demand
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    // second scratch (spectral extension: path queues and slots, sized after wave 0) and its wave counters
+    void *d_scratch2 = nullptr;
+    size_t scratch2_bytes = 0;
+    unsigned *d_spec_counts = nullptr, *h_spec_counts = nullptr;
     std::mutex mu;
 
     cudaError_t reserve(size_t bytes) {
@@ -94,6 +99,15 @@ struct ft_scene {
         if (e == cudaSuccess) scratch_bytes = bytes;
         return e;
     }
+    cudaError_t reserve2(size_t bytes) {
+        if (bytes <= scratch2_bytes) return cudaSuccess;
+        if (d_scratch2) cudaFree(d_scratch2);
+        d_scratch2 = nullptr;
+        scratch2_bytes = 0;
+        cudaError_t e = cudaMalloc(&d_scratch2, bytes);
+        if (e == cudaSuccess) scratch2_bytes = bytes;
+        return e;
+    }
     void release() {
         const void *ptrs[] = {dev.nodes, dev.cells, dev.entries, dev.links,
                               dev.objects, dev.obj_links, dev.materials, dev.lights};
@@ -103,6 +117,9 @@ struct ft_scene {
         if (d_counters) cudaFree(d_counters);
         if (h_stats) cudaFreeHost(h_stats);
         if (d_scratch) cudaFree(d_scratch);
+        if (d_scratch2) cudaFree(d_scratch2);
+        if (d_spec_counts) cudaFree(d_spec_counts);
+        if (h_spec_counts) cudaFreeHost(h_spec_counts);
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -431,6 +448,8 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
     if (st != FT_OK) return st;
     if (scene->device == FT_DEVICE_NONE)
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    if (scene->host.has_glass)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
     std::lock_guard<std::mutex> lock(scene->mu);
     DeviceGuard guard(scene->device);
     if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
@@ -480,6 +499,8 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
     if (st != FT_OK) return st;
     if (scene->device == FT_DEVICE_NONE)
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    if (scene->host.has_glass)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
     std::lock_guard<std::mutex> lock(scene->mu);
     DeviceGuard guard(scene->device);
     if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
@@ -571,6 +592,8 @@ FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_
     if (n == 0) return FT_OK;
     if (scene->device == FT_DEVICE_NONE)
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    if (scene->host.has_glass)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
     std::lock_guard<std::mutex> lock(scene->mu);
     DeviceGuard guard(scene->device);
     if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
@@ -632,6 +655,114 @@ FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint3
     if (e != cudaSuccess) return cuda_fail(e, "distance kernel launch");
     CU(cudaMemcpyAsync(out_distance, d_out, N * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    return FT_OK;
+}
+
+FT_API int ft_render_spectral(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                              float length, int32_t n_wavelengths, int32_t max_bounces, uint64_t seed, float *out_rgb,
+                              ft_render_stats *stats) {
+    if (!scene || !camera || !out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (width <= 0 || height <= 0 || (int64_t)width * height >= ((int64_t)1 << 31))
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size");
+    if (n_wavelengths < 1 || n_wavelengths > 64) return fail(FT_ERR_INVALID_ARGUMENT, "n_wavelengths must be in 1..64");
+    if (max_bounces < 0 || max_bounces > 256) return fail(FT_ERR_INVALID_ARGUMENT, "max_bounces must be in 0..256");
+    int st = check_ray_params(epsilon, length);
+    if (st != FT_OK) return st;
+    if (scene->host.n_lights > FT_SPECTRAL_MAX_LIGHTS)
+        return fail(FT_ERR_INVALID_ARGUMENT, "ft_render_spectral supports at most FT_SPECTRAL_MAX_LIGHTS lights");
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    const size_t npix = (size_t)width * height;
+    const size_t rgb_bytes = (npix * 3 * sizeof(float) + 255) & ~(size_t)255;
+    CU(scene->reserve(rgb_bytes + npix * 3 * sizeof(float4)));  // image + worst-case hit queue
+    if (!scene->d_spec_counts) {
+        CU(cudaMalloc(&scene->d_spec_counts, 512 * sizeof(unsigned)));
+        CU(cudaMallocHost(&scene->h_spec_counts, 512 * sizeof(unsigned)));
+    }
+    cudaStream_t s = scene->stream;
+    SpectralParams P{};
+    P.cam = *camera;
+    P.width = width;
+    P.height = height;
+    P.epsilon = epsilon;
+    P.length = length;
+    P.max_size = (float)std::max(width, height);
+    P.nl = n_wavelengths;
+    P.max_bounces = max_bounces;
+    P.seed_lo = (uint32_t)seed;
+    P.seed_hi = (uint32_t)(seed >> 32);
+    P.n_items = (long long)((width + 3) / 4) * ((height + 7) / 8) * 32;
+    P.out_rgb = (float *)scene->d_scratch;
+    P.hit_q = (float4 *)((char *)scene->d_scratch + rgb_bytes);
+    unsigned *counts = scene->d_spec_counts;  // [0] glass hits, [1 + w] live paths entering wave w
+    P.hit_count = counts;
+    P.stats = scene->d_stats;
+    CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(counts, 0, 512 * sizeof(unsigned), s));
+    CU(cudaEventRecord(scene->ev[0], s));
+    int launches = 0;
+    // ---- wave 0: primary rays
+    P.wave = 0;
+    CU(fresh_counter(scene, s, &P.work_counter));
+    cudaError_t e = spectral_launch_primary(scene->dev, P, scene->sm_count, s);
+    if (e != cudaSuccess) return cuda_fail(e, "spectral primary kernel launch");
+    launches++;
+    CU(cudaMemcpyAsync(scene->h_spec_counts, counts, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));  // the one host round trip: the path queues are sized by the glass hit count
+    const unsigned n_hits = scene->h_spec_counts[0];
+    const unsigned long long n_paths0 = (unsigned long long)n_hits * (unsigned)n_wavelengths;
+    if (n_paths0 >= (1ull << 31)) return fail(FT_ERR_INVALID_ARGUMENT, "too many spectral paths for one call (>= 2^31)");
+    if (n_hits > 0) {
+        const size_t slot_bytes = (n_paths0 * sizeof(float) + 255) & ~(size_t)255;
+        const size_t q_bytes = max_bounces > 0 ? n_paths0 * 3 * sizeof(float4) : 0;
+        CU(scene->reserve2(slot_bytes + 2 * q_bytes));
+        P.slots = (float *)scene->d_scratch2;
+        float4 *qa = (float4 *)((char *)scene->d_scratch2 + slot_bytes), *qb = (float4 *)((char *)qa + q_bytes);
+        // ---- the material stage of wave 0
+        P.out_q = qa;
+        e = spectral_launch_spawn(scene->dev, P, n_hits, s);
+        if (e != cudaSuccess) return cuda_fail(e, "spectral spawn kernel launch");
+        launches++;
+        if (max_bounces > 0) {
+            scene->h_spec_counts[1] = (unsigned)n_paths0;  // pinned
+            CU(cudaMemcpyAsync(counts + 1, scene->h_spec_counts + 1, sizeof(unsigned), cudaMemcpyHostToDevice, s));
+            // ---- waves 1 .. max_bounces (a wave whose queue is empty exits at once)
+            for (int w = 1; w <= max_bounces; w++) {
+                P.wave = w;
+                P.in_q = (w & 1) ? qa : qb;
+                P.out_q = (w & 1) ? qb : qa;
+                P.in_count = counts + w;
+                P.out_count = counts + w + 1;
+                CU(fresh_counter(scene, s, &P.work_counter));
+                e = spectral_launch_wave(scene->dev, P, (long long)n_paths0, scene->sm_count, s);
+                if (e != cudaSuccess) return cuda_fail(e, "spectral wave kernel launch");
+                launches++;
+            }
+        }
+        e = spectral_launch_resolve(P, n_hits, s);
+        if (e != cudaSuccess) return cuda_fail(e, "spectral resolve kernel launch");
+        launches++;
+    }
+    CU(cudaEventRecord(scene->ev[1], s));
+    CU(cudaMemcpyAsync(out_rgb, P.out_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(scene->ev[2], s));
+    CU(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        sum_stats(scene->h_stats, stats);
+        unsigned long long paths = 0;
+        for (int k = 0; k < FT_STAT_SLOTS; k++) paths += scene->h_stats[(size_t)k * FT_STAT_STRIDE + FT_STAT_PATHS];
+        stats->primary_rays = (int64_t)npix;
+        stats->shadow_rays += (int64_t)paths;  // every secondary ray: shadow rays + continuation segments
+        stats->reserved = (int32_t)n_hits;     // pixels whose primary ray hit glass
+        stats->launches = launches;
+        cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
+        cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
+    }
     return FT_OK;
 }
 

@@ -13,6 +13,7 @@
 #define FT_STAT_STEPS 3
 #define FT_STAT_FLOPS 4
 #define FT_STAT_ESCAPED 5
+#define FT_STAT_PATHS 6  // spectral extension: continuation path segments marched
 
 struct RenderParams {
     int width, height;   // image X, Y

@@ -16,26 +16,9 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "philox.h"
 
 namespace {
-
-__host__ __device__ inline uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t *hi) {
-    const unsigned long long p = (unsigned long long)a * b;
-    *hi = (uint32_t)(p >> 32);
-    return (uint32_t)p;
-}
-
-// Philox4x32-10 (Salmon et al., SC'11)
-__host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-    for (int r = 0; r < 10; r++) {
-        uint32_t hi0, hi1;
-        const uint32_t lo0 = mulhilo(0xD2511F53u, c[0], &hi0), lo1 = mulhilo(0xCD9E8D57u, c[2], &hi1);
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
 
 __device__ inline float atomic_max_float(float *addr, float v) {  // v >= 0 in practice; handles any non-NaN
     int *ia = (int *)addr;
@@ -87,7 +70,7 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const float *__restrict__ 
         if (x < X && y < Y) {
             const long long idx = (long long)x * Y + y;
             uint32_t c[4] = {(uint32_t)idx, (uint32_t)((unsigned long long)idx >> 32), 0u, 0u};
-            philox4x32_10(c, k0, k1);
+            ft_philox4x32_10(c, k0, k1);
             const float r = __ldg(rgb + 3 * idx), g = __ldg(rgb + 3 * idx + 1), b = __ldg(rgb + 3 * idx + 2);
             tile[ty][3 * tx + 2] = to_byte(r, inv_gamma, mx, c[0]);  // draws in R, G, B order (FColor.fs:44-46)
             tile[ty][3 * tx + 1] = to_byte(g, inv_gamma, mx, c[1]);

@@ -429,12 +429,13 @@ class Compiler {
             case FT_OBJECT_LEAF: {  // SdfObject.fs:6-10
                 if (od.material < 0 || od.material >= d_->n_materials)
                     return fail(FT_ERR_INVALID_ARGUMENT, "material id out of range");
-                if (d_->materials[od.material].kind != FT_MATERIAL_SOLID)
+                if (d_->materials[od.material].kind != FT_MATERIAL_SOLID && d_->materials[od.material].kind != FT_MATERIAL_GLASS)
                     return fail(FT_ERR_UNSUPPORTED_NODE, "unsupported material kind (user-written closures cannot "
                                                          "run on the device)");
                 int st = build_form(od.form, 0, &o.form);
                 if (st != FT_OK) return st;
                 o.material = od.material;
+                if (d_->materials[od.material].kind == FT_MATERIAL_GLASS) out_->has_glass = 1;
                 break;
             }
             case FT_OBJECT_UNION: {  // SdfObject.fs:12-48
@@ -692,7 +693,8 @@ class Compiler {
         o.root_word = nodes_[(size_t)objs_[(size_t)o.root_object].form].word;
         // 5. materials, lights, background
         for (int i = 0; i < d_->n_materials; i++)
-            o.materials.push_back(f4(d_->materials[i].rgb[0], d_->materials[i].rgb[1], d_->materials[i].rgb[2], 0.f));
+            o.materials.push_back(f4(d_->materials[i].rgb[0], d_->materials[i].rgb[1], d_->materials[i].rgb[2],
+                                     as_float((uint32_t)d_->materials[i].kind)));
         if (o.materials.empty()) o.materials.push_back(f4(0, 0, 0, 0));
         for (int i = 0; i < d_->n_lights; i++) {
             const ft_light_desc &l = d_->lights[i];

@@ -5,6 +5,7 @@ same draw order, same float32 arithmetic.
 config 1  default_scene()           Program.fs verbatim: 1000 tori, intersect sphere 3.5, subtract sphere 2.5
 config 2  spheres_capsules_scene()  512 randomSphere + 512 randomCapsule in one union (capsule stands in
                                     for the reference's non-existent cone), 1920x1080
+config 3  spectral_glass_scene()    EXTENSION (no reference): config-2 generator, every 3rd object dispersive glass
 config 5  mixed_scene()             256 each torus/sphere/capsule/triangle in one union, 7680x4320
 """
 from __future__ import annotations
@@ -119,3 +120,23 @@ def mixed_scene(seed: int = 19, n_each: int = 256, width: int = 7680, height: in
     scene = SdfScene(Object=SdfObject.union(objs), BackgroundColor=FColor.ofRGB(0.1, 0.1, 0.1),
                      Lights=default_lights())
     return Workload("config5_mixed_1024_8k", scene, default_camera(), ImageSize(width, height), 0.01, 30.0, objs)
+
+
+# BK7-like Cauchy coefficients with the dispersion term exaggerated 10x so that the colour split is visible at
+# image scale (n = 1.5046 + 0.042 / lambda^2, lambda in micrometres)
+GLASS_CAUCHY = (1.5046, 0.042)
+
+
+def spectral_glass_scene(seed: int = 19, n_spheres: int = 192, n_capsules: int = 192, glass_every: int = 3,
+                         width: int = 3840, height: int = 2160) -> Workload:
+    """config 3 -- EXTENSION, no reference implementation: the config-2 generator
+    (Program.fs:32-46 helpers, same System.Random stream) where every `glass_every`-th object is dispersive glass,
+    lit by a white directional and a white point light."""
+    b = SceneBuilder(seed)
+    objs = [b.randomSphere() for _ in range(n_spheres)] + [b.randomCapsule() for _ in range(n_capsules)]
+    glass = SdfMaterial.createGlass(*GLASS_CAUCHY)
+    objs = [SdfObject.create(glass, o.form) if i % glass_every == 0 else o for i, o in enumerate(objs)]
+    lights = [SdfLight.directional((-0.5, -1.0, 1.0), FColor.ofRGB(2.0, 2.0, 2.0)),
+              SdfLight.point((-0.5, 0.0, -2.0), FColor.ofRGB(10.0, 10.0, 10.0))]
+    scene = SdfScene(Object=SdfObject.union(objs), BackgroundColor=FColor.ofRGB(0.3, 0.4, 0.6), Lights=lights)
+    return Workload("config3_spectral_glass_4k", scene, default_camera(), ImageSize(width, height), 0.01, 30.0, objs)

@@ -90,7 +90,10 @@ typedef struct ft_form_desc {
 
 /* ---- materials: mirror SdfMaterial (SdfMaterial.fs:4-10) ---------------- */
 enum {
-    FT_MATERIAL_SOLID = 1 /* SdfMaterial.createSolid color                     */
+    FT_MATERIAL_SOLID = 1, /* SdfMaterial.createSolid color                    */
+    /* EXTENSION (no reference implementation): dispersive glass, rgb = {A, B, unused} of the Cauchy
+     * index n = A + B / lambda^2 (lambda in micrometres).  Only ft_render_spectral accepts scenes that use it.     */
+    FT_MATERIAL_GLASS = 2
 };
 
 typedef struct ft_material_desc {
@@ -313,6 +316,18 @@ FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_
  * -- the closure every march step calls (Types.fs:42).                      */
 FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint32_t flags,
                        float *out_distance);
+
+/* ---- EXTENSION: spectral / refractive ray-test (BASELINE config 3) ------------------------------------------
+ * No reference implementation exists: builder-defined spec in DESIGN.md 4.6, anchored in
+ * the reference's dead code Light.fresnel (Light.fs:30-59) and Light.Colors (Light.fs:12-26).  n_wavelengths
+ * frequencies per pixel (midpoints of equal strata of 400..789 THz), glass interactions chosen by
+ * Philox4x32-10(seed; pixel, wavelength, bounce), at most max_bounces of them per path.  Wavefront pipeline on the
+ * device; out_rgb is a HOST FColor[X,Y].  stats->launches counts the kernels, stats->shadow_rays every secondary
+ * ray (shadow rays + continuation path segments), stats->reserved the pixels whose primary ray hit glass.       */
+#define FT_SPECTRAL_MAX_LIGHTS 8
+FT_API int ft_render_spectral(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                              float length, int32_t n_wavelengths, int32_t max_bounces, uint64_t seed,
+                              float *out_rgb, ft_render_stats *stats);
 
 /* ---- post-process: Image.toColors / toBitmap / saveBitmap (Image.fs:37-90) -- */
 /* max over the n_floats values of an FColor image (Array2D.Parallel.maxWith FColor.getMaxColor, Image.fs:40-42);

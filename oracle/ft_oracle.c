@@ -550,6 +550,7 @@ typedef struct fto_scene {
     int n_owned_obj;
     olight *lights;
     v3 *material_rgb;
+    int *material_kind;
     v3 background;
     oobj *root;
     grid **grids; int n_grids, cap_grids; /* form-union grids in creation order, for tests */
@@ -892,7 +893,7 @@ FTO_API void fto_scene_destroy(fto_scene *s) {
         free(s->owned_obj[i]);
     }
     free(s->owned); free(s->owned_obj); free(s->forms); free(s->objects);
-    free(s->lights); free(s->material_rgb); free(s->grids);
+    free(s->lights); free(s->material_rgb); free(s->material_kind); free(s->grids);
     free(s);
 }
 
@@ -905,10 +906,13 @@ FTO_API int fto_scene_create(const ft_scene_desc *d, fto_scene **out, char *err,
     s->objects = (oobj **)calloc((size_t)d->n_objects + 1, sizeof(oobj *));
     s->owned_obj = (oobj **)calloc((size_t)d->n_objects + 1, sizeof(oobj *));
     s->material_rgb = (v3 *)calloc((size_t)d->n_materials + 1, sizeof(v3));
+    s->material_kind = (int *)calloc((size_t)d->n_materials + 1, sizeof(int));
     s->lights = (olight *)calloc((size_t)d->n_lights + 1, sizeof(olight));
     s->step_cap = (int64_t)1 << 22;
-    for (int i = 0; i < d->n_materials; i++)
+    for (int i = 0; i < d->n_materials; i++) {
         s->material_rgb[i] = V(d->materials[i].rgb[0], d->materials[i].rgb[1], d->materials[i].rgb[2]);
+        s->material_kind[i] = d->materials[i].kind;
+    }
     for (int i = 0; i < d->n_lights; i++) {
         const ft_light_desc *l = &d->lights[i];
         s->lights[i].kind = l->kind;
@@ -1200,4 +1204,205 @@ FTO_API float fto_to_bitmap(const float *rgb, int X, int Y, float gamma, uint64_
             p[0] = to_byte(rgb[3 * idx + 2], inv_gamma, mx, c[2]);
         }
     return raw;
+}
+
+/* ------------------------------------------------------------------------ */
+/* EXTENSION: spectral / refractive ray-test.  NOT reference behaviour: the reference has no   */
+/* wavelengths, glass or material-spawned rays.  This is the CPU restatement of this repository's own spec,    */
+/* anchored in the reference's dead code Light.fresnel (Light.fs:30-59) and Light.Colors (Light.fs:12-26).     */
+/* ------------------------------------------------------------------------ */
+static void band_weight(float nu, float w[3]) { /* Light.fs:21-26, frequencies in THz */
+    if (nu < 484.0f) { w[0] = 1.0f; w[1] = 0.0f; w[2] = 0.0f; }        /* red    */
+    else if (nu < 508.0f) { w[0] = 1.0f; w[1] = 0.5f; w[2] = 0.0f; }   /* orange */
+    else if (nu < 526.0f) { w[0] = 1.0f; w[1] = 1.0f; w[2] = 0.0f; }   /* yellow */
+    else if (nu < 606.0f) { w[0] = 0.0f; w[1] = 1.0f; w[2] = 0.0f; }   /* green  */
+    else if (nu < 668.0f) { w[0] = 0.0f; w[1] = 0.0f; w[2] = 1.0f; }   /* blue   */
+    else { w[0] = 0.5f; w[1] = 0.0f; w[2] = 1.0f; }                    /* violet */
+}
+static float spec(v3 rgb, float nu) {
+    float w[3];
+    band_weight(nu, w);
+    return ((rgb.x * w[0] + rgb.y * w[1]) + rgb.z * w[2]) / ((w[0] + w[1]) + w[2]);
+}
+static float wavelength_nu(int k, int n) { return 400.0f + 389.0f * (((float)k + 0.5f) / (float)n); }
+
+/* The spectral march.  Primary and shadow rays (armed = 1) are SdfForm.tryTrace as the reference writes it.
+ * Continuation rays (armed = 0) start 2 epsilon off the surface they come from: while |Distance| < epsilon they step by
+ * epsilon; the first evaluation with |Distance| >= epsilon arms the ray and fixes its medium -- inside glass
+ * (Distance < 0: the march continues on -Distance) or outside.  *inside_out receives the medium. */
+static int march_signed(const fto_scene *s, oray ray, int armed, oray *hit, int *inside_out) {
+    int64_t steps = 0;
+    float sign = 1.0f;
+    for (;;) {
+        if (ray.length <= 0.0f) break;
+        if (steps >= s->step_cap) break;
+        float D = form_distance(s->root->form, ray.origin);
+        steps++;
+        if (armed) {
+            float d = sign * D;
+            if (d < ray.epsilon) { *hit = ray; *inside_out = sign < 0.0f; return 1; }
+            ray = ray_move(ray, d);
+        } else {
+            sign = D < 0.0f ? -1.0f : 1.0f;
+            float d = sign * D;
+            if (d >= ray.epsilon) { armed = 1; ray = ray_move(ray, d); }
+            else ray = ray_move(ray, ray.epsilon);
+        }
+    }
+    *inside_out = sign < 0.0f;
+    return 0;
+}
+
+typedef struct { int n; float lcos[FT_SPECTRAL_MAX_LIGHTS]; v3 intensity[FT_SPECTRAL_MAX_LIGHTS]; } lit_set;
+
+/* which lights reach the hit (the reference's light loop, SdfScene.fs:13-26), wavelength independent */
+static void gather_lights(const fto_scene *s, const oray *hit, v3 normal, int inside, lit_set *ls) {
+    oray moved = ray_move(*hit, -hit->epsilon); /* SdfObject.fs:73 */
+    v3 pos = moved.origin;
+    ls->n = 0;
+    for (int l = 0; l < s->n_lights; l++) {
+        const olight *lt = &s->lights[l];
+        v3 ldir = (lt->kind == FT_LIGHT_DIRECTIONAL) ? lt->v : vnormalize(vsub(lt->v, pos));
+        float lcos = vdot(normal, ldir);
+        if (!(lcos > 0.0f)) continue;
+        oray sr;
+        v3 intensity;
+        sr.origin = pos;
+        sr.epsilon = hit->epsilon;
+        if (lt->kind == FT_LIGHT_DIRECTIONAL) { sr.direction = lt->v; sr.length = 1000.0f; intensity = lt->color; }
+        else {
+            v3 diff = vsub(lt->v, pos);
+            float d2 = vlen2(diff);
+            sr.direction = vdiv(diff, d2);
+            sr.length = sqrtf(d2);
+            intensity = vdiv(lt->color, d2);
+        }
+        int shadowed = 0;
+        if (!inside) { oray dummy; int dm; shadowed = march_signed(s, sr, 1, &dummy, &dm); }
+        if (!shadowed) { ls->lcos[ls->n] = lcos; ls->intensity[ls->n] = intensity; ls->n++; }
+    }
+}
+static float shade_solid(const fto_scene *s, v3 albedo, const lit_set *ls, float nu) {
+    float lc = spec(s->background, nu); /* SdfScene.fs:12 */
+    for (int i = 0; i < ls->n; i++) lc = lc + spec(ls->intensity[i], nu) * ls->lcos[i];
+    const float pi_inv = 1.0f / 3.14159274f;
+    return spec(albedo, nu) * (lc * pi_inv); /* SdfScene.fs:28 */
+}
+
+/* Light.fresnel n1 n2 normal direction (Light.fs:30-59) as written + the choice of the continuation */
+static void glass_interact(const fto_scene *s, v3 ab, float nu, uint64_t seed, uint32_t pixel, uint32_t k, uint32_t bounce,
+                           const oray *hit, v3 normal, int inside, oray *next) {
+    (void)s;
+    float lam = 299.792458f / nu;
+    float nn = ab.x + ab.y / (lam * lam);
+    float n1 = inside ? nn : 1.0f, n2 = inside ? 1.0f : nn;
+    v3 d = hit->direction;
+    v3 N = vdot(normal, d) > 0.0f ? normal : vneg(normal);
+    float n1n2 = n1 / n2;
+    float cosi = vdot(N, d);
+    float n1n2cosi = n1n2 * cosi;
+    float cost = sqrtf(1.0f + n1n2cosi * cosi - n1n2);
+    float reflectance = 1.0f;
+    if (!isnan(cost)) {
+        float a = n2 * cosi, b = n1 * cost;
+        float x = (a - b) / (a + b);
+        float rs = x * x;
+        a = n1 * cosi; b = n2 * cost;
+        x = (a - b) / (a + b);
+        float rp = x * x;
+        reflectance = 0.5f * (rs + rp);
+    }
+    uint32_t c[4] = {pixel, k, bounce, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float u = (float)((double)c[0] * (1.0 / 4294967296.0));
+    v3 nd;
+    if (u < reflectance) nd = vnormalize(vsub(d, vscale(N, 2.0f * cosi)));
+    else nd = vnormalize(vadd(vscale(d, n1n2), vscale(N, n1n2cosi - cost)));
+    next->origin = vadd(hit->origin, vscale(nd, 2.0f * hit->epsilon));
+    next->direction = nd;
+    next->length = hit->length - 2.0f * hit->epsilon;
+    next->epsilon = hit->epsilon;
+}
+
+typedef struct {
+    const fto_scene *s; const ft_camera *cam; int W, H; float eps, len; int nl, max_bounces; uint64_t seed;
+    float *out; volatile int64_t next;
+} sjob;
+
+static void spectral_pixel(const sjob *j, int x, int y, float *rgb) {
+    const fto_scene *s = j->s;
+    const int nl = j->nl;
+    uint32_t pixel = (uint32_t)((int64_t)x * j->H + y);
+    float L[64];
+    oray ray = pixel_ray(j->cam, x, y, j->W, j->H, j->eps, j->len), hit;
+    /* wave 0: one primary ray for all wavelengths */
+    int inside0;
+    if (!march_signed(s, ray, 1, &hit, &inside0)) {
+        for (int k = 0; k < nl; k++) L[k] = spec(s->background, wavelength_nu(k, nl));
+    } else {
+        v3 normal = form_normal_from_ray(s->root->form, &hit);
+        const oobj *leaf = object_material_leaf(s->root, hit.origin);
+        if (s->material_kind[leaf->material] != FT_MATERIAL_GLASS) {
+            lit_set ls;
+            gather_lights(s, &hit, normal, 0, &ls);
+            for (int k = 0; k < nl; k++) L[k] = shade_solid(s, s->material_rgb[leaf->material], &ls, wavelength_nu(k, nl));
+        } else {
+            for (int k = 0; k < nl; k++) { /* one continuation path per wavelength */
+                float nu = wavelength_nu(k, nl);
+                int inside = 0;
+                oray cur_hit = hit;
+                v3 cur_normal = normal;
+                v3 ab = s->material_rgb[leaf->material];
+                float val = 0.0f;
+                for (uint32_t bounce = 0;; bounce++) {
+                    if ((int)bounce >= j->max_bounces) { val = 0.0f; break; }
+                    oray nxt;
+                    glass_interact(s, ab, nu, j->seed, pixel, (uint32_t)k, bounce, &cur_hit, cur_normal, inside, &nxt);
+                    if (!march_signed(s, nxt, 0, &cur_hit, &inside)) { val = spec(s->background, nu); break; }
+                    cur_normal = form_normal_from_ray(s->root->form, &cur_hit);
+                    const oobj *lf = object_material_leaf(s->root, cur_hit.origin);
+                    if (s->material_kind[lf->material] != FT_MATERIAL_GLASS) {
+                        lit_set ls;
+                        gather_lights(s, &cur_hit, cur_normal, inside, &ls);
+                        val = shade_solid(s, s->material_rgb[lf->material], &ls, nu);
+                        break;
+                    }
+                    ab = s->material_rgb[lf->material];
+                }
+                L[k] = val;
+            }
+        }
+    }
+    float acc[3] = {0, 0, 0}, den[3] = {0, 0, 0};
+    for (int k = 0; k < nl; k++) {
+        float w[3];
+        band_weight(wavelength_nu(k, nl), w);
+        for (int c = 0; c < 3; c++) { acc[c] = acc[c] + w[c] * L[k]; den[c] = den[c] + w[c]; }
+    }
+    for (int c = 0; c < 3; c++) rgb[c] = den[c] > 0.0f ? acc[c] / den[c] : 0.0f;
+}
+static void *spectral_worker(void *arg) {
+    sjob *j = (sjob *)arg;
+    for (;;) {
+        int64_t x = __sync_fetch_and_add(&j->next, 1);
+        if (x >= j->W) break;
+        for (int y = 0; y < j->H; y++) spectral_pixel(j, (int)x, y, j->out + 3 * ((int64_t)x * j->H + y));
+    }
+    return NULL;
+}
+FTO_API int fto_render_spectral(const fto_scene *s, const ft_camera *cam, int W, int H, float eps, float len, int n_wavelengths,
+                                int max_bounces, uint64_t seed, int threads, float *out_rgb) {
+    if (!s || !cam || !out_rgb || W <= 0 || H <= 0 || n_wavelengths < 1 || n_wavelengths > 64 || max_bounces < 0 ||
+        s->n_lights > FT_SPECTRAL_MAX_LIGHTS)
+        return FT_ERR_INVALID_ARGUMENT;
+    sjob j;
+    memset(&j, 0, sizeof(j));
+    j.s = s; j.cam = cam; j.W = W; j.H = H; j.eps = eps; j.len = len; j.nl = n_wavelengths; j.max_bounces = max_bounces;
+    j.seed = seed; j.out = out_rgb; j.next = 0;
+    if (threads < 1) threads = 1;
+    pthread_t *t = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    for (int i = 0; i < threads; i++) pthread_create(&t[i], NULL, spectral_worker, &j);
+    for (int i = 0; i < threads; i++) pthread_join(t[i], NULL);
+    free(t);
+    return FT_OK;
 }

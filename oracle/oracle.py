@@ -73,6 +73,8 @@ def lib():
         L.fto_form_boundary.argtypes = [vp, C.c_int, vp]
         L.fto_root_boundary.argtypes = [vp, vp]
         L.fto_philox4x32_10.argtypes = [vp, vp, vp]
+        L.fto_render_spectral.argtypes = [vp, P(A.ft_camera), C.c_int, C.c_int, f32, f32, C.c_int, C.c_int, C.c_uint64,
+                                          C.c_int, vp]
         L.fto_to_bitmap.restype = f32
         L.fto_to_bitmap.argtypes = [vp, C.c_int, C.c_int, f32, C.c_uint64, vp, C.c_int]
         _lib = L
@@ -170,6 +172,15 @@ class OracleScene:
         if counters:
             out["counters"] = ctr.as_dict()
         return out
+
+    def render_spectral(self, camera, X, Y, eps, length, n_wavelengths=16, max_bounces=8, seed=19, threads=None):
+        """EXTENSION (no reference implementation): CPU restatement of ft_render_spectral"""
+        cam = camera.to_c() if hasattr(camera, "to_c") else camera
+        rgb = np.zeros((X, Y, 3), np.float32)
+        st = lib().fto_render_spectral(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), n_wavelengths,
+                                       max_bounces, C.c_uint64(seed), threads or os.cpu_count() or 1, _ptr(rgb))
+        assert st == 0, st
+        return rgb
 
     def trace_rays(self, rays, threads=None, counters=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
