@@ -6,11 +6,11 @@ API over that ABI.  There is no CPU fallback.
 """
 from ._abi import (FT_FLAG_COUNTERS, FT_FLAG_DEFAULT, FT_FLAG_FAST_MATH, FrayTracerError, load_library)
 from . import distributed  # noqa: F401
-from .api import (Camera, FColor, Image, ImageSize, Lens, Ray, SceneDescription, SceneTracer, SdfForm,
+from .api import (Camera, CloudParams, FColor, Image, ImageSize, Lens, Ray, SceneDescription, SceneTracer, SdfForm,
                   SdfLight, SdfMaterial, SdfObject, SdfScene)
 
 __all__ = [
-    "Camera", "FColor", "Image", "ImageSize", "Lens", "Ray", "SceneDescription", "SceneTracer", "SdfForm",
+    "Camera", "CloudParams", "FColor", "Image", "ImageSize", "Lens", "Ray", "SceneDescription", "SceneTracer", "SdfForm",
     "SdfLight", "SdfMaterial", "SdfObject", "SdfScene", "FrayTracerError", "load_library",
     "FT_FLAG_DEFAULT", "FT_FLAG_COUNTERS", "FT_FLAG_FAST_MATH",
 ]

@@ -37,6 +37,7 @@ FT_FORM_UNION_SMOOTH = 19
 FT_MATERIAL_SOLID = 1
 FT_MATERIAL_GLASS = 2  # EXTENSION (no reference implementation): Cauchy glass, rgb = (A, B, unused)
 FT_SPECTRAL_MAX_LIGHTS = 8
+FT_MATERIAL_CLOUD = 3  # EXTENSION (no reference implementation): participating medium, rgb = albedo
 
 FT_OBJECT_LEAF = 1
 FT_OBJECT_UNION = 2
@@ -101,6 +102,12 @@ class ft_grid_info(C.Structure):
                 ("n_entries", C.c_int64)]
 
 
+class ft_cloud_params(C.Structure):
+    _fields_ = [("density", C.c_float), ("frequency", C.c_float), ("step", C.c_float), ("fade", C.c_float),
+                ("bias", C.c_float), ("gain", C.c_float), ("perm", C.POINTER(C.c_int32)),
+                ("gradients", C.POINTER(C.c_double))]
+
+
 class ft_render_stats(C.Structure):
     _fields_ = [("primary_rays", C.c_int64), ("primary_hits", C.c_int64), ("shadow_rays", C.c_int64),
                 ("capped_rays", C.c_int64), ("march_steps", C.c_int64), ("eval_flops", C.c_int64),
@@ -119,7 +126,7 @@ EXPORTS = [
     "ft_scene_grid_count", "ft_scene_grid_info", "ft_scene_grid_read",
     "ft_render", "ft_render_device", "ft_render_strips_device", "ft_strip_layout", "ft_deinterleave_device",
     "ft_deinterleave_strips_device",
-    "ft_trace_rays", "ft_distance", "ft_render_spectral",
+    "ft_trace_rays", "ft_distance", "ft_render_spectral", "ft_render_cloud",
     "ft_image_max_device", "ft_tonemap_device", "ft_to_bitmap", "ft_save_bitmap",
     "ft_host_register", "ft_host_unregister", "ft_host_alloc", "ft_host_free",
     "ft_measure_fp32_peak",
@@ -173,6 +180,8 @@ def load_library(path: str | None = None):
         "ft_distance": (C.c_int, [vp, i64, vp, u32, vp]),
         "ft_render_spectral": (C.c_int, [vp, P(ft_camera), i32, i32, f32, f32, i32, i32, C.c_uint64, vp,
                                          P(ft_render_stats)]),
+        "ft_render_cloud": (C.c_int, [vp, P(ft_camera), i32, i32, f32, f32, P(ft_cloud_params), i32, C.c_uint64, vp,
+                                      P(ft_render_stats)]),
         "ft_image_max_device": (C.c_int, [vp, i64, vp, vp]),
         "ft_tonemap_device": (C.c_int, [vp, i32, i32, f32, vp, f32, C.c_uint64, vp, i32, vp]),
         "ft_to_bitmap": (C.c_int, [C.c_int, vp, i32, i32, f32, C.c_uint64, vp, i32]),

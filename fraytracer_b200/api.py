@@ -164,6 +164,12 @@ class SdfMaterial:
         return SdfMaterial(A.FT_MATERIAL_SOLID, _vec3(color))
 
     @staticmethod
+    def createCloud(albedo) -> "SdfMaterial":
+        """EXTENSION, not in the reference: participating medium bounded by the object's form, `albedo`
+        its single-scattering colour.  Only `SceneTracer.render_cloud` renders it."""
+        return SdfMaterial(A.FT_MATERIAL_CLOUD, _vec3(albedo))
+
+    @staticmethod
     def createGlass(cauchy_a: float, cauchy_b: float) -> "SdfMaterial":
         """EXTENSION, not in the reference: dispersive glass with the Cauchy index
         n(lambda) = A + B / lambda^2 (lambda in micrometres).  Only `SceneTracer.render_spectral` renders it."""
@@ -497,6 +503,24 @@ class SceneTracer:
                                             C.byref(stats)))
         return out, stats.as_dict()
 
+    def render_cloud(self, camera: Camera, size: ImageSize, epsilon: float, length: float, cloud: "CloudParams",
+                     samples_per_pixel: int = 64, seed: int = 19, out: np.ndarray | None = None):
+        """EXTENSION (BASELINE config 4; no reference implementation): stochastic volumetric render,
+        `samples_per_pixel` jittered samples per pixel.  Returns (float32 [X,Y,3] mean image, stats dict):
+        stats["shadow_rays"] counts every secondary march (shadow rays, continuation segments, light tracks),
+        stats["march_steps"] the tracking steps, stats["reserved"] the samples that scattered inside a cloud."""
+        X, Y = int(size.X), int(size.Y)
+        if out is None:
+            out = np.empty((X, Y, 3), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == X * Y * 3
+        stats = A.ft_render_stats()
+        cam = camera.to_c()
+        cp = cloud.to_c()
+        A.check(self.lib.ft_render_cloud(self.handle, C.byref(cam), X, Y, C.c_float(epsilon), C.c_float(length),
+                                         C.byref(cp), int(samples_per_pixel), C.c_uint64(seed), _ptr(out),
+                                         C.byref(stats)))
+        return out, stats.as_dict()
+
     def render_device(self, camera: Camera, size: ImageSize, epsilon: float, length: float, d_out_rgb: int,
                       d_out_leaf: int = 0, stream: int = 0, flags: int = 0, strip_width: int = 8,
                       rank: int = 0, world: int = 1, want_stats: bool = False, first_local_strip: int = 0,
@@ -538,6 +562,55 @@ class SceneTracer:
         """the reference's `Ray -> FColor`"""
         res, _ = self.trace_rays(ray.as_row()[None, :])
         return tuple(float(x) for x in res["rgb"][0])
+
+
+class CloudParams:
+    """EXTENSION: parameters of the cloud medium plus the two tables of the reference's dead-code lattice
+    noise (Noise.fs): `gradients` is Noise.gradientTable regenerated exactly as Noise.fs:31-33,72-76 draws it
+    (System.Random(666): 256 value-table draws first, then z and theta per entry); `perm` plays the role of
+    Noise.permutationTable (Noise.fs:7-23) -- the reference's literal is not copied here: the default is a Fisher-Yates
+    shuffle by the same generator, and an F# host can pass the reference's own table."""
+
+    def __init__(self, density=6.0, frequency=1.5, step=0.05, fade=0.25, bias=0.45, gain=0.9, perm=None, gradients=None):
+        self.density, self.frequency, self.step, self.fade, self.bias, self.gain = (float(density), float(frequency),
+                                                                                   float(step), float(fade), float(bias),
+                                                                                   float(gain))
+        if perm is None or gradients is None:
+            dperm, dgrad = CloudParams.default_tables()
+        self.perm = np.ascontiguousarray(dperm if perm is None else perm, dtype=np.int32)
+        self.gradients = np.ascontiguousarray(dgrad if gradients is None else gradients, dtype=np.float64).reshape(256, 3)
+        assert self.perm.shape == (256,)
+
+    _tables = None
+
+    @staticmethod
+    def default_tables():
+        if CloudParams._tables is None:
+            import math
+            from .dotnet_random import DotNetRandom
+            rng = DotNetRandom(666)  # Noise.fs:31
+            for _ in range(256):  # Noise.fs:33 valueTable draws come first
+                rng.NextDouble()
+            grad = np.empty((256, 3), np.float64)
+            for i in range(256):  # Noise.fs:72-76
+                z = rng.NextDouble() * 2.0 - 1.0
+                r = math.sqrt(1.0 - z * z)
+                theta = 2.0 * math.pi * rng.NextDouble()
+                grad[i] = (r * math.cos(theta), r * math.sin(theta), z)
+            perm = np.arange(256, dtype=np.int32)
+            for i in range(255, 0, -1):  # Fisher-Yates with the same generator
+                j = int(rng.NextDouble() * (i + 1))
+                perm[i], perm[j] = perm[j], perm[i]
+            CloudParams._tables = (perm, grad)
+        return CloudParams._tables
+
+    def to_c(self) -> "A.ft_cloud_params":
+        cp = A.ft_cloud_params()
+        cp.density, cp.frequency, cp.step, cp.fade, cp.bias, cp.gain = (self.density, self.frequency, self.step,
+                                                                        self.fade, self.bias, self.gain)
+        cp.perm = self.perm.ctypes.data_as(C.POINTER(C.c_int32))
+        cp.gradients = self.gradients.ctypes.data_as(C.POINTER(C.c_double))
+        return cp
 
 
 class Image:

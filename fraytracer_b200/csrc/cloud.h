@@ -1,0 +1,23 @@
+// cloud.h -- parameters and launcher of the volumetric cloud extension (cloud_kernels.cu).
+// EXTENSION: no reference implementation exists.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+struct CloudParams {
+    ft_camera cam;
+    int width, height;
+    float epsilon, length, max_size;
+    int spp;
+    uint32_t seed_lo, seed_hi;
+    long long n_tiles;  // 4 x 8 pixel tiles
+    float density, frequency, step, fade, bias, gain;  // ft_cloud_params
+    const int *perm;          // device, 256
+    const double *gradients;  // device, 768
+    float *out_rgb;           // device FColor[X,Y]
+    unsigned long long *work_counter;
+    unsigned long long *stats;
+};
+
+cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, int sm_count, cudaStream_t stream);

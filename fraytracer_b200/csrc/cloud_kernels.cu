@@ -1,0 +1,394 @@
+// cloud_kernels.cu -- EXTENSION (BASELINE config 4): volumetric cloud material, stochastic, N samples per pixel.
+//
+// NOT reference behaviour.  The reference has no participating media, no stochastic sampling and no
+// anti-aliasing; the spec is this repository's own.  Reused unchanged from
+// the reference: the march loop (SdfForm.fs:93-104), normalFromRay (SdfForm.fs:106-115), the material arg-min
+// (SdfObject.fs:27-46), shadow rays and the Lambert sum for solid hits (SdfLight.fs:6-42, SdfScene.fs:12-28).
+// The density field is the reference's dead-code lattice noise Noise.gradient (Noise.fs:78-110), float64, restated
+// as written (including `z+fz`, Noise.fs:80); its tables arrive as data through the ABI.
+// Parity target: oracle/ft_oracle.c fto_render_cloud, bit for bit (compiled with -fmad=false, IEEE div/sqrt;
+// no transcendental function on the path: collisions are Bernoulli draws per fixed step, not exponential
+// free paths, so that no libm call separates the two implementations).
+//
+// One persistent kernel.  A warp owns a 4 x 8 pixel tile; every lane runs ALL samples of its own pixel one after
+// the other (per-lane refill costs no coherence here: consecutive samples of a pixel are near-identical rays) and
+// sums them in sample order in registers -- deterministic, no atomics, no sample buffer.  As in the hot path's ray
+// machine every lane is a state machine around ONE distance-evaluation call site, so lanes that march a camera
+// ray, probe a normal, track through the medium or follow a shadow ray all execute the same evaluator
+// instructions: the divergence this config stresses is confined to the (cheap) transition code.
+#include <cuda_runtime.h>
+
+#define FT_NS ft_cloud
+#include "cloud.h"
+#include "kernels.h"
+#include "philox.h"
+#include "trace_device.cuh"
+
+namespace ft_cloud {
+
+constexpr int CB = 128;
+constexpr unsigned FULL = 0xffffffffu;
+
+enum : int {
+    C_FETCH = 0,
+    C_MARCH = 1,   // camera ray segment (SdfForm.tryTrace)
+    C_SHADOW = 2,  // the reference's shadow ray
+    C_N0 = 3,
+    C_N1 = 4,
+    C_N2 = 5,
+    C_N3 = 6,
+    C_TRACK = 7,   // fixed-step tracking along the camera ray inside the medium
+    C_LTRACK = 8,  // fixed-step tracking from the scatter point towards a light
+};
+
+struct NoiseTab {
+    int perm[256];
+    double grad[768];
+};
+
+__device__ __forceinline__ int nperm(const NoiseTab &n, int x) { return n.perm[x & 255]; }
+__device__ __forceinline__ int nindex(const NoiseTab &n, int ix, int iy, int iz) { return nperm(n, ix + nperm(n, iy + nperm(n, iz))); }
+__device__ __forceinline__ double glattice(const NoiseTab &n, int ix, int iy, int iz, double fx, double fy, double fz) {
+    const double *g = n.grad + 3 * nindex(n, ix, iy, iz);
+    return ((g[0] * fx + g[1] * fy) + g[2]) + fz;  // Noise.fs:80 as written
+}
+__device__ __forceinline__ double nlerp(double t, double x0, double x1) { return x0 + t * (x1 - x0); }
+__device__ __forceinline__ double smooth_step(double x) { return (x * x) * (3.0 - 2.0 * x); }
+__device__ __forceinline__ double lat_and_lerp(const NoiseTab &n, double w, int ix0, int iy0, int iz0, double fx0, double fy0,
+                                               double fz0, int ix1, int iy1, int iz1, double fx1, double fy1, double fz1) {
+    const double a = glattice(n, ix0, iy0, iz0, fx0, fy0, fz0);
+    const double b = glattice(n, ix1, iy1, iz1, fx1, fy1, fz1);
+    return nlerp(w, a, b);
+}
+__device__ double noise_gradient(const NoiseTab &n, double x, double y, double z) {  // Noise.fs:97-110
+    const int ix = (int)floor(x), iy = (int)floor(y), iz = (int)floor(z);
+    const double fx0 = x - (double)ix, fy0 = y - (double)iy, fz0 = z - (double)iz;
+    const double fx1 = fx0 - 1.0, fy1 = fy0 - 1.0, fz1 = fz0 - 1.0;
+    const double wx = smooth_step(fx0), wy = smooth_step(fy0), wz = smooth_step(fz0);
+    double vy0 = lat_and_lerp(n, wx, ix, iy, iz, fx0, fy0, fz0, ix + 1, iy, iz, fx1, fy0, fz0);
+    double vy1 = lat_and_lerp(n, wx, ix, iy + 1, iz, fx0, fy1, fz0, ix + 1, iy + 1, iz, fx1, fy1, fz0);
+    const double vz0 = nlerp(wy, vy0, vy1);
+    vy0 = lat_and_lerp(n, wx, ix, iy, iz + 1, fx0, fy0, fz1, ix + 1, iy, iz + 1, fx1, fy0, fz1);
+    vy1 = lat_and_lerp(n, wx, ix, iy + 1, iz + 1, fx0, fy1, fz1, ix + 1, iy + 1, iz + 1, fx1, fy1, fz1);
+    const double vz1 = nlerp(wy, vy0, vy1);
+    return nlerp(wz, vz0, vz1);
+}
+__device__ __forceinline__ float clamp01f(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+__device__ __forceinline__ float cloud_density(const NoiseTab &n, const CloudParams &P, V3 p, float D) {
+    const double f = (double)P.frequency;
+    const float nz = (float)noise_gradient(n, (double)p.x * f, (double)p.y * f, (double)p.z * f);
+    const float shape = clamp01f(P.bias + P.gain * nz);
+    const float edge = clamp01f(-D / P.fade);
+    return (P.density * shape) * edge;
+}
+__device__ __forceinline__ void cloud_rnd(const CloudParams &P, uint32_t pixel, uint32_t sample, uint32_t step, uint32_t stream,
+                                          float &u0, float &u1) {
+    uint32_t c[4] = {pixel, sample, step, stream};
+    ft_philox4x32_10(c, P.seed_lo, P.seed_hi);
+    u0 = __uint2float_rn(c[0]) * 2.3283064365386963e-10f;  // == (float)(c * 2^-32 in double)
+    u1 = __uint2float_rn(c[1]) * 2.3283064365386963e-10f;
+}
+
+template <bool CHAIN>
+__global__ void __launch_bounds__(CB, 4) cloud_kernel(const __grid_constant__ DevScene S, const __grid_constant__ CloudParams P) {
+    __shared__ NoiseTab tab;
+    for (int i = threadIdx.x; i < 256; i += CB) tab.perm[i] = P.perm[i];
+    for (int i = threadIdx.x; i < 768; i += CB) tab.grad[i] = P.gradients[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const float eps = P.epsilon;
+    const uint32_t nstreams = 1u + (uint32_t)S.n_lights;
+    const int tiles_y = (P.height + 7) / 8;
+    const V3 cam = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
+    const V3 bg = V3{S.bg[0], S.bg[1], S.bg[2]};
+    Acc acc{0ull, 0ull};
+    // Distance at the common origin of all camera rays, once per warp
+    const float d0 = CHAIN ? eval_chain<false>(S, cam, acc) : eval_form<false>(S, S.root_word, cam, acc);
+
+    int phase = C_FETCH;
+    bool have_tile = false, active = false, cloud_mode = false;
+    int x = 0, y = 0, s = 0, spp_eff = 0;
+    uint32_t pixel = 0, seg = 0, stream = 0, k = 0;
+    V3 sum{0, 0, 0}, o{0, 0, 0}, d{0, 0, 0}, cd{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, ho{0, 0, 0}, ps{0, 0, 0}, lc{0, 0, 0}, cint{0, 0, 0};
+    float len = 0.f, hlen = 0.f, lcos = 0.f, xi0 = 0.f, ucur = 0.f, maxdist = 0.f;
+    int steps = 0, light = 0, mat = 0;
+    unsigned n_hits = 0, n_secondary = 0, n_capped = 0, n_escaped = 0, n_scattered = 0;
+    unsigned long long n_track = 0;
+
+    for (;;) {
+        // ------------------------------------------------------------------ tile finished: write it, take the next one
+        if (__all_sync(FULL, phase == C_FETCH && s >= spp_eff)) {
+            if (have_tile && active) {
+                const float inv = (float)P.spp;
+                P.out_rgb[3ull * pixel + 0] = sum.x / inv;
+                P.out_rgb[3ull * pixel + 1] = sum.y / inv;
+                P.out_rgb[3ull * pixel + 2] = sum.z / inv;
+            }
+            unsigned long long tile = 0;
+            if (lane == 0) tile = atomicAdd(P.work_counter, 1ull);
+            tile = __shfl_sync(FULL, tile, 0);
+            if ((long long)tile >= P.n_tiles) break;
+            const int tx = (int)(tile / tiles_y), ty = (int)(tile - (unsigned long long)tx * tiles_y);
+            x = tx * 4 + (lane >> 3);
+            y = ty * 8 + (lane & 7);
+            active = x < P.width && y < P.height;
+            pixel = (uint32_t)((long long)x * P.height + y);
+            s = 0;
+            spp_eff = active ? P.spp : 0;
+            sum = V3{0.f, 0.f, 0.f};
+            have_tile = true;
+            continue;
+        }
+        // ------------------------------------------------------------------ per-lane refill: the lane's next sample
+        if (phase == C_FETCH && s < spp_eff) {
+            float u0, u1;
+            cloud_rnd(P, pixel, (uint32_t)s, 0u, 0u, u0, u1);  // sub-pixel jitter
+            const float pu = ((float)x + u0) / P.max_size, pv = ((float)y + u1) / P.max_size;
+            const V3 fwd = V3{P.cam.forward[0], P.cam.forward[1], P.cam.forward[2]};
+            const V3 rs = V3{P.cam.right_scaled[0], P.cam.right_scaled[1], P.cam.right_scaled[2]};
+            const V3 us = V3{P.cam.up_scaled[0], P.cam.up_scaled[1], P.cam.up_scaled[2]};
+            cd = normalize((fwd + rs * (pu - 0.5f)) + us * (pv - 0.5f));
+            o = cam;
+            d = cd;
+            len = P.length;
+            steps = 0;
+            if (len > 0.0f && d0 >= eps) {  // first iteration of the march with the shared Distance
+                o = o + d * d0;
+                len = len - d0;
+                steps = 1;
+            }
+            seg = 0;
+            phase = C_MARCH;
+        }
+        // ------------------------------------------------------------------ pre-checks
+        // event: 1 march miss, 2 march hit, 3 shadow unoccluded, 4 shadow occluded, 5 normal done, 6 sample ends on the
+        // background, 7 light visible, 8 light hidden
+        int event = 0;
+        float t = 0.f;
+        V3 p = o;
+        if (phase == C_MARCH || phase == C_SHADOW) {
+            if (len <= 0.0f || steps >= S.step_cap) {
+                if (!(len <= 0.0f)) n_capped++;
+                event = phase == C_MARCH ? 1 : 3;
+            } else if (S.esc_valid && outside_box(S.esc_lo, S.esc_hi, o) && ray_escapes(S, o, d, eps)) {
+                n_escaped++;
+                event = phase == C_MARCH ? 1 : 3;
+            }
+        } else if (phase >= C_N0 && phase <= C_N3) {
+            const float h = eps * 0.125f;
+            p = q;
+            if (phase == C_N0) p.x = q.x + h;
+            else if (phase == C_N1) p.y = q.y + h;
+            else if (phase == C_N2) p.z = q.z + h;
+        } else if (phase == C_TRACK) {
+            t = ((float)k + xi0) * P.step;
+            if (hlen - t <= 0.0f || k >= (uint32_t)FT_CLOUD_MAX_TRACK_STEPS) event = 6;
+            p = ho + cd * t;
+        } else if (phase == C_LTRACK) {
+            t = ((float)k + xi0) * P.step;
+            if (t >= maxdist) event = 7;
+            else if (k >= (uint32_t)FT_CLOUD_MAX_TRACK_STEPS) event = 8;
+            p = ps + d * t;
+        }
+        // ------------------------------------------------------------------ the one distance evaluation
+        if (phase > C_FETCH && event == 0) {
+            const float dist = CHAIN ? eval_chain<false>(S, p, acc) : eval_form<false>(S, S.root_word, p, acc);
+            if (phase <= C_SHADOW) {
+                steps++;
+                if (dist < eps) {
+                    event = phase == C_MARCH ? 2 : 4;
+                } else {
+                    o = o + d * dist;
+                    len = len - dist;
+                }
+            } else if (phase == C_N0) {
+                n.x = dist;
+                phase = C_N1;
+            } else if (phase == C_N1) {
+                n.y = dist;
+                phase = C_N2;
+            } else if (phase == C_N2) {
+                n.z = dist;
+                phase = C_N3;
+            } else if (phase == C_N3) {
+                n = normalize(n - V3{dist, dist, dist});
+                event = 5;
+            } else {  // tracking step inside the medium
+                n_track++;
+                if (dist >= eps) {
+                    if (phase == C_TRACK) {  // left the medium: the camera ray goes on as an ordinary ray
+                        seg++;
+                        if (seg >= (uint32_t)FT_CLOUD_MAX_SEGMENTS) {
+                            event = 6;
+                        } else {
+                            n_secondary++;
+                            o = p;
+                            d = cd;
+                            len = hlen - t;
+                            steps = 0;
+                            phase = C_MARCH;
+                        }
+                    } else {  // the reference's shadow ray from here (SdfLight.fs:10-20 / 26-41)
+                        n_secondary++;
+                        const float4 lv = ld4(S.lights + 2 * light);
+                        o = p;
+                        if (__float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL) {
+                            d = xyz(lv);
+                            len = 1000.0f;
+                        } else {
+                            const V3 diff = xyz(lv) - p;
+                            const float d2 = length2(diff);
+                            d = diff / d2;
+                            len = sqrtf(d2);
+                        }
+                        steps = 0;
+                        phase = C_SHADOW;
+                    }
+                } else {
+                    if (k > 0u) {
+                        float u1;
+                        cloud_rnd(P, pixel, (uint32_t)s, k, stream + (phase == C_LTRACK ? 1u + (uint32_t)light : 0u), ucur, u1);
+                    }
+                    if (ucur < cloud_density(tab, P, p, dist) * P.step) {
+                        if (phase == C_TRACK) {  // real collision: single scattering at p
+                            n_scattered++;
+                            ps = p;
+                            lc = bg;
+                            light = 0;
+                            cloud_mode = true;
+                            event = 9;
+                        } else {
+                            event = 8;
+                        }
+                    } else {
+                        k++;
+                    }
+                }
+            }
+        }
+        // ------------------------------------------------------------------ transitions
+        if (event != 0) {
+            bool next_light = false, finish = false;
+            V3 L = bg;
+            if (event == 1 || event == 6) {  // SdfScene.fs:10
+                finish = true;
+            } else if (event == 2) {  // hit: the un-moved hit ray stays in ho / hlen, probe the normal
+                ho = o;
+                hlen = len;
+                q = o + d * (-eps);
+                n_hits++;
+                phase = C_N0;
+            } else if (event == 5) {
+                const int leaf_obj = material_leaf<false>(S, ho, acc);
+                mat = __ldg(S.objects + leaf_obj).z;
+                if (__float_as_uint(ld4(S.materials + mat).w) == (uint32_t)FT_MATERIAL_CLOUD) {
+                    stream = 1u + seg * nstreams;
+                    cloud_rnd(P, pixel, (uint32_t)s, 0u, stream, ucur, xi0);
+                    k = 0u;
+                    phase = C_TRACK;
+                } else {  // the reference's shading, SdfScene.fs:12-28
+                    lc = bg;
+                    light = 0;
+                    cloud_mode = false;
+                    next_light = true;
+                }
+            } else if (event == 9) {
+                next_light = true;
+            } else {  // a light is decided: 3 / 7 it contributes, 4 / 8 it does not
+                if (event == 3 || event == 7) lc = cloud_mode ? lc + cint : lc + cint * lcos;
+                light++;
+                next_light = true;
+            }
+            if (next_light) {
+                finish = true;
+                for (; light < S.n_lights; light++) {
+                    const float4 lv = ld4(S.lights + 2 * light), lrgb = ld4(S.lights + 2 * light + 1);
+                    const bool directional = __float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL;
+                    if (cloud_mode) {  // isotropic scattering: every light, visibility by tracking
+                        cint = xyz(lrgb);
+                        maxdist = __int_as_float(0x7f800000);
+                        if (directional) {
+                            d = xyz(lv);
+                        } else {
+                            const V3 diff = xyz(lv) - ps;
+                            const float d2 = length2(diff);
+                            maxdist = sqrtf(d2);
+                            d = diff / maxdist;
+                            cint = xyz(lrgb) / d2;
+                        }
+                        n_secondary++;
+                        cloud_rnd(P, pixel, (uint32_t)s, 0u, stream + 1u + (uint32_t)light, ucur, xi0);
+                        k = 0u;
+                        phase = C_LTRACK;
+                        finish = false;
+                        break;
+                    }
+                    const V3 ldir = directional ? xyz(lv) : normalize(xyz(lv) - q);  // SdfScene.fs:13-19
+                    lcos = dot(n, ldir);
+                    if (lcos > 0.0f) {
+                        o = q;
+                        if (directional) {
+                            d = xyz(lv);
+                            len = 1000.0f;
+                            cint = xyz(lrgb);
+                        } else {
+                            const V3 diff = xyz(lv) - q;
+                            const float d2 = length2(diff);
+                            len = sqrtf(d2);
+                            d = diff / d2;
+                            cint = xyz(lrgb) / d2;
+                        }
+                        steps = 0;
+                        n_secondary++;
+                        phase = C_SHADOW;
+                        finish = false;
+                        break;
+                    }
+                }
+                if (finish) {
+                    const V3 albedo = xyz(ld4(S.materials + mat));
+                    const float pi_inv = 1.0f / 3.14159274f;
+                    L = cloud_mode ? albedo * (lc * (pi_inv * 0.25f)) : albedo * (lc * pi_inv);
+                }
+            }
+            if (finish) {
+                sum = sum + L;
+                s++;
+                phase = C_FETCH;
+            }
+        }
+    }
+
+    const unsigned hits = __reduce_add_sync(FULL, n_hits), secondary = __reduce_add_sync(FULL, n_secondary);
+    const unsigned capped = __reduce_add_sync(FULL, n_capped), escaped = __reduce_add_sync(FULL, n_escaped);
+    const unsigned scattered = __reduce_add_sync(FULL, n_scattered);
+    for (int sh = 16; sh > 0; sh >>= 1) n_track += __shfl_xor_sync(FULL, n_track, sh);
+    if (lane == 0) {
+        const unsigned w = (blockIdx.x * (CB / 32) + (threadIdx.x >> 5)) & (FT_STAT_SLOTS - 1);
+        unsigned long long *st = P.stats + w * FT_STAT_STRIDE;
+        if (hits) atomicAdd(st + FT_STAT_HITS, (unsigned long long)hits);
+        if (secondary) atomicAdd(st + FT_STAT_SHADOW, (unsigned long long)secondary);
+        if (capped) atomicAdd(st + FT_STAT_CAPPED, (unsigned long long)capped);
+        if (escaped) atomicAdd(st + FT_STAT_ESCAPED, (unsigned long long)escaped);
+        if (scattered) atomicAdd(st + FT_STAT_PATHS, (unsigned long long)scattered);
+        if (n_track) atomicAdd(st + FT_STAT_STEPS, n_track);
+    }
+}
+
+}  // namespace ft_cloud
+
+cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, int sm_count, cudaStream_t stream) {
+    using namespace ft_cloud;
+    if (P.n_tiles <= 0) return cudaSuccess;
+    int per_sm = 0;
+    cudaError_t e = S.chain_valid ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cloud_kernel<true>, CB, 0)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cloud_kernel<false>, CB, 0);
+    if (e != cudaSuccess) return e;
+    long long grid = (long long)(per_sm < 1 ? 1 : per_sm) * sm_count;
+    const long long need = (P.n_tiles + CB / 32 - 1) / (CB / 32);
+    if (grid > need) grid = need;
+    if (S.chain_valid) cloud_kernel<true><<<(unsigned)grid, CB, 0, stream>>>(S, P);
+    else cloud_kernel<false><<<(unsigned)grid, CB, 0, stream>>>(S, P);
+    return cudaGetLastError();
+}

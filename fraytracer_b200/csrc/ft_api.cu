@@ -13,6 +13,7 @@
 #include "kernels.h"
 #include "scene_compiler.h"
 #include "spectral.h"
+#include "cloud.h"
 
 namespace {
 
@@ -85,6 +86,8 @@ struct ft_scene {
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
     // second scratch (spectral extension: path queues and slots, sized after wave 0) and its wave counters
+    int *d_cloud_perm = nullptr;  // volumetric extension: the noise tables of the last ft_render_cloud call
+    double *d_cloud_grad = nullptr;
     void *d_scratch2 = nullptr;
     size_t scratch2_bytes = 0;
     unsigned *d_spec_counts = nullptr, *h_spec_counts = nullptr;
@@ -119,6 +122,8 @@ struct ft_scene {
         if (d_scratch) cudaFree(d_scratch);
         if (d_scratch2) cudaFree(d_scratch2);
         if (d_spec_counts) cudaFree(d_spec_counts);
+        if (d_cloud_perm) cudaFree(d_cloud_perm);
+        if (d_cloud_grad) cudaFree(d_cloud_grad);
         if (h_spec_counts) cudaFreeHost(h_spec_counts);
         for (auto &e : ev)
             if (e) cudaEventDestroy(e);
@@ -450,6 +455,8 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
     if (scene->host.has_glass)
         return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
+    if (scene->host.has_cloud)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_CLOUD (volumetric extension): render it with ft_render_cloud");
     std::lock_guard<std::mutex> lock(scene->mu);
     DeviceGuard guard(scene->device);
     if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
@@ -501,6 +508,8 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
     if (scene->host.has_glass)
         return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
+    if (scene->host.has_cloud)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_CLOUD (volumetric extension): render it with ft_render_cloud");
     std::lock_guard<std::mutex> lock(scene->mu);
     DeviceGuard guard(scene->device);
     if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
@@ -594,6 +603,8 @@ FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
     if (scene->host.has_glass)
         return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
+    if (scene->host.has_cloud)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_CLOUD (volumetric extension): render it with ft_render_cloud");
     std::lock_guard<std::mutex> lock(scene->mu);
     DeviceGuard guard(scene->device);
     if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
@@ -670,6 +681,8 @@ FT_API int ft_render_spectral(ft_scene *scene, const ft_camera *camera, int32_t 
     if (st != FT_OK) return st;
     if (scene->host.n_lights > FT_SPECTRAL_MAX_LIGHTS)
         return fail(FT_ERR_INVALID_ARGUMENT, "ft_render_spectral supports at most FT_SPECTRAL_MAX_LIGHTS lights");
+    if (scene->host.has_cloud)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_CLOUD (volumetric extension): render it with ft_render_cloud");
     if (scene->device == FT_DEVICE_NONE)
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
     std::lock_guard<std::mutex> lock(scene->mu);
@@ -760,6 +773,79 @@ FT_API int ft_render_spectral(ft_scene *scene, const ft_camera *camera, int32_t 
         stats->shadow_rays += (int64_t)paths;  // every secondary ray: shadow rays + continuation segments
         stats->reserved = (int32_t)n_hits;     // pixels whose primary ray hit glass
         stats->launches = launches;
+        cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
+        cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
+    }
+    return FT_OK;
+}
+
+FT_API int ft_render_cloud(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                           float length, const ft_cloud_params *cloud, int32_t samples_per_pixel, uint64_t seed,
+                           float *out_rgb, ft_render_stats *stats) {
+    if (!scene || !camera || !out_rgb || !cloud || !cloud->perm || !cloud->gradients) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (width <= 0 || height <= 0 || (int64_t)width * height >= ((int64_t)1 << 31))
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size");
+    if (samples_per_pixel < 1 || samples_per_pixel > 65536) return fail(FT_ERR_INVALID_ARGUMENT, "samples_per_pixel must be in 1..65536");
+    if (!(cloud->step > 0.0f) || !(cloud->fade > 0.0f)) return fail(FT_ERR_INVALID_ARGUMENT, "cloud step and fade must be > 0");
+    for (int i = 0; i < 256; i++)
+        if (cloud->perm[i] < 0 || cloud->perm[i] > 255) return fail(FT_ERR_INVALID_ARGUMENT, "cloud perm entries must be in 0..255");
+    int st = check_ray_params(epsilon, length);
+    if (st != FT_OK) return st;
+    if (scene->host.has_glass)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    const size_t npix = (size_t)width * height;
+    CU(scene->reserve(npix * 3 * sizeof(float)));
+    if (!scene->d_cloud_perm) {
+        CU(cudaMalloc(&scene->d_cloud_perm, 256 * sizeof(int)));
+        CU(cudaMalloc(&scene->d_cloud_grad, 768 * sizeof(double)));
+    }
+    cudaStream_t s = scene->stream;
+    CU(cudaMemcpyAsync(scene->d_cloud_perm, cloud->perm, 256 * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(scene->d_cloud_grad, cloud->gradients, 768 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CloudParams P{};
+    P.cam = *camera;
+    P.width = width;
+    P.height = height;
+    P.epsilon = epsilon;
+    P.length = length;
+    P.max_size = (float)std::max(width, height);
+    P.spp = samples_per_pixel;
+    P.seed_lo = (uint32_t)seed;
+    P.seed_hi = (uint32_t)(seed >> 32);
+    P.n_tiles = (long long)((width + 3) / 4) * ((height + 7) / 8);
+    P.density = cloud->density;
+    P.frequency = cloud->frequency;
+    P.step = cloud->step;
+    P.fade = cloud->fade;
+    P.bias = cloud->bias;
+    P.gain = cloud->gain;
+    P.perm = scene->d_cloud_perm;
+    P.gradients = scene->d_cloud_grad;
+    P.out_rgb = (float *)scene->d_scratch;
+    P.stats = scene->d_stats;
+    CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    CU(fresh_counter(scene, s, &P.work_counter));
+    CU(cudaEventRecord(scene->ev[0], s));
+    cudaError_t e = cloud_launch(scene->dev, P, scene->sm_count, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cloud kernel launch");
+    CU(cudaEventRecord(scene->ev[1], s));
+    CU(cudaMemcpyAsync(out_rgb, P.out_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(scene->ev[2], s));
+    CU(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        sum_stats(scene->h_stats, stats);
+        unsigned long long scattered = 0;
+        for (int k = 0; k < FT_STAT_SLOTS; k++) scattered += scene->h_stats[(size_t)k * FT_STAT_STRIDE + FT_STAT_PATHS];
+        stats->primary_rays = (int64_t)npix * samples_per_pixel;
+        stats->reserved = (int32_t)std::min<unsigned long long>(scattered, 0x7fffffffull);
+        stats->launches = 1;
         cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
         cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
     }

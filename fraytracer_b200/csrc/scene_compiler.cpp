@@ -429,13 +429,15 @@ class Compiler {
             case FT_OBJECT_LEAF: {  // SdfObject.fs:6-10
                 if (od.material < 0 || od.material >= d_->n_materials)
                     return fail(FT_ERR_INVALID_ARGUMENT, "material id out of range");
-                if (d_->materials[od.material].kind != FT_MATERIAL_SOLID && d_->materials[od.material].kind != FT_MATERIAL_GLASS)
+                if (d_->materials[od.material].kind != FT_MATERIAL_SOLID && d_->materials[od.material].kind != FT_MATERIAL_GLASS &&
+                    d_->materials[od.material].kind != FT_MATERIAL_CLOUD)
                     return fail(FT_ERR_UNSUPPORTED_NODE, "unsupported material kind (user-written closures cannot "
                                                          "run on the device)");
                 int st = build_form(od.form, 0, &o.form);
                 if (st != FT_OK) return st;
                 o.material = od.material;
                 if (d_->materials[od.material].kind == FT_MATERIAL_GLASS) out_->has_glass = 1;
+                if (d_->materials[od.material].kind == FT_MATERIAL_CLOUD) out_->has_cloud = 1;
                 break;
             }
             case FT_OBJECT_UNION: {  // SdfObject.fs:12-48

@@ -47,6 +47,7 @@ struct CompiledScene {
     uint32_t chain_union = 0, chain_ops = 0;
     int32_t n_nodes = 0, n_primitives = 0, max_depth = 0;
     int32_t grids_built_on_gpu = 0;
+    int32_t has_cloud = 0;  // a leaf uses FT_MATERIAL_CLOUD (volumetric extension): only ft_render_cloud renders it
     int32_t has_glass = 0;  // a leaf uses FT_MATERIAL_GLASS (spectral extension): only ft_render_spectral renders it
 };
 

@@ -6,6 +6,7 @@ config 1  default_scene()           Program.fs verbatim: 1000 tori, intersect sp
 config 2  spheres_capsules_scene()  512 randomSphere + 512 randomCapsule in one union (capsule stands in
                                     for the reference's non-existent cone), 1920x1080
 config 3  spectral_glass_scene()    EXTENSION (no reference): config-2 generator, every 3rd object dispersive glass
+config 4  cloud_scene()             EXTENSION (no reference): solids + large spheres of cloud medium, 64 spp
 config 5  mixed_scene()             256 each torus/sphere/capsule/triangle in one union, 7680x4320
 """
 from __future__ import annotations
@@ -140,3 +141,38 @@ def spectral_glass_scene(seed: int = 19, n_spheres: int = 192, n_capsules: int =
               SdfLight.point((-0.5, 0.0, -2.0), FColor.ofRGB(10.0, 10.0, 10.0))]
     scene = SdfScene(Object=SdfObject.union(objs), BackgroundColor=FColor.ofRGB(0.3, 0.4, 0.6), Lights=lights)
     return Workload("config3_spectral_glass_4k", scene, default_camera(), ImageSize(width, height), 0.01, 30.0, objs)
+
+
+def _bound(form: SdfForm):
+    """bounding sphere of a sphere / capsule form (SdfForm.fs:131-134, 166-169), float64 is fine for placement"""
+    p = form.params
+    if form.kind == 1:  # FT_FORM_SPHERE
+        return np.array(p[0:3]), p[3]
+    a, b = np.array(p[0:3]), np.array(p[3:6])
+    return (a + b) * 0.5, p[6] + float(np.linalg.norm(b - a)) * 0.5
+
+
+def cloud_scene(seed: int = 19, n_spheres: int = 64, n_capsules: int = 64, n_clouds: int = 24,
+                width: int = 1920, height: int = 1080) -> Workload:
+    """config 4 -- EXTENSION, no reference implementation: solid spheres and capsules
+    from the config-2 generator (Program.fs:32-46 helpers) plus `n_clouds` large spheres of cloud medium drawn from the
+    same System.Random stream (rejected while they touch a solid: what overlaps a cloud is hidden inside it), lit by a
+    white directional and a white point light."""
+    b = SceneBuilder(seed)
+    objs = [b.randomSphere() for _ in range(n_spheres)] + [b.randomCapsule() for _ in range(n_capsules)]
+    bounds = [_bound(o.form) for o in objs]
+    cloud = SdfMaterial.createCloud(FColor.ofRGB(0.95, 0.95, 0.95))
+    placed = 0
+    for _ in range(100000):
+        if placed == n_clouds:
+            break
+        center = b.rng.pointInBall(5.0)
+        radius = float(b.rng.range(0.6, 1.6))
+        if any(np.linalg.norm(np.asarray(center, np.float64) - c) < radius + r + 0.05 for c, r in bounds):
+            continue
+        objs.append(SdfObject.create(cloud, SdfForm.Primitive.sphere(Center=center, Radius=radius)))
+        placed += 1
+    lights = [SdfLight.directional((-0.5, -1.0, 1.0), FColor.ofRGB(2.0, 2.0, 2.0)),
+              SdfLight.point((-0.5, 0.0, -2.0), FColor.ofRGB(10.0, 10.0, 10.0))]
+    scene = SdfScene(Object=SdfObject.union(objs), BackgroundColor=FColor.ofRGB(0.3, 0.4, 0.6), Lights=lights)
+    return Workload("config4_cloud_1080p_64spp", scene, default_camera(), ImageSize(width, height), 0.01, 30.0, objs)

@@ -93,7 +93,10 @@ enum {
     FT_MATERIAL_SOLID = 1, /* SdfMaterial.createSolid color                    */
     /* EXTENSION (no reference implementation): dispersive glass, rgb = {A, B, unused} of the Cauchy
      * index n = A + B / lambda^2 (lambda in micrometres).  Only ft_render_spectral accepts scenes that use it.     */
-    FT_MATERIAL_GLASS = 2
+    FT_MATERIAL_GLASS = 2,
+    /* EXTENSION (no reference implementation): participating medium bounded by the object's form,
+     * rgb = single-scattering albedo.  Only ft_render_cloud accepts scenes that use it.                            */
+    FT_MATERIAL_CLOUD = 3
 };
 
 typedef struct ft_material_desc {
@@ -328,6 +331,32 @@ FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint3
 FT_API int ft_render_spectral(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
                               float length, int32_t n_wavelengths, int32_t max_bounces, uint64_t seed,
                               float *out_rgb, ft_render_stats *stats);
+
+/* ---- EXTENSION: volumetric cloud material (BASELINE config 4) ----------------------------------------------------
+ * No reference implementation exists: builder-defined spec in DESIGN.md 4.7.  The density field
+ * is the reference's dead-code lattice noise Noise.gradient (Noise.fs:78-110, float64, used as written including the
+ * `z+fz` of Noise.fs:80); its two tables are DATA passed by the caller: `perm` (256 entries, the role of
+ * Noise.permutationTable, Noise.fs:7-23) and `gradients` (256 x 3 doubles, Noise.gradientTable, Noise.fs:72-76).
+ * spp stochastic samples per pixel (sub-pixel jitter, fixed-step tracking with Bernoulli collisions, single
+ * scattering with tracked visibility), every draw from Philox4x32-10(seed; pixel, sample, step, stream).
+ * out_rgb is a HOST FColor[X,Y] holding the mean of the samples (summed in sample order: deterministic).
+ * stats->shadow_rays counts every secondary march (shadow rays, continuation segments, light tracks),
+ * stats->march_steps the tracking steps, stats->reserved the samples that scattered inside a cloud.            */
+typedef struct ft_cloud_params {
+    float density;   /* collision rate per unit length at full density                                   */
+    float frequency; /* the noise is sampled at position * frequency                                    */
+    float step;      /* fixed tracking step                                                             */
+    float fade;      /* depth below the surface at which the density reaches its full value             */
+    float bias;      /* local density = density * clamp01(bias + gain * noise) * clamp01(-Distance/fade) */
+    float gain;
+    const int32_t *perm;     /* 256 values in 0..255                                                    */
+    const double *gradients; /* 256 x {x, y, z}                                                         */
+} ft_cloud_params;
+#define FT_CLOUD_MAX_SEGMENTS 8     /* camera-ray segments per sample (a segment ends where the ray leaves a cloud) */
+#define FT_CLOUD_MAX_TRACK_STEPS 4096
+FT_API int ft_render_cloud(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                           float length, const ft_cloud_params *cloud, int32_t samples_per_pixel, uint64_t seed,
+                           float *out_rgb, ft_render_stats *stats);
 
 /* ---- post-process: Image.toColors / toBitmap / saveBitmap (Image.fs:37-90) -- */
 /* max over the n_floats values of an FColor image (Array2D.Parallel.maxWith FColor.getMaxColor, Image.fs:40-42);

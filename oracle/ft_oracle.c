@@ -1406,3 +1406,222 @@ FTO_API int fto_render_spectral(const fto_scene *s, const ft_camera *cam, int W,
     free(t);
     return FT_OK;
 }
+
+/* ------------------------------------------------------------------------ */
+/* EXTENSION: volumetric cloud material.  NOT reference behaviour: the reference has no media,    */
+/* no stochastic sampling and no anti-aliasing.  CPU restatement of this repository's own spec; the density      */
+/* field is the reference's dead-code Noise.gradient (Noise.fs:78-110) restated as written, float64.             */
+/* ------------------------------------------------------------------------ */
+typedef struct { const int32_t *perm; const double *grad; } noise_tab;
+static inline int nperm(const noise_tab *n, int x) { return n->perm[x & 255]; }                       /* Noise.fs:25-26 */
+static inline int nindex(const noise_tab *n, int ix, int iy, int iz) {                                /* Noise.fs:28-29 */
+    return nperm(n, ix + nperm(n, iy + nperm(n, iz)));
+}
+static inline double glattice(const noise_tab *n, int ix, int iy, int iz, double fx, double fy, double fz) {
+    const double *g = n->grad + 3 * nindex(n, ix, iy, iz);
+    return ((g[0] * fx + g[1] * fy) + g[2]) + fz; /* Noise.fs:80 as written: x*fx + y*fy + z+fz */
+}
+static inline double nlerp(double t, double x0, double x1) { return x0 + t * (x1 - x0); }             /* Noise.fs:82 */
+static inline double smooth_step(double x) { return (x * x) * (3.0 - 2.0 * x); }                      /* Noise.fs:83 */
+static inline double lat_and_lerp(const noise_tab *n, double w, int ix0, int iy0, int iz0, double fx0, double fy0, double fz0,
+                                  int ix1, int iy1, int iz1, double fx1, double fy1, double fz1) {  /* Noise.fs:92-95 */
+    double a = glattice(n, ix0, iy0, iz0, fx0, fy0, fz0);
+    double b = glattice(n, ix1, iy1, iz1, fx1, fy1, fz1);
+    return nlerp(w, a, b);
+}
+static double noise_gradient(const noise_tab *n, double x, double y, double z) {                      /* Noise.fs:97-110 */
+    int ix = (int)floor(x), iy = (int)floor(y), iz = (int)floor(z);                                   /* Noise.fs:85-90 */
+    double fx0 = x - (double)ix, fy0 = y - (double)iy, fz0 = z - (double)iz;
+    double fx1 = fx0 - 1.0, fy1 = fy0 - 1.0, fz1 = fz0 - 1.0;
+    double wx = smooth_step(fx0), wy = smooth_step(fy0), wz = smooth_step(fz0);
+    double vy0 = lat_and_lerp(n, wx, ix, iy, iz, fx0, fy0, fz0, ix + 1, iy, iz, fx1, fy0, fz0);
+    double vy1 = lat_and_lerp(n, wx, ix, iy + 1, iz, fx0, fy1, fz0, ix + 1, iy + 1, iz, fx1, fy1, fz0);
+    double vz0 = nlerp(wy, vy0, vy1);
+    vy0 = lat_and_lerp(n, wx, ix, iy, iz + 1, fx0, fy0, fz1, ix + 1, iy, iz + 1, fx1, fy0, fz1);
+    vy1 = lat_and_lerp(n, wx, ix, iy + 1, iz + 1, fx0, fy1, fz1, ix + 1, iy + 1, iz + 1, fx1, fy1, fz1);
+    double vz1 = nlerp(wy, vy0, vy1);
+    return nlerp(wz, vz0, vz1);
+}
+FTO_API double fto_noise_gradient(const int32_t *perm, const double *gradients, double x, double y, double z) {
+    noise_tab n = {perm, gradients};
+    return noise_gradient(&n, x, y, z);
+}
+
+typedef struct {
+    const fto_scene *s; const ft_camera *cam; int W, H; float eps, len; const ft_cloud_params *cp; int spp; uint64_t seed;
+    float *out; volatile int64_t next;
+    int64_t secondary, track_steps, scattered; pthread_mutex_t mu;
+} cjob;
+typedef struct { int64_t secondary, track_steps, scattered; } cstat;
+
+static inline float clamp01f(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+
+/* local collision rate: density * clamp01(bias + gain * noise(p f)) * clamp01(-Distance / fade) */
+static float cloud_density(const ft_cloud_params *cp, v3 p, float D) {
+    noise_tab n = {cp->perm, cp->gradients};
+    double f = (double)cp->frequency;
+    float nz = (float)noise_gradient(&n, (double)p.x * f, (double)p.y * f, (double)p.z * f);
+    float shape = clamp01f(cp->bias + cp->gain * nz);
+    float edge = clamp01f(-D / cp->fade);
+    return (cp->density * shape) * edge;
+}
+static void cloud_rnd(const cjob *j, uint32_t pixel, uint32_t sample, uint32_t step, uint32_t stream, float u[2]) {
+    uint32_t c[4] = {pixel, sample, step, stream};
+    philox4x32_10(c, (uint32_t)j->seed, (uint32_t)(j->seed >> 32));
+    u[0] = (float)((double)c[0] * (1.0 / 4294967296.0));
+    u[1] = (float)((double)c[1] * (1.0 / 4294967296.0));
+}
+/* the reference's shadow ray of light lt from `origin` (SdfLight.fs:10-20 / 26-41): 1 when unoccluded */
+static int shadow_unoccluded(const fto_scene *s, const olight *lt, v3 origin, float eps) {
+    oray sr;
+    sr.origin = origin;
+    sr.epsilon = eps;
+    if (lt->kind == FT_LIGHT_DIRECTIONAL) { sr.direction = lt->v; sr.length = 1000.0f; }
+    else {
+        v3 diff = vsub(lt->v, origin);
+        float d2 = vlen2(diff);
+        sr.direction = vdiv(diff, d2);
+        sr.length = sqrtf(d2);
+    }
+    oray dummy;
+    return !form_try_trace(s, s->root->form, sr, &dummy, NULL);
+}
+/* visibility of light lt from the scatter point p: fixed-step tracking through the medium, then the shadow ray */
+static int light_track(const cjob *j, cstat *st, const olight *lt, v3 p, v3 ldir, float maxdist, uint32_t pixel, uint32_t sample,
+                       uint32_t stream) {
+    const ft_cloud_params *cp = j->cp;
+    float u[2];
+    cloud_rnd(j, pixel, sample, 0u, stream, u);
+    const float xi0 = u[1];
+    st->secondary++;
+    for (uint32_t k = 0;; k++) {
+        float t = ((float)k + xi0) * cp->step;
+        if (t >= maxdist) return 1;
+        if (k >= FT_CLOUD_MAX_TRACK_STEPS) return 0;
+        v3 q = vadd(p, vscale(ldir, t));
+        float D = form_distance(j->s->root->form, q);
+        st->track_steps++;
+        if (D >= j->eps) { st->secondary++; return shadow_unoccluded(j->s, lt, q, j->eps); }
+        if (k > 0) cloud_rnd(j, pixel, sample, k, stream, u);
+        if (u[0] < cloud_density(cp, q, D) * cp->step) return 0;
+    }
+}
+
+static v3 cloud_sample(const cjob *j, cstat *st, int x, int y, uint32_t sample) {
+    const fto_scene *s = j->s;
+    const ft_cloud_params *cp = j->cp;
+    const uint32_t pixel = (uint32_t)((int64_t)x * j->H + y);
+    const uint32_t nstreams = 1u + (uint32_t)s->n_lights;
+    float u[2];
+    cloud_rnd(j, pixel, sample, 0u, 0u, u); /* sub-pixel jitter */
+    float max_size = (float)(j->W > j->H ? j->W : j->H);
+    float pu = ((float)x + u[0]) / max_size, pv = ((float)y + u[1]) / max_size;
+    v3 fwd = V(j->cam->forward[0], j->cam->forward[1], j->cam->forward[2]);
+    v3 rs = V(j->cam->right_scaled[0], j->cam->right_scaled[1], j->cam->right_scaled[2]);
+    v3 us = V(j->cam->up_scaled[0], j->cam->up_scaled[1], j->cam->up_scaled[2]);
+    oray ray;
+    ray.origin = V(j->cam->position[0], j->cam->position[1], j->cam->position[2]);
+    ray.direction = vnormalize(vadd(vadd(fwd, vscale(rs, pu - 0.5f)), vscale(us, pv - 0.5f)));
+    ray.epsilon = j->eps;
+    ray.length = j->len;
+    const float pi_inv = 1.0f / 3.14159274f;
+    for (uint32_t seg = 0;; seg++) {
+        if (seg >= FT_CLOUD_MAX_SEGMENTS) return s->background;
+        if (seg > 0) st->secondary++;
+        oray hit;
+        if (!form_try_trace(s, s->root->form, ray, &hit, NULL)) return s->background; /* SdfScene.fs:10 */
+        v3 normal = form_normal_from_ray(s->root->form, &hit);
+        const oobj *leaf = object_material_leaf(s->root, hit.origin);
+        if (s->material_kind[leaf->material] != FT_MATERIAL_CLOUD) { /* the reference's shading, SdfScene.fs:12-28 */
+            v3 pos = ray_move(hit, -hit.epsilon).origin;
+            v3 lc = s->background;
+            for (int l = 0; l < s->n_lights; l++) {
+                const olight *lt = &s->lights[l];
+                v3 ldir = (lt->kind == FT_LIGHT_DIRECTIONAL) ? lt->v : vnormalize(vsub(lt->v, pos));
+                float lcos = vdot(normal, ldir);
+                if (!(lcos > 0.0f)) continue;
+                v3 intensity = lt->color;
+                if (lt->kind != FT_LIGHT_DIRECTIONAL) intensity = vdiv(lt->color, vlen2(vsub(lt->v, pos)));
+                st->secondary++;
+                if (shadow_unoccluded(s, lt, pos, hit.epsilon)) lc = vadd(lc, vscale(intensity, lcos));
+            }
+            return vmul(s->material_rgb[leaf->material], vscale(lc, pi_inv));
+        }
+        /* cloud: fixed-step tracking along the camera ray from the hit point */
+        const uint32_t stream = 1u + seg * nstreams;
+        cloud_rnd(j, pixel, sample, 0u, stream, u);
+        const float xi0 = u[1];
+        int exited = 0;
+        for (uint32_t k = 0;; k++) {
+            float t = ((float)k + xi0) * cp->step;
+            if (hit.length - t <= 0.0f || k >= FT_CLOUD_MAX_TRACK_STEPS) return s->background;
+            v3 p = vadd(hit.origin, vscale(hit.direction, t));
+            float D = form_distance(s->root->form, p);
+            st->track_steps++;
+            if (D >= hit.epsilon) { /* left the medium: the camera ray goes on as an ordinary ray */
+                ray.origin = p;
+                ray.length = hit.length - t;
+                exited = 1;
+                break;
+            }
+            if (k > 0) cloud_rnd(j, pixel, sample, k, stream, u);
+            if (u[0] < cloud_density(cp, p, D) * cp->step) { /* real collision: single scattering */
+                st->scattered++;
+                v3 lc = s->background;
+                for (int l = 0; l < s->n_lights; l++) {
+                    const olight *lt = &s->lights[l];
+                    v3 ldir, intensity = lt->color;
+                    float maxdist = INFINITY;
+                    if (lt->kind == FT_LIGHT_DIRECTIONAL) ldir = lt->v;
+                    else {
+                        v3 diff = vsub(lt->v, p);
+                        float d2 = vlen2(diff);
+                        maxdist = sqrtf(d2);
+                        ldir = vdiv(diff, maxdist);
+                        intensity = vdiv(lt->color, d2);
+                    }
+                    if (light_track(j, st, lt, p, ldir, maxdist, pixel, sample, stream + 1u + (uint32_t)l)) lc = vadd(lc, intensity);
+                }
+                return vmul(s->material_rgb[leaf->material], vscale(lc, pi_inv * 0.25f)); /* isotropic phase 1/(4 pi) */
+            }
+        }
+        if (!exited) return s->background;
+    }
+}
+static void *cloud_worker(void *arg) {
+    cjob *j = (cjob *)arg;
+    cstat st = {0, 0, 0};
+    for (;;) {
+        int64_t x = __sync_fetch_and_add(&j->next, 1);
+        if (x >= j->W) break;
+        for (int y = 0; y < j->H; y++) {
+            v3 sum = V(0.0f, 0.0f, 0.0f);
+            for (int k = 0; k < j->spp; k++) sum = vadd(sum, cloud_sample(j, &st, (int)x, y, (uint32_t)k));
+            float *o = j->out + 3 * ((int64_t)x * j->H + y);
+            o[0] = sum.x / (float)j->spp; o[1] = sum.y / (float)j->spp; o[2] = sum.z / (float)j->spp;
+        }
+    }
+    pthread_mutex_lock(&j->mu);
+    j->secondary += st.secondary; j->track_steps += st.track_steps; j->scattered += st.scattered;
+    pthread_mutex_unlock(&j->mu);
+    return NULL;
+}
+/* counters (optional): {secondary marches, tracking steps, scattered samples} */
+FTO_API int fto_render_cloud(const fto_scene *s, const ft_camera *cam, int W, int H, float eps, float len, const ft_cloud_params *cp,
+                             int spp, uint64_t seed, int threads, float *out_rgb, int64_t *counters) {
+    if (!s || !cam || !cp || !cp->perm || !cp->gradients || !out_rgb || W <= 0 || H <= 0 || spp < 1 || !(cp->step > 0.0f) ||
+        !(cp->fade > 0.0f))
+        return FT_ERR_INVALID_ARGUMENT;
+    cjob j;
+    memset(&j, 0, sizeof(j));
+    j.s = s; j.cam = cam; j.W = W; j.H = H; j.eps = eps; j.len = len; j.cp = cp; j.spp = spp; j.seed = seed; j.out = out_rgb;
+    pthread_mutex_init(&j.mu, NULL);
+    if (threads < 1) threads = 1;
+    pthread_t *t = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    for (int i = 0; i < threads; i++) pthread_create(&t[i], NULL, cloud_worker, &j);
+    for (int i = 0; i < threads; i++) pthread_join(t[i], NULL);
+    free(t);
+    pthread_mutex_destroy(&j.mu);
+    if (counters) { counters[0] = j.secondary; counters[1] = j.track_steps; counters[2] = j.scattered; }
+    return FT_OK;
+}

@@ -73,6 +73,10 @@ def lib():
         L.fto_form_boundary.argtypes = [vp, C.c_int, vp]
         L.fto_root_boundary.argtypes = [vp, vp]
         L.fto_philox4x32_10.argtypes = [vp, vp, vp]
+        L.fto_render_cloud.argtypes = [vp, P(A.ft_camera), C.c_int, C.c_int, f32, f32, P(A.ft_cloud_params), C.c_int,
+                                       C.c_uint64, C.c_int, vp, vp]
+        L.fto_noise_gradient.restype = C.c_double
+        L.fto_noise_gradient.argtypes = [vp, vp, C.c_double, C.c_double, C.c_double]
         L.fto_render_spectral.argtypes = [vp, P(A.ft_camera), C.c_int, C.c_int, f32, f32, C.c_int, C.c_int, C.c_uint64,
                                           C.c_int, vp]
         L.fto_to_bitmap.restype = f32
@@ -182,6 +186,18 @@ class OracleScene:
         assert st == 0, st
         return rgb
 
+    def render_cloud(self, camera, X, Y, eps, length, cloud, spp=64, seed=19, threads=None):
+        """EXTENSION (no reference implementation): CPU restatement of ft_render_cloud.
+        Returns (rgb [X,Y,3], dict(secondary, track_steps, scattered))"""
+        cam = camera.to_c() if hasattr(camera, "to_c") else camera
+        cp = cloud.to_c()
+        rgb = np.zeros((X, Y, 3), np.float32)
+        ctr = np.zeros(3, np.int64)
+        st = lib().fto_render_cloud(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), C.byref(cp), spp,
+                                    C.c_uint64(seed), threads or os.cpu_count() or 1, _ptr(rgb), _ptr(ctr))
+        assert st == 0, st
+        return rgb, dict(secondary=int(ctr[0]), track_steps=int(ctr[1]), scattered=int(ctr[2]))
+
     def trace_rays(self, rays, threads=None, counters=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         n = rays.shape[0]
@@ -224,6 +240,13 @@ class OracleScene:
         out = np.empty(4, np.float32)
         lib().fto_root_boundary(self.h, _ptr(out))
         return out
+
+
+def noise_gradient(perm, gradients, x, y, z):
+    """Noise.gradient x y z (Noise.fs:97-110) over the given tables"""
+    perm = np.ascontiguousarray(perm, np.int32)
+    gradients = np.ascontiguousarray(gradients, np.float64)
+    return float(lib().fto_noise_gradient(_ptr(perm), _ptr(gradients), float(x), float(y), float(z)))
 
 
 def philox4x32_10(ctr, key):
