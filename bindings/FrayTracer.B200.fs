@@ -40,6 +40,12 @@ module Native =
           nForms : int; nObjects : int; nChildren : int; nMaterials : int; nLights : int; rootObject : int
           bgR : float32; bgG : float32; bgB : float32 }
 
+    // ft_cloud_params (EXTENSION): perm -> 256 x int32, gradients -> 256 x 3 x float (F# float = float64)
+    [<Struct; StructLayout(LayoutKind.Sequential)>]
+    type CloudParamsDesc =
+        { density : float32; frequency : float32; step : float32; fade : float32; bias : float32; gain : float32
+          perm : nativeint; gradients : nativeint }
+
     // mirrors the Camera record (Camera.fs:16-22): 4 x Vector3
     [<Struct; StructLayout(LayoutKind.Sequential)>]
     type CameraDesc = { position : Vector3; forward : Vector3; upScaled : Vector3; rightScaled : Vector3 }
@@ -53,6 +59,15 @@ module Native =
     [<DllImport(Lib)>]
     extern int ft_render(nativeint scene, CameraDesc& camera, int width, int height, float32 epsilon, float32 length,
                          uint32 flags, nativeint outRgb, nativeint outLeaf, nativeint stats)
+    // EXTENSIONS (no reference implementation; DESIGN.md 4.6 / 4.7)
+    [<DllImport(Lib)>]
+    extern int ft_render_spectral(nativeint scene, CameraDesc& camera, int width, int height, float32 epsilon,
+                                  float32 length, int nWavelengths, int maxBounces, uint64 seed, nativeint outRgb,
+                                  nativeint stats)
+    [<DllImport(Lib)>]
+    extern int ft_render_cloud(nativeint scene, CameraDesc& camera, int width, int height, float32 epsilon,
+                               float32 length, CloudParamsDesc& cloud, int samplesPerPixel, uint64 seed,
+                               nativeint outRgb, nativeint stats)
     [<DllImport(Lib)>]
     extern int ft_trace_rays(nativeint scene, int64 n, nativeint rays, uint32 flags, nativeint outRgb,
                              nativeint outLeaf, nativeint outSteps, nativeint outShadow, nativeint stats)
