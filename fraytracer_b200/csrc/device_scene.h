@@ -90,6 +90,9 @@ struct DevScene {
     uint32_t chain_union;  // node offset of U
     int32_t chain_n_ops;
     uint32_t chain_ops;
+    // records [1..3] of U (aabbMin | cellBase, cellSizeInv, counts): kernel-parameter copies, so that the chain
+    // evaluator's cell lookup starts from the constant bank instead of three dependent global loads
+    float4 chain_g1, chain_g2, chain_g3;
 };
 enum : uint32_t {
     FT_OP_INTERSECT = 1,  // if v < dist(C,p)+R then v = Max(v, D(p))      SdfForm.fs:62-63

@@ -310,6 +310,11 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
     s->dev.chain_union = h.chain_union;
     s->dev.chain_n_ops = h.chain_n_ops;
     s->dev.chain_ops = h.chain_ops;
+    if (h.chain_valid) {
+        s->dev.chain_g1 = h.nodes[(size_t)h.chain_union + 1];
+        s->dev.chain_g2 = h.nodes[(size_t)h.chain_union + 2];
+        s->dev.chain_g3 = h.nodes[(size_t)h.chain_union + 3];
+    }
     if (getenv("FT_NO_CHAIN")) s->dev.chain_valid = 0;  // experiments / tests of the generic interpreter
     if (getenv("FT_NO_ESCAPE")) s->dev.esc_valid = 0;  // experiments only
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");

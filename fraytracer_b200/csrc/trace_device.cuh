@@ -111,10 +111,7 @@ __device__ __forceinline__ float prim_distance(const DevScene &S, uint32_t word,
 }
 
 // ---- spatial lookup (SdfBoundary.fs:276-282): returns the cell's first entry index and dist(p, centre)
-template <bool COUNT>
-__device__ __forceinline__ void grid_cell(const DevScene &S, uint32_t uoff, V3 p, uint32_t &begin, float &dtc, Acc &acc) {
-    add_flops<COUNT>(acc, FLOPS_CELL_LOOKUP);
-    const float4 g1 = ld4(S.nodes + uoff + 1), g2 = ld4(S.nodes + uoff + 2), g3 = ld4(S.nodes + uoff + 3);
+__device__ __forceinline__ void grid_cell_from(const DevScene &S, float4 g1, float4 g2, float4 g3, V3 p, uint32_t &begin, float &dtc) {
     const V3 c = (p - xyz(g1)) * xyz(g2);
     const int mx = __float_as_int(g3.x), my = __float_as_int(g3.y), mz = __float_as_int(g3.z);
     const int ix = clamp_int(0, mx, floor_to_int(c.x));
@@ -124,6 +121,11 @@ __device__ __forceinline__ void grid_cell(const DevScene &S, uint32_t uoff, V3 p
     const float4 cell = ld4(S.cells + ci);
     dtc = distance(p, xyz(cell));  // SdfForm.fs:25
     begin = __float_as_uint(cell.w);
+}
+template <bool COUNT>
+__device__ __forceinline__ void grid_cell(const DevScene &S, uint32_t uoff, V3 p, uint32_t &begin, float &dtc, Acc &acc) {
+    add_flops<COUNT>(acc, FLOPS_CELL_LOOKUP);
+    grid_cell_from(S, ld4(S.nodes + uoff + 1), ld4(S.nodes + uoff + 2), ld4(S.nodes + uoff + 3), p, begin, dtc);
 }
 
 // one 32-byte candidate record (device_scene.h): two independent LDG.128 from the same sector
@@ -346,7 +348,8 @@ template <bool COUNT>
 __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
     uint32_t i;
     float dtc;
-    grid_cell<COUNT>(S, S.chain_union, p, i, dtc, acc);
+    add_flops<COUNT>(acc, FLOPS_CELL_LOOKUP);
+    grid_cell_from(S, S.chain_g1, S.chain_g2, S.chain_g3, p, i, dtc);  // U's header from the constant bank
     float m = __int_as_float(0x7f800000);  // +inf passes both tests: the first entry is evaluated unconditionally (:26)
 #if FT_SCAN_PTR
     // `ep` points at the record the unrolled loop started its current round with; the record under test is ep + 2 K
@@ -429,6 +432,8 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
     }
 #undef FT_LD_ENTRY
     float v = m;
+    // (measured: also serving the chain operations' operands from the constant bank, unrolled, made config 1 4 % slower
+    // -- four inlined copies of the primitive evaluator)
     for (int k = 0; k < S.chain_n_ops; k++) {
         const uint32_t op = __ldg(S.links + S.chain_ops + 2 * k), w = __ldg(S.links + S.chain_ops + 2 * k + 1);
         const float4 b0 = ld4(S.nodes + FT_WORD_OFF(w));
