@@ -22,8 +22,8 @@ like the reference's Stopwatch scope, Program.fs:89-94).
              on all host cores, on a bounded column sample of the same workload
 
 N > 1 is weak scaling: every GPU renders 1080p worth of pixels of an N-times larger frame of the same scene
-(column strips dealt round-robin, one NCCL all-gather of the framebuffer, de-interleave kernel), all inside
-the timed step.
+(column strips dealt round-robin; the framebuffer gather is fused into the render kernel as peer stores over
+NVLink -- or, with --gather nccl, one NCCL all-gather + de-interleave kernel), all inside the timed step.
 """
 from __future__ import annotations
 
@@ -204,7 +204,7 @@ def bench_b200(args):
 
     w = workload(args.workload, world)
     tracer = ft.SceneTracer(w.scene, device=local_rank)  # scene compile: outside the timed region (Program.fs:67-93)
-    renderer = DistributedRenderer(tracer, w.size, strip_width=8)
+    renderer = DistributedRenderer(tracer, w.size, strip_width=8, gather=args.gather)
     X, Y = w.size.X, w.size.Y
     lib = tracer.lib
 
@@ -349,7 +349,9 @@ def bench_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "image": f"{X}x{Y}", "rays_per_step": int(total_rays),
                        "primitives": info["n_primitives"], "grid_entries": info["n_entries"],
-                       "parallelism": f"image strips x{world}" + (" + NCCL all-gather" if world > 1 else ""),
+                       "parallelism": f"image strips x{world}" + (
+                           "" if world == 1 else " + P2P stores from the render kernel (CUDA IPC over NVLink), 4-byte NCCL all-reduce"
+                           if renderer.gather == "p2p" else " + NCCL all-gather + de-interleave"),
                        "l2": "flushed between timed iterations (512 MiB write)", "capped_rays": int(capped),
                        "mode": "fast" if args.fast else "strict"},
             "clocks": clocks,
@@ -373,6 +375,8 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config5"])
     ap.add_argument("--fast", action="store_true", help="FT_FLAG_FAST_MATH (FMA contraction, not bit-exact)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default=None, choices=["p2p", "nccl"],
+                    help="N > 1: how the framebuffer is gathered (default p2p: peer stores fused into the render kernel)")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

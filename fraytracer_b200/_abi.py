@@ -124,7 +124,8 @@ EXPORTS = [
     "ft_abi_version", "ft_last_error", "ft_device_count", "ft_lens_create", "ft_camera_look_at",
     "ft_scene_create", "ft_scene_destroy", "ft_scene_info_get", "ft_scene_set_step_cap",
     "ft_scene_grid_count", "ft_scene_grid_info", "ft_scene_grid_read",
-    "ft_render", "ft_render_device", "ft_render_strips_device", "ft_strip_layout", "ft_deinterleave_device",
+    "ft_render", "ft_render_device", "ft_render_strips_device", "ft_render_gather_device",
+    "ft_device_alloc", "ft_device_free", "ft_ipc_export", "ft_ipc_import", "ft_ipc_close", "ft_strip_layout", "ft_deinterleave_device",
     "ft_deinterleave_strips_device",
     "ft_trace_rays", "ft_distance", "ft_render_spectral", "ft_render_cloud",
     "ft_image_max_device", "ft_tonemap_device", "ft_to_bitmap", "ft_save_bitmap",
@@ -173,6 +174,13 @@ def load_library(path: str | None = None):
                                        P(ft_render_stats)]),
         "ft_render_strips_device": (C.c_int, [vp, P(ft_camera), i32, i32, f32, f32, u32, i32, i32, i32, i32, i32, vp, vp,
                                               vp, P(ft_render_stats)]),
+        "ft_render_gather_device": (C.c_int, [vp, P(ft_camera), i32, i32, f32, f32, u32, i32, i32, i32, P(vp), i32, vp,
+                                              P(ft_render_stats)]),
+        "ft_device_alloc": (C.c_int, [C.c_int, i64, P(vp)]),
+        "ft_device_free": (C.c_int, [C.c_int, vp]),
+        "ft_ipc_export": (C.c_int, [C.c_int, vp, vp]),
+        "ft_ipc_import": (C.c_int, [C.c_int, vp, P(vp)]),
+        "ft_ipc_close": (C.c_int, [C.c_int, vp]),
         "ft_deinterleave_strips_device": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
         "ft_strip_layout": (C.c_int, [i32, i32, i32, i32, P(i32), P(i64)]),
         "ft_deinterleave_device": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),

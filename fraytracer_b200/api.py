@@ -539,6 +539,19 @@ class SceneTracer:
                                                  C.byref(stats) if want_stats else None))
         return stats.as_dict() if want_stats else None
 
+    def render_gather_device(self, camera: Camera, size: ImageSize, epsilon: float, length: float, dst_ptrs, stream: int = 0,
+                             flags: int = 0, strip_width: int = 8, rank: int = 0, world: int = 1, want_stats: bool = False):
+        """Fused render + framebuffer gather: renders the strips `rank` owns and stores every pixel at its final position
+        in each framebuffer of `dst_ptrs` (raw device pointers: own buffer and IPC-mapped peers)."""
+        cam = camera.to_c()
+        stats = A.ft_render_stats() if want_stats else None
+        arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        A.check(self.lib.ft_render_gather_device(self.handle, C.byref(cam), int(size.X), int(size.Y), C.c_float(epsilon),
+                                                 C.c_float(length), int(flags), int(strip_width), int(rank), int(world),
+                                                 arr, len(dst_ptrs), C.c_void_p(stream) if stream else None,
+                                                 C.byref(stats) if want_stats else None))
+        return stats.as_dict() if want_stats else None
+
     def trace_rays(self, rays: np.ndarray, flags: int = 0):
         """Batched SdfScene.trace: rays float32 [n,8] = origin, direction, length, epsilon."""
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)

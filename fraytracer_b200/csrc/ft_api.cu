@@ -503,6 +503,91 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
     return FT_OK;
 }
 
+FT_API int ft_render_gather_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                                   float length, uint32_t flags, int32_t strip_width, int32_t rank, int32_t world,
+                                   float *const *d_dst, int32_t n_dst, void *stream, ft_render_stats *stats) {
+    if (!scene || !camera || !d_dst) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || rank < 0 || rank >= world || n_dst < 1 || n_dst > 16)
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size, strip partition or destination count");
+    for (int k = 0; k < n_dst; k++)
+        if (!d_dst[k]) return fail(FT_ERR_INVALID_ARGUMENT, "null destination framebuffer");
+    int st = check_ray_params(epsilon, length);
+    if (st != FT_OK) return st;
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    if (scene->host.has_glass || scene->host.has_cloud)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses an extension material: render it with ft_render_spectral / ft_render_cloud");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool count = (flags & FT_FLAG_COUNTERS) != 0;
+    RenderParams P = make_params(width, height, epsilon, length, strip_width, rank, world);
+    if (world == 1) P.local_cols = ((width + strip_width - 1) / strip_width) * strip_width;
+    if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    unsigned long long *wc;
+    CU(fresh_counter(scene, s, &wc));
+    cudaError_t e = (flags & FT_FLAG_FAST_MATH)
+                        ? ft_fast::launch_render_gather(scene->dev, *camera, P, d_dst, n_dst, wc, scene->d_stats, count, scene->sm_count, s)
+                        : ft_strict::launch_render_gather(scene->dev, *camera, P, d_dst, n_dst, wc, scene->d_stats, count, scene->sm_count, s);
+    if (e != cudaSuccess) return cuda_fail(e, "render-gather kernel launch");
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        sum_stats(scene->h_stats, stats);
+        long long owned = 0;
+        for (int xl = 0; xl < P.local_cols; xl++) {
+            const int strip = xl / strip_width;
+            owned += (strip * world + rank) * strip_width + (xl - strip * strip_width) < width;
+        }
+        stats->primary_rays = owned * height;
+        stats->launches = 1;
+    }
+    return FT_OK;
+}
+
+FT_API int ft_device_alloc(int device, int64_t bytes, void **d_ptr) {
+    if (!d_ptr || bytes <= 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    CU(cudaMalloc(d_ptr, (size_t)bytes));
+    return FT_OK;
+}
+FT_API int ft_device_free(int device, void *d_ptr) {
+    if (!d_ptr) return FT_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    CU(cudaFree(d_ptr));
+    return FT_OK;
+}
+FT_API int ft_ipc_export(int device, void *d_ptr, uint8_t handle[FT_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == FT_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    if (!d_ptr || !handle) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle, &h, sizeof(h));
+    return FT_OK;
+}
+FT_API int ft_ipc_import(int device, const uint8_t handle[FT_IPC_HANDLE_BYTES], void **d_ptr) {
+    if (!d_ptr || !handle) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FT_OK;
+}
+FT_API int ft_ipc_close(int device, void *d_ptr) {
+    if (!d_ptr) return FT_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return FT_OK;
+}
+
 FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon, float length,
                      uint32_t flags, float *out_rgb, int32_t *out_leaf, ft_render_stats *stats) {
     if (!scene || !camera || !out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");

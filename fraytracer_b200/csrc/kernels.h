@@ -29,6 +29,9 @@ struct RenderParams {
     cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb,         \
                               int *out_leaf, unsigned long long *work_counter, unsigned long long *stats, bool count, \
                               int sm_count, cudaStream_t stream);                                                     \
+    cudaError_t launch_render_gather(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *const *dst,     \
+                                     int n_dst, unsigned long long *work_counter, unsigned long long *stats, bool count,   \
+                                     int sm_count, cudaStream_t stream);                                              \
     cudaError_t launch_trace_rays(const DevScene &S, const float4 *rays, long long n, float *out_rgb, int *out_leaf,  \
                                   int *out_steps, unsigned *out_shadow, unsigned long long *work_counter,             \
                                   unsigned long long *stats, bool count, int sm_count, cudaStream_t stream);          \

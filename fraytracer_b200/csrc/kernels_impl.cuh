@@ -58,6 +58,27 @@ cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderP
     return cudaGetLastError();
 }
 
+cudaError_t launch_render_gather(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *const *dst, int n_dst,
+                                 unsigned long long *work_counter, unsigned long long *stats, bool count, int sm_count,
+                                 cudaStream_t stream) {
+    if (n_dst < 1 || n_dst > FT_MAX_GATHER_DST) return cudaErrorInvalidValue;
+    GatherJob job;
+    job.cam = cam;
+    job.P = P;
+    for (int k = 0; k < FT_MAX_GATHER_DST; k++) job.dst[k] = k < n_dst ? dst[k] : nullptr;
+    job.n_dst = n_dst;
+    job.n_items = (long long)((P.local_cols + FT_TILE_W - 1) / FT_TILE_W) * ((P.height + FT_TILE_H - 1) / FT_TILE_H) * 32;
+    if (job.n_items <= 0) return cudaSuccess;
+    unsigned grid = 1;
+    cudaError_t e;
+    const bool chain = S.chain_valid != 0;
+    if (count && chain) FT_LAUNCH(true, true, true, GatherJob, job.n_items);
+    else if (count) FT_LAUNCH(true, true, false, GatherJob, job.n_items);
+    else if (chain) FT_LAUNCH(false, true, true, GatherJob, job.n_items);
+    else FT_LAUNCH(false, true, false, GatherJob, job.n_items);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_trace_rays(const DevScene &S, const float4 *rays, long long n, float *out_rgb, int *out_leaf,
                               int *out_steps, unsigned *out_shadow, unsigned long long *work_counter,
                               unsigned long long *stats, bool count, int sm_count, cudaStream_t stream) {

@@ -99,6 +99,56 @@ struct RenderJob {
     }
 };
 
+// Image.render of this rank's column strips, fused with the framebuffer gather: every finished
+// pixel is stored at its final x-major position in the framebuffer of EVERY destination -- the rank's own and its
+// peers', mapped through CUDA IPC, so the stores travel over NVLink / NVSwitch while the rest of the tile is still
+// being traced.  No compact strip buffer, no all-gather, no de-interleave pass; a 4-byte all-reduce afterwards tells
+// every rank that all writers have finished.
+#define FT_MAX_GATHER_DST 16
+struct GatherJob {
+    ft_camera cam;
+    RenderParams P;
+    float *dst[FT_MAX_GATHER_DST];
+    int n_dst;
+    long long n_items;
+
+    __device__ __forceinline__ long long total() const { return n_items; }
+    static constexpr bool kProbe = true;
+    __device__ __forceinline__ V3 probe_point() const { return V3{cam.position[0], cam.position[1], cam.position[2]}; }
+    __device__ __forceinline__ bool load(long long i, float d0, V3 &o, V3 &d, float &len, float &eps, long long &slot,
+                                         int &steps) const {
+        const long long tile = i >> 5;
+        const int lane = (int)(i & 31);
+        const int tiles_y = (P.height + FT_TILE_H - 1) / FT_TILE_H;
+        const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
+        const int xl = tx * FT_TILE_W + lane / FT_TILE_H;  // column in the rank's compact strip space
+        const int y = ty * FT_TILE_H + lane % FT_TILE_H;
+        const int strip = xl / P.strip_width;
+        const int x = (strip * P.world + P.rank) * P.strip_width + (xl - strip * P.strip_width);
+        if (xl >= P.local_cols || y >= P.height || x >= P.width) return false;
+        slot = (long long)x * P.height + y;  // final position in FColor[X,Y]
+        o = V3{cam.position[0], cam.position[1], cam.position[2]};
+        d = pixel_direction(cam, x, y, P.max_size);
+        len = P.length;
+        eps = P.epsilon;
+        steps = 0;
+        if (len > 0.0f && d0 >= eps) {  // first march iteration with the shared Distance (see RenderJob)
+            o = o + d * d0;
+            len = len - d0;
+            steps = 1;
+        }
+        return true;
+    }
+    __device__ __forceinline__ void store(long long slot, float r, float g, float b, int, int, unsigned) const {
+        for (int k = 0; k < n_dst; k++) {
+            float *out = dst[k] + 3 * slot;
+            out[0] = r;
+            out[1] = g;
+            out[2] = b;
+        }
+    }
+};
+
 // batched SdfScene.trace: 32-byte ft_ray records read as two LDG.128
 struct RaysJob {
     const float4 *rays;

@@ -1,7 +1,12 @@
 """Multi-GPU image partitioning: pixels are independent, the compiled scene is small
 and replicated on every GPU, the image is cut into column strips dealt round-robin to the ranks
 (strip s -> rank s % world), every rank renders its strips into a compact buffer, one NCCL all-gather
-moves the framebuffer over NVLink and a de-interleave kernel restores the x-major FColor[X,Y].
+moves the framebuffer over NVLink and a de-interleave kernel restores the x-major FColor[X,Y]  (gather="nccl").
+
+gather="p2p" (the default with more than one rank) fuses the gather into the render kernel: every rank maps its peers'
+framebuffers through CUDA IPC and the kernel stores each finished pixel at its final position in all of them -- the
+transfer rides over NVLink / NVSwitch pixel by pixel while the rest of the frame is still being traced; a 4-byte NCCL
+all-reduce afterwards is the only collective (it tells every rank that all writers are done).
 
 One process per GPU; torch.distributed is only the plumbing around the C ABI (`ft_render_device`,
 `ft_deinterleave_device`).  The N-GPU framebuffer must be bit-identical to the 1-GPU one.
@@ -45,6 +50,13 @@ def deinterleave_reference(gathered, width: int, height: int, strip_width: int, 
     return out
 
 
+class _DeviceArray:
+    """raw device pointer -> __cuda_array_interface__ (float32), so that torch can view library-allocated memory"""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
 class DistributedRenderer:
     """Renders one frame cooperatively on all ranks of `group`; every rank ends with the full framebuffer.
 
@@ -54,7 +66,7 @@ class DistributedRenderer:
     (3.09 ms per step with 2 chunks against 2.60 ms with 1).  The default is therefore one chunk: render, one
     all-gather, de-interleave."""
 
-    def __init__(self, tracer, size, strip_width: int = 8, group=None, chunks: int = 1):
+    def __init__(self, tracer, size, strip_width: int = 8, group=None, chunks: int = 1, gather: str | None = None):
         import torch
         import torch.distributed as dist
 
@@ -65,8 +77,40 @@ class DistributedRenderer:
         dev = torch.device("cuda", tracer.device)
         X, Y = size.X, size.Y
         self.spr, _ = strip_layout(X, Y, strip_width, self.world)
-        self.final = torch.empty((X, Y, 3), dtype=torch.float32, device=dev)
+        self.gather = gather or ("p2p" if self.world > 1 else "nccl")
         self.chunk_ranges = []
+        self._owned, self._imported = [], []
+        if self.world > 1 and self.gather == "p2p":
+            # Two framebuffers per rank (frame parity): peers may already store frame k+1 while this rank still reads
+            # frame k; a rank re-enters a buffer only after one more completion all-reduce, i.e. after every reader's
+            # stream has moved past that frame.
+            lib, nbytes = tracer.lib, X * Y * 12
+            self.frames, self.dst = [], []
+            for parity in range(2):
+                ptr = C.c_void_p()
+                A.check(lib.ft_device_alloc(tracer.device, nbytes, C.byref(ptr)))
+                self._owned.append(ptr)
+                handle = (C.c_uint8 * 64)()
+                A.check(lib.ft_ipc_export(tracer.device, ptr, handle))
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle), group=group)
+                ptrs = []
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        ptrs.append(ptr.value)
+                    else:
+                        peer = C.c_void_p()
+                        A.check(lib.ft_ipc_import(tracer.device, (C.c_uint8 * 64).from_buffer_copy(h), C.byref(peer)))
+                        self._imported.append(peer)
+                        ptrs.append(peer.value)
+                self.dst.append(ptrs)
+                self.frames.append(torch.as_tensor(_DeviceArray(ptr.value, (X, Y, 3)), device=dev))
+            self.final = self.frames[0]
+            self._done = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._frame = 0
+            self.launches_per_frame = 1
+            return
+        self.final = torch.empty((X, Y, 3), dtype=torch.float32, device=dev)
         if self.world > 1:
             chunks = max(1, min(int(chunks), self.spr))
             edges = [round(i * self.spr / chunks) for i in range(chunks + 1)]
@@ -77,10 +121,30 @@ class DistributedRenderer:
                              for _, n in self.chunk_ranges]
         self.launches_per_frame = 1 if self.world == 1 else 2 * len(self.chunk_ranges)
 
+    def close(self):
+        """release the IPC mappings and the shared framebuffers (after a barrier: no peer may still be writing)"""
+        if self._owned:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            for p in self._imported:
+                self.tracer.lib.ft_ipc_close(self.tracer.device, p)
+            self.dist.barrier(group=self.group)
+            for p in self._owned:
+                self.tracer.lib.ft_device_free(self.tracer.device, p)
+            self._owned, self._imported, self.frames = [], [], []
+
     def render(self, camera, epsilon: float, length: float, flags: int = 0):
         torch = self.torch
         stream = torch.cuda.current_stream().cuda_stream
         X, Y = self.size.X, self.size.Y
+        if self.world > 1 and self.gather == "p2p":
+            parity = self._frame & 1
+            self._frame += 1
+            self.tracer.render_gather_device(camera, self.size, epsilon, length, self.dst[parity], stream=stream, flags=flags,
+                                             strip_width=self.strip_width, rank=self.rank, world=self.world)
+            self.dist.all_reduce(self._done, group=self.group)  # every writer's kernel has finished: the frame is complete
+            self.final = self.frames[parity]
+            return self.final
         if self.world == 1:
             self.tracer.render_device(camera, self.size, epsilon, length, self.final.data_ptr(), stream=stream,
                                       flags=flags, strip_width=self.strip_width, rank=0, world=1)

@@ -291,6 +291,23 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
                                    int32_t world, int32_t first_local_strip, int32_t n_local_strips,
                                    float *d_out_rgb, int32_t *d_out_leaf, void *stream, ft_render_stats *stats);
 
+/* Fused render + framebuffer gather (multi-GPU): renders the strips `rank` owns and stores every finished pixel at its
+ * final position of the x-major FColor[X,Y] in EACH of the n_dst destination framebuffers (DEVICE pointers: the rank's
+ * own buffer and its peers', opened with ft_ipc_import) -- peer stores over NVLink / NVSwitch from inside the render
+ * kernel, replacing compact strips + NCCL all-gather + de-interleave.  Pixels of other ranks' strips are not touched.
+ * The caller orders frames: after the call, a collective on the same stream (a 4-byte all-reduce) tells every rank
+ * that all writers are done.  n_dst <= 16.                                                                          */
+FT_API int ft_render_gather_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                                   float length, uint32_t flags, int32_t strip_width, int32_t rank, int32_t world,
+                                   float *const *d_dst, int32_t n_dst, void *stream, ft_render_stats *stats);
+/* device memory that can be shared between the per-GPU processes of one node (cudaMalloc + CUDA IPC)               */
+#define FT_IPC_HANDLE_BYTES 64
+FT_API int ft_device_alloc(int device, int64_t bytes, void **d_ptr);
+FT_API int ft_device_free(int device, void *d_ptr);
+FT_API int ft_ipc_export(int device, void *d_ptr, uint8_t handle[FT_IPC_HANDLE_BYTES]);
+FT_API int ft_ipc_import(int device, const uint8_t handle[FT_IPC_HANDLE_BYTES], void **d_ptr);
+FT_API int ft_ipc_close(int device, void *d_ptr);
+
 /* number of strips and of floats in the compact per-rank buffer above       */
 FT_API int ft_strip_layout(int32_t width, int32_t height, int32_t strip_width, int32_t world,
                            int32_t *strips_per_rank, int64_t *floats_per_rank);

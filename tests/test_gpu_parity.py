@@ -318,3 +318,40 @@ def test_full_size_properties_config5_4k():
                                               C.c_void_p(final.data_ptr()), None))
     torch.cuda.synchronize()
     assert np.array_equal(bits(final.cpu().numpy()), bits(a)) and hits == sa["primary_hits"]
+
+
+def test_fused_render_gather_equals_render():
+    """ft_render_gather_device with world = 1 and several destinations: every destination holds ft_render's frame"""
+    import torch
+
+    w = scenes.default_scene(n_tori=200)
+    tracer = ft.SceneTracer(w.scene, device=0)
+    for X, Y in ((130, 61), (64, 64)):
+        size = ft.ImageSize(X, Y)
+        ref, _, _ = tracer.render(w.camera, size, w.epsilon, w.length)
+        for world in (1, 3):
+            dsts = [torch.full((X, Y, 3), -7.0, dtype=torch.float32, device="cuda") for _ in range(3)]
+            for rank in range(world):
+                tracer.render_gather_device(w.camera, size, w.epsilon, w.length, [d.data_ptr() for d in dsts],
+                                            stream=torch.cuda.current_stream().cuda_stream, rank=rank, world=world)
+            torch.cuda.synchronize()
+            for d in dsts:
+                assert np.array_equal(bits(d.cpu().numpy()), bits(ref))
+    tracer.close()
+
+
+def test_two_rank_p2p_gather_when_two_gpus_are_present():
+    """the CUDA IPC path needs one process per GPU: run tools/check_p2p.py under torchrun when the box has >= 2 GPUs"""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (covered by `gpurun --gpus 2 -- torchrun ... tools/check_p2p.py`)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "check_p2p.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

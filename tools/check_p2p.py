@@ -1,0 +1,36 @@
+"""torchrun check (N >= 2 GPUs): the fused render + P2P gather framebuffer equals the single-GPU render bit for bit on every
+rank, for both gather modes, several frames in a row (frame-parity buffers).
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_p2p.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fraytracer_b200 as ft
+from fraytracer_b200 import scenes
+from fraytracer_b200.distributed import DistributedRenderer
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for w, (X, Y) in ((scenes.default_scene(n_tori=300), (333, 251)), (scenes.spheres_capsules_scene(), (640, 360))):
+    size = ft.ImageSize(X, Y)
+    tr = ft.SceneTracer(w.scene, device=local)
+    ref, _, _ = tr.render(w.camera, size, w.epsilon, w.length)
+    for mode in ("p2p", "nccl"):
+        r = DistributedRenderer(tr, size, strip_width=8, gather=mode)
+        for frame in range(3):
+            img = r.render(w.camera, w.epsilon, w.length).cpu().numpy()
+            same = np.array_equal(img.view(np.uint32), ref.view(np.uint32))
+            ok &= same
+            print(f"rank {rank}/{world} {w.name} {X}x{Y} {mode} frame {frame}: identical={same}", flush=True)
+        r.close()
+    tr.close()
+t = torch.tensor([0 if ok else 1], device="cuda")
+dist.all_reduce(t)
+dist.destroy_process_group()
+sys.exit(int(t.item()) != 0)
