@@ -129,7 +129,7 @@ EXPORTS = [
     "ft_deinterleave_strips_device",
     "ft_trace_rays", "ft_distance", "ft_render_spectral", "ft_render_cloud",
     "ft_image_max_device", "ft_tonemap_device", "ft_to_bitmap", "ft_save_bitmap",
-    "ft_host_register", "ft_host_unregister", "ft_host_alloc", "ft_host_free",
+    "ft_host_register", "ft_host_unregister", "ft_host_alloc", "ft_host_free", "ft_host_get_device_pointer",
     "ft_measure_fp32_peak",
 ]
 
@@ -198,6 +198,7 @@ def load_library(path: str | None = None):
         "ft_host_unregister": (C.c_int, [vp]),
         "ft_host_alloc": (C.c_int, [P(vp), i64]),
         "ft_host_free": (C.c_int, [vp]),
+        "ft_host_get_device_pointer": (C.c_int, [vp, P(vp)]),
         "ft_measure_fp32_peak": (C.c_int, [C.c_int, P(f32), P(f32)]),
     }
     for name, (res, args) in sig.items():

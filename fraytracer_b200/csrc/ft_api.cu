@@ -1051,6 +1051,11 @@ FT_API int ft_host_alloc(void **ptr, int64_t bytes) {
     CU(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped));
     return FT_OK;
 }
+FT_API int ft_host_get_device_pointer(void *host_ptr, void **d_ptr) {
+    if (!host_ptr || !d_ptr) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    CU(cudaHostGetDevicePointer(d_ptr, host_ptr, 0));
+    return FT_OK;
+}
 FT_API int ft_host_free(void *ptr) {
     if (!ptr) return FT_OK;
     CU(cudaFreeHost(ptr));

@@ -121,8 +121,67 @@ class DistributedRenderer:
                              for _, n in self.chunk_ranges]
         self.launches_per_frame = 1 if self.world == 1 else 2 * len(self.chunk_ranges)
 
+    # ---- framebuffer in shared, page-locked host memory: every GPU delivers its own strips over its own PCIe link
+    def host_frame(self):
+        """Creates (once) a FColor[X,Y] in POSIX shared memory, mapped and page-locked by every rank's process.
+        Returns the numpy view; `render_to_host` fills it."""
+        if getattr(self, "_host", None) is not None:
+            return self._host
+        import numpy as np
+        from multiprocessing import shared_memory
+
+        X, Y = self.size.X, self.size.Y
+        nbytes = X * Y * 12
+        name = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self._shm.name
+        if self.world > 1:
+            self.dist.broadcast_object_list(name, src=0, group=self.group)
+            if self.rank != 0:
+                self._shm = shared_memory.SharedMemory(name=name[0])
+                try:  # only the creating rank owns (and unlinks) the segment
+                    from multiprocessing import resource_tracker
+
+                    resource_tracker.unregister(self._shm._name, "shared_memory")
+                except Exception:
+                    pass
+        self._host = np.ndarray((X, Y, 3), dtype=np.float32, buffer=self._shm.buf)
+        lib = self.tracer.lib
+        self._host_addr = self._host.ctypes.data
+        self.torch.cuda.set_device(self.tracer.device)
+        A.check(lib.ft_host_register(C.c_void_p(self._host_addr), nbytes))
+        dptr = C.c_void_p()
+        A.check(lib.ft_host_get_device_pointer(C.c_void_p(self._host_addr), C.byref(dptr)))
+        self._host_dev = dptr.value
+        if not hasattr(self, "_done"):
+            self._done = self.torch.zeros(1, dtype=self.torch.int32, device=self.torch.device("cuda", self.tracer.device))
+        return self._host
+
+    def render_to_host(self, camera, epsilon: float, length: float, flags: int = 0):
+        """One frame straight into the shared host framebuffer (no device framebuffer, no device->host copy): every
+        rank's kernel stores its strips over its own PCIe link; returns after all ranks have finished (the numpy view
+        of `host_frame()` is then complete on every rank's host)."""
+        host = self.host_frame()
+        stream = self.torch.cuda.current_stream().cuda_stream
+        self.tracer.render_gather_device(camera, self.size, epsilon, length, [self._host_dev], stream=stream, flags=flags,
+                                         strip_width=self.strip_width, rank=self.rank, world=self.world)
+        if self.world > 1:
+            self.dist.all_reduce(self._done, group=self.group)
+        self.torch.cuda.current_stream().synchronize()
+        return host
+
     def close(self):
         """release the IPC mappings and the shared framebuffers (after a barrier: no peer may still be writing)"""
+        if getattr(self, "_host", None) is not None:
+            self.torch.cuda.synchronize()
+            if self.world > 1:
+                self.dist.barrier(group=self.group)
+            self.tracer.lib.ft_host_unregister(C.c_void_p(self._host_addr))
+            self._host = None
+            self._shm.close()
+            if self.rank == 0:
+                self._shm.unlink()
         if self._owned:
             self.torch.cuda.synchronize()
             self.dist.barrier(group=self.group)

@@ -398,6 +398,11 @@ FT_API int ft_host_register(void *ptr, int64_t bytes);
 FT_API int ft_host_unregister(void *ptr);
 FT_API int ft_host_alloc(void **ptr, int64_t bytes);
 FT_API int ft_host_free(void *ptr);
+/* device-side address of page-locked, mapped host memory (ft_host_alloc / ft_host_register): a valid destination of
+ * ft_render_gather_device -- the kernel then stores finished pixels straight into host memory over PCIe.  With one
+ * process per GPU, a framebuffer in shared host memory registered by every process lets each GPU deliver its own
+ * strips over its own PCIe link.                                                                                 */
+FT_API int ft_host_get_device_pointer(void *host_ptr, void **d_ptr);
 
 /* ---- measurement --------------------------------------------------------- */
 /* dependent-free FFMA stream over all SMs: the FP32 roofline denominator

@@ -28,6 +28,12 @@ for w, (X, Y) in ((scenes.default_scene(n_tori=300), (333, 251)), (scenes.sphere
             same = np.array_equal(img.view(np.uint32), ref.view(np.uint32))
             ok &= same
             print(f"rank {rank}/{world} {w.name} {X}x{Y} {mode} frame {frame}: identical={same}", flush=True)
+        if mode == "p2p":  # shared host framebuffer: every rank's kernel stores its strips over its own PCIe link
+            for frame in range(2):
+                host = r.render_to_host(w.camera, w.epsilon, w.length)
+                same = np.array_equal(host.view(np.uint32), ref.view(np.uint32))
+                ok &= same
+                print(f"rank {rank}/{world} {w.name} {X}x{Y} host frame {frame}: identical={same}", flush=True)
         r.close()
     tr.close()
 t = torch.tensor([0 if ok else 1], device="cuda")
