@@ -29,6 +29,7 @@ FT_FORM_SPHERE = 1
 FT_FORM_CAPSULE = 2
 FT_FORM_TORUS = 3
 FT_FORM_TRIANGLE = 4
+FT_FORM_CONE = 5  # EXTENSION (no reference implementation): capped cone
 FT_FORM_UNION = 16
 FT_FORM_SUBTRACT = 17
 FT_FORM_INTERSECT = 18

@@ -128,6 +128,19 @@ class SdfForm:
             V3: tuple
             Radius: float
 
+        @dataclass(frozen=True)
+        class Cone:
+            """EXTENSION, not in the reference (BASELINE.json names cones, the reference has none): capped cone"""
+            From: tuple
+            To: tuple
+            FromRadius: float
+            ToRadius: float
+
+        @staticmethod
+        def cone(data=None, **kw) -> "SdfForm":
+            d = data or SdfForm.Primitive.Cone(**kw)
+            return SdfForm(A.FT_FORM_CONE, (*_vec3(d.From), *_vec3(d.To), d.FromRadius, d.ToRadius))
+
         @staticmethod
         def sphere(data=None, **kw) -> "SdfForm":
             d = data or SdfForm.Primitive.Sphere(**kw)

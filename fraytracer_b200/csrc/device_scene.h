@@ -45,6 +45,7 @@ enum : uint32_t {
     FT_K_CAPSULE = 2,
     FT_K_TORUS = 3,
     FT_K_TRIANGLE = 4,
+    FT_K_CONE = 5,  // EXTENSION (no reference): [1] {From, ra} [2] {To - From, rb} [3] {baba, rb - ra, (rb-ra)^2 + baba, -}
     FT_K_UNION = 8,
     FT_K_SUBTRACT = 9,
     FT_K_INTERSECT = 10,

@@ -153,6 +153,15 @@ void sum_stats(const unsigned long long *h, ft_render_stats *st) {
         flops += p[FT_STAT_FLOPS];
         escaped += p[FT_STAT_ESCAPED];
     }
+    if (getenv("FT_PRINT_LONG")) {  // experiments: share of the work done outside the largest grid's box
+        unsigned long long lf = 0, le = 0, ev = 0;
+        for (int k = 0; k < FT_STAT_SLOTS; k++) {
+            lf += h[(size_t)k * FT_STAT_STRIDE + FT_STAT_LONG_FLOPS];
+            le += h[(size_t)k * FT_STAT_STRIDE + FT_STAT_LONG_EVALS];
+            ev += h[(size_t)k * FT_STAT_STRIDE + FT_STAT_EVALS];
+        }
+        fprintf(stderr, "[ft] evaluations %llu (outside the grid box %llu), flops %llu (outside %llu)\n", ev, le, flops, lf);
+    }
     st->escaped_rays = (int64_t)escaped;
     st->primary_hits = (int64_t)hits;
     st->shadow_rays = (int64_t)shadow;

@@ -13,6 +13,9 @@
 #define FT_STAT_STEPS 3
 #define FT_STAT_FLOPS 4
 #define FT_STAT_ESCAPED 5
+#define FT_STAT_LONG_FLOPS 7  // COUNT variant: work of the evaluations outside the largest grid's box
+#define FT_STAT_LONG_EVALS 8
+#define FT_STAT_EVALS 9
 #define FT_STAT_PATHS 6  // spectral extension: continuation path segments marched
 
 struct RenderParams {

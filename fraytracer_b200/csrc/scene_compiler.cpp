@@ -362,6 +362,24 @@ class Compiler {
                 idx = (int)nodes_.size() - 1;
                 break;
             }
+            case FT_FORM_CONE: {  // EXTENSION: capped cone, no reference implementation
+                FormNode nd;
+                nd.kind = f.kind;
+                V3 from = v3(p[0], p[1], p[2]), to = v3(p[3], p[4], p[5]);
+                const float ra = p[6], rb = p[7];
+                nd.v[0] = from;
+                nd.v[1] = to - from;
+                nd.s[0] = ra;
+                nd.s[1] = rb;
+                nd.s[2] = dot(nd.v[1], nd.v[1]);  // baba
+                if (!(nd.s[2] > 0.f) || !(ra >= 0.f) || !(rb >= 0.f))
+                    return fail(FT_ERR_INVALID_ARGUMENT, "cone: From and To must differ and the radii must be >= 0");
+                const float h = distance(from, to) * 0.5f, rm = ra > rb ? ra : rb;
+                nd.b = Bnd{lerp(from, to, 0.5f), sqrtf(h * h + rm * rm) * 1.000001f};  // rim of the larger cap, a hair of slack
+                nodes_.push_back(nd);
+                idx = (int)nodes_.size() - 1;
+                break;
+            }
             case FT_FORM_TRIANGLE: {  // SdfForm.fs:214-263
                 FormNode nd;
                 nd.kind = f.kind;
@@ -527,7 +545,7 @@ class Compiler {
         EscBox b{{0, 0, 0}, {0, 0, 0}, 0.0, true};
         if (depth > 64) { b.ok = false; return b; }
         switch (n.kind) {
-            case FT_FORM_SPHERE: case FT_FORM_CAPSULE: case FT_FORM_TORUS: case FT_FORM_TRIANGLE: {
+            case FT_FORM_SPHERE: case FT_FORM_CAPSULE: case FT_FORM_TORUS: case FT_FORM_TRIANGLE: case FT_FORM_CONE: {
                 // every primitive's surface lies inside its bounding sphere (SdfForm.fs:131-134,166-169,199-202,252-263)
                 const double c[3] = {n.b.c.x, n.b.c.y, n.b.c.z}, r = n.b.r;
                 b.ok = std::isfinite(r) && r >= 0.0 && std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]);
@@ -569,6 +587,7 @@ class Compiler {
                 case FT_FORM_CAPSULE: kcode = FT_K_CAPSULE; len = 4; break;
                 case FT_FORM_TORUS: kcode = FT_K_TORUS; len = 3; break;
                 case FT_FORM_TRIANGLE: kcode = FT_K_TRIANGLE; len = 14; break;
+                case FT_FORM_CONE: kcode = FT_K_CONE; len = 4; break;
                 case FT_FORM_UNION: kcode = FT_K_UNION; len = 4; break;
                 case FT_FORM_SUBTRACT: kcode = FT_K_SUBTRACT; len = 2; break;
                 case FT_FORM_INTERSECT: kcode = FT_K_INTERSECT; len = 2; break;
@@ -606,6 +625,14 @@ class Compiler {
                     r[1] = f4(n.v[0], n.s[0]);
                     for (int k = 1; k < 13; k++) r[1 + k] = f4(n.v[k], 0.f);
                     break;
+                case FT_FORM_CONE: {
+                    o.n_primitives++;
+                    const float rba = n.s[1] - n.s[0];
+                    r[1] = f4(n.v[0], n.s[0]);
+                    r[2] = f4(n.v[1], n.s[1]);
+                    r[3] = f4(n.s[2], rba, rba * rba + n.s[2], 0.f);
+                    break;
+                }
                 case FT_FORM_UNION: {
                     const GridHost &g = grids_[(size_t)n.grid];
                     r[1] = f4(g.aabb_min[0], g.aabb_min[1], g.aabb_min[2], as_float((uint32_t)g.cell_base));

@@ -16,6 +16,7 @@ using namespace ftm;
 constexpr int FLOPS_SPHERE = 10;
 constexpr int FLOPS_CAPSULE = 21;
 constexpr int FLOPS_TORUS = 27;
+constexpr int FLOPS_CONE = 52;  // EXTENSION primitive (no reference)
 constexpr int FLOPS_TRI_EDGE = 85;
 constexpr int FLOPS_TRI_FACE = 34;
 constexpr int FLOPS_LB_TEST = 2;      // lb - dtc, compare
@@ -46,6 +47,8 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 struct Acc {
     unsigned long long flops;
     unsigned long long steps;
+    unsigned long long long_flops = 0ull;  // COUNT only: flops / evaluations of positions outside the largest grid's box
+    unsigned long long long_evals = 0ull, evals = 0ull;
 };
 
 template <bool COUNT>
@@ -84,6 +87,26 @@ __device__ __forceinline__ float prim_distance(const DevScene &S, uint32_t word,
         else if (t >= 1.0f) d = distance(diff, xyz(r2));
         else d = distance(diff, xyz(r2) * t);
         return d - r1.w;
+    }
+    if (kind == FT_K_CONE) {  // EXTENSION, no reference implementation: exact capped-cone distance
+        add_flops<COUNT>(acc, FLOPS_CONE);
+        const float4 r1 = ld4(rec + 1), r2 = ld4(rec + 2), r3 = ld4(rec + 3);
+        const V3 ba = xyz(r2), pa = p - xyz(r1);
+        const float ra = r1.w, rb = r2.w, baba = r3.x, rba = r3.y, k = r3.z;
+        const float papa = dot(pa, pa);
+        const float paba = dot(pa, ba) / baba;
+        const float x2 = papa - (paba * paba) * baba;
+        const float x = sqrtf(x2 > 0.0f ? x2 : 0.0f);
+        const float cx = x - (paba < 0.5f ? ra : rb);
+        const float cax = cx > 0.0f ? cx : 0.0f;
+        const float cay = fabsf(paba - 0.5f) - 0.5f;
+        const float fr = (rba * (x - ra) + paba * baba) / k;
+        const float f = fr < 0.0f ? 0.0f : (fr > 1.0f ? 1.0f : fr);
+        const float cbx = (x - ra) - f * rba;
+        const float cby = paba - f;
+        const float da = cax * cax + (cay * cay) * baba, db = cbx * cbx + (cby * cby) * baba;
+        const float dm = sqrtf(da < db ? da : db);
+        return (cbx < 0.0f && cay < 0.0f) ? -dm : dm;
     }
     {  // triangle :227-250
         const float4 r1 = ld4(rec + 1);

@@ -280,7 +280,15 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         const unsigned m_long = __ballot_sync(FULL, wants && is_long), m_short = __ballot_sync(FULL, wants && !is_long);
         const bool run_long = m_short == 0u || __popc(m_long) >= FT_LONG_BATCH;
         if (wants && is_long == run_long) {
+            const unsigned long long f0 = acc.flops;
             const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc) : eval_form<COUNT>(S, S.root_word, p, acc);
+            if (COUNT) {
+                acc.evals++;
+                if (is_long) {
+                    acc.long_flops += acc.flops - f0;
+                    acc.long_evals++;
+                }
+            }
             if (phase <= PH_SHADOW) {  // SdfForm.fs:97-104
                 steps++;
                 if (COUNT) acc.steps++;
@@ -391,11 +399,14 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     const unsigned shadows = __reduce_add_sync(FULL, n_shadow);
     const unsigned capped = __reduce_add_sync(FULL, n_capped);
     const unsigned escaped = __reduce_add_sync(FULL, n_escaped);
-    unsigned long long st = acc.steps, fl = acc.flops;
+    unsigned long long st = acc.steps, fl = acc.flops, lf = acc.long_flops, le = acc.long_evals, ev = acc.evals;
     if (COUNT) {
         for (int k = 16; k > 0; k >>= 1) {
             st += __shfl_xor_sync(FULL, st, k);
             fl += __shfl_xor_sync(FULL, fl, k);
+            lf += __shfl_xor_sync(FULL, lf, k);
+            le += __shfl_xor_sync(FULL, le, k);
+            ev += __shfl_xor_sync(FULL, ev, k);
         }
     }
     if (lane == 0) {
@@ -408,6 +419,9 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         if (COUNT) {
             atomicAdd(s + FT_STAT_STEPS, st);
             atomicAdd(s + FT_STAT_FLOPS, fl);
+            atomicAdd(s + FT_STAT_LONG_FLOPS, lf);
+            atomicAdd(s + FT_STAT_LONG_EVALS, le);
+            atomicAdd(s + FT_STAT_EVALS, ev);
         }
     }
 }

@@ -47,6 +47,15 @@ class SceneBuilder:
         form = SdfForm.Primitive.capsule(From=center, To=to, Radius=radius)
         return SdfObject.create(self.randomMaterial(), form)
 
+    def randomCone(self) -> SdfObject:
+        """EXTENSION (the reference has no cone): randomCapsule's draws (Program.fs:39-46) with the tip radius 0"""
+        center = self.rng.pointInBall(4.0)
+        length = self.rng.range(0.5, 2.0)
+        to = (center + self.rng.pointOnSphere(length)).astype(f32)
+        radius = self.rng.range(0.1, 0.3)
+        form = SdfForm.Primitive.cone(From=center, To=to, FromRadius=float(radius) * 2.0, ToRadius=0.0)
+        return SdfObject.create(self.randomMaterial(), form)
+
     def randomTorus(self) -> SdfObject:  # Program.fs:48-55
         center = self.rng.pointInBall(4.0)
         normal = self.rng.pointOnSphere(1.0)
@@ -111,6 +120,18 @@ def spheres_capsules_scene(seed: int = 19, n_spheres: int = 512, n_capsules: int
                      Lights=default_lights())
     return Workload("config2_spheres_capsules_1080p", scene, default_camera(), ImageSize(width, height),
                     0.01, 30.0, objs)
+
+
+def spheres_cones_scene(seed: int = 19, n_spheres: int = 512, n_cones: int = 512, width: int = 1920,
+                        height: int = 1080) -> Workload:
+    """config 2 as BASELINE.json words it ("spheres + cones") -- EXTENSION: the cone primitive has no reference
+    implementation (SURVEY.md section 0), so this scene is a parity case against the repository's own CPU restatement;
+    the bench workload stays `spheres_capsules_scene`, whose primitives the reference defines."""
+    b = SceneBuilder(seed)
+    objs = [b.randomSphere() for _ in range(n_spheres)] + [b.randomCone() for _ in range(n_cones)]
+    scene = SdfScene(Object=SdfObject.union(objs), BackgroundColor=FColor.ofRGB(0.1, 0.1, 0.1),
+                     Lights=default_lights())
+    return Workload("config2b_spheres_cones_1080p", scene, default_camera(), ImageSize(width, height), 0.01, 30.0, objs)
 
 
 def mixed_scene(seed: int = 19, n_each: int = 256, width: int = 7680, height: int = 4320) -> Workload:

@@ -71,6 +71,9 @@ enum {
     FT_FORM_TORUS = 3,
     /* SdfForm.Primitive.triangle (SdfForm.fs:205-268) p = V1.xyz, V2.xyz, V3.xyz, Radius */
     FT_FORM_TRIANGLE = 4,
+    /* EXTENSION, not in the reference (BASELINE.json names cones; the reference has none):
+     * capped cone, p = From.xyz, To.xyz, FromRadius, ToRadius (exact distance)              */
+    FT_FORM_CONE = 5,
     /* SdfForm.union       (SdfForm.fs:14-40)   children = forms              */
     FT_FORM_UNION = 16,
     /* SdfForm.subtract    (SdfForm.fs:42-49)   children = [a, b]             */

@@ -451,6 +451,26 @@ static float form_distance(const onode *n, v3 p) {
         float dcircle = dcenter - n->r1;
         return sqrtf(dplane * dplane + dcircle * dcircle) - n->r2; /* Vector2.Length */
     }
+    case FT_FORM_CONE: { /* EXTENSION, no reference implementation: exact capped-cone distance.
+                            a = From, b = To - From, r0 = ra, r1 = rb, r2 = baba */
+        CNT(eval_capsule);
+        v3 pa = vsub(p, n->a);
+        float ra = n->r0, rb = n->r1, baba = n->r2, rba = rb - ra, k = rba * rba + baba;
+        float papa = vdot(pa, pa);
+        float paba = vdot(pa, n->b) / baba;
+        float x2 = papa - (paba * paba) * baba;
+        float x = sqrtf(x2 > 0.0f ? x2 : 0.0f);
+        float cx = x - (paba < 0.5f ? ra : rb);
+        float cax = cx > 0.0f ? cx : 0.0f;
+        float cay = fabsf(paba - 0.5f) - 0.5f;
+        float fr = (rba * (x - ra) + paba * baba) / k;
+        float f = fr < 0.0f ? 0.0f : (fr > 1.0f ? 1.0f : fr);
+        float cbx = (x - ra) - f * rba;
+        float cby = paba - f;
+        float da = cax * cax + (cay * cay) * baba, db = cbx * cbx + (cby * cby) * baba;
+        float dm = sqrtf(da < db ? da : db);
+        return (cbx < 0.0f && cay < 0.0f) ? -dm : dm;
+    }
     case FT_FORM_TRIANGLE: { /* SdfForm.fs:227-250 */
         v3 p1 = vsub(p, n->a), p2 = vsub(p, n->b), p3 = vsub(p, n->c);
         float d;
@@ -757,6 +777,16 @@ static onode *build_form(fto_scene *s, const ft_scene_desc *d, int id, int depth
         nd->r0 = -(vdot(nd->a, nd->b));
         nd->r1 = p[6]; nd->r2 = p[7];
         nd->boundary.c = nd->a; nd->boundary.r = p[6] + p[7];
+        break;
+    }
+    case FT_FORM_CONE: { /* EXTENSION (no reference) */
+        nd = new_node(s); nd->kind = f->kind;
+        v3 from = V(p[0], p[1], p[2]), to = V(p[3], p[4], p[5]);
+        nd->a = from; nd->b = vsub(to, from); nd->r0 = p[6]; nd->r1 = p[7]; nd->r2 = vdot(nd->b, nd->b);
+        if (!(nd->r2 > 0.0f) || !(p[6] >= 0.0f) || !(p[7] >= 0.0f)) { set_err(err, errlen, "cone: degenerate"); return NULL; }
+        float h = vdist(from, to) * 0.5f, rm = p[6] > p[7] ? p[6] : p[7];
+        nd->boundary.c = vlerp(from, to, 0.5f);
+        nd->boundary.r = sqrtf(h * h + rm * rm) * 1.000001f;
         break;
     }
     case FT_FORM_TRIANGLE: { /* SdfForm.fs:214-263 */

@@ -8,7 +8,7 @@ P = SdfForm.Primitive
 
 def random_primitive(rng, spread=2.5):
     c = rng.normal(size=3) * spread / 2
-    kind = rng.integers(0, 4)
+    kind = rng.integers(0, 5)
     if kind == 0:
         return P.sphere(Center=c, Radius=rng.uniform(0.2, 0.9))
     if kind == 1:
@@ -16,6 +16,10 @@ def random_primitive(rng, spread=2.5):
         return P.capsule(From=c, To=c + d / np.linalg.norm(d) * rng.uniform(0.3, 1.5), Radius=rng.uniform(0.1, 0.4))
     if kind == 2:
         return P.torus(Center=c, Normal=rng.normal(size=3), MajorRadius=rng.uniform(0.2, 0.7), MinorRadius=rng.uniform(0.08, 0.3))
+    if kind == 4:  # EXTENSION primitive (no reference): capped cone
+        d = rng.normal(size=3)
+        return P.cone(From=c, To=c + d / np.linalg.norm(d) * rng.uniform(0.3, 1.5), FromRadius=rng.uniform(0.0, 0.6),
+                      ToRadius=rng.uniform(0.0, 0.6))
     a, b = rng.normal(size=3), rng.normal(size=3)
     return P.triangle(V1=c, V2=c + a / np.linalg.norm(a) * rng.uniform(0.3, 0.9),
                       V3=c + b / np.linalg.norm(b) * rng.uniform(0.3, 0.9), Radius=rng.uniform(0.08, 0.3))
