@@ -1357,6 +1357,7 @@ static void glass_interact(const fto_scene *s, v3 ab, float nu, uint64_t seed, u
 typedef struct {
     const fto_scene *s; const ft_camera *cam; int W, H; float eps, len; int nl, max_bounces; uint64_t seed;
     float *out; volatile int64_t next;
+    int x0, xstride, ncols; /* columns x0, x0 + xstride, ... (ncols of them) */
 } sjob;
 
 static void spectral_pixel(const sjob *j, int x, int y, float *rgb) {
@@ -1414,21 +1415,25 @@ static void spectral_pixel(const sjob *j, int x, int y, float *rgb) {
 static void *spectral_worker(void *arg) {
     sjob *j = (sjob *)arg;
     for (;;) {
-        int64_t x = __sync_fetch_and_add(&j->next, 1);
-        if (x >= j->W) break;
+        int64_t i = __sync_fetch_and_add(&j->next, 1);
+        if (i >= j->ncols) break;
+        int64_t x = j->x0 + i * j->xstride;
         for (int y = 0; y < j->H; y++) spectral_pixel(j, (int)x, y, j->out + 3 * ((int64_t)x * j->H + y));
     }
     return NULL;
 }
+/* columns x_begin, x_begin + x_stride, ... < x_end only (the output is the full-size x-major array) */
 FTO_API int fto_render_spectral(const fto_scene *s, const ft_camera *cam, int W, int H, float eps, float len, int n_wavelengths,
-                                int max_bounces, uint64_t seed, int threads, float *out_rgb) {
+                                int max_bounces, uint64_t seed, int x_begin, int x_end, int x_stride, int threads,
+                                float *out_rgb) {
     if (!s || !cam || !out_rgb || W <= 0 || H <= 0 || n_wavelengths < 1 || n_wavelengths > 64 || max_bounces < 0 ||
-        s->n_lights > FT_SPECTRAL_MAX_LIGHTS)
+        s->n_lights > FT_SPECTRAL_MAX_LIGHTS || x_begin < 0 || x_end > W || x_stride < 1)
         return FT_ERR_INVALID_ARGUMENT;
     sjob j;
     memset(&j, 0, sizeof(j));
     j.s = s; j.cam = cam; j.W = W; j.H = H; j.eps = eps; j.len = len; j.nl = n_wavelengths; j.max_bounces = max_bounces;
     j.seed = seed; j.out = out_rgb; j.next = 0;
+    j.x0 = x_begin; j.xstride = x_stride; j.ncols = x_end > x_begin ? (x_end - x_begin + x_stride - 1) / x_stride : 0;
     if (threads < 1) threads = 1;
     pthread_t *t = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
     for (int i = 0; i < threads; i++) pthread_create(&t[i], NULL, spectral_worker, &j);
@@ -1481,6 +1486,7 @@ typedef struct {
     const fto_scene *s; const ft_camera *cam; int W, H; float eps, len; const ft_cloud_params *cp; int spp; uint64_t seed;
     float *out; volatile int64_t next;
     int64_t secondary, track_steps, scattered; pthread_mutex_t mu;
+    int x0, xstride, ncols;
 } cjob;
 typedef struct { int64_t secondary, track_steps, scattered; } cstat;
 
@@ -1622,8 +1628,9 @@ static void *cloud_worker(void *arg) {
     cjob *j = (cjob *)arg;
     cstat st = {0, 0, 0};
     for (;;) {
-        int64_t x = __sync_fetch_and_add(&j->next, 1);
-        if (x >= j->W) break;
+        int64_t i = __sync_fetch_and_add(&j->next, 1);
+        if (i >= j->ncols) break;
+        int64_t x = j->x0 + i * j->xstride;
         for (int y = 0; y < j->H; y++) {
             v3 sum = V(0.0f, 0.0f, 0.0f);
             for (int k = 0; k < j->spp; k++) sum = vadd(sum, cloud_sample(j, &st, (int)x, y, (uint32_t)k));
@@ -1638,13 +1645,15 @@ static void *cloud_worker(void *arg) {
 }
 /* counters (optional): {secondary marches, tracking steps, scattered samples} */
 FTO_API int fto_render_cloud(const fto_scene *s, const ft_camera *cam, int W, int H, float eps, float len, const ft_cloud_params *cp,
-                             int spp, uint64_t seed, int threads, float *out_rgb, int64_t *counters) {
+                             int spp, uint64_t seed, int x_begin, int x_end, int x_stride, int threads, float *out_rgb,
+                             int64_t *counters) {
     if (!s || !cam || !cp || !cp->perm || !cp->gradients || !out_rgb || W <= 0 || H <= 0 || spp < 1 || !(cp->step > 0.0f) ||
-        !(cp->fade > 0.0f))
+        !(cp->fade > 0.0f) || x_begin < 0 || x_end > W || x_stride < 1)
         return FT_ERR_INVALID_ARGUMENT;
     cjob j;
     memset(&j, 0, sizeof(j));
     j.s = s; j.cam = cam; j.W = W; j.H = H; j.eps = eps; j.len = len; j.cp = cp; j.spp = spp; j.seed = seed; j.out = out_rgb;
+    j.x0 = x_begin; j.xstride = x_stride; j.ncols = x_end > x_begin ? (x_end - x_begin + x_stride - 1) / x_stride : 0;
     pthread_mutex_init(&j.mu, NULL);
     if (threads < 1) threads = 1;
     pthread_t *t = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);

@@ -74,11 +74,11 @@ def lib():
         L.fto_root_boundary.argtypes = [vp, vp]
         L.fto_philox4x32_10.argtypes = [vp, vp, vp]
         L.fto_render_cloud.argtypes = [vp, P(A.ft_camera), C.c_int, C.c_int, f32, f32, P(A.ft_cloud_params), C.c_int,
-                                       C.c_uint64, C.c_int, vp, vp]
+                                       C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.fto_noise_gradient.restype = C.c_double
         L.fto_noise_gradient.argtypes = [vp, vp, C.c_double, C.c_double, C.c_double]
         L.fto_render_spectral.argtypes = [vp, P(A.ft_camera), C.c_int, C.c_int, f32, f32, C.c_int, C.c_int, C.c_uint64,
-                                          C.c_int, vp]
+                                          C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.fto_to_bitmap.restype = f32
         L.fto_to_bitmap.argtypes = [vp, C.c_int, C.c_int, f32, C.c_uint64, vp, C.c_int]
         _lib = L
@@ -177,16 +177,20 @@ class OracleScene:
             out["counters"] = ctr.as_dict()
         return out
 
-    def render_spectral(self, camera, X, Y, eps, length, n_wavelengths=16, max_bounces=8, seed=19, threads=None):
-        """EXTENSION (no reference implementation): CPU restatement of ft_render_spectral"""
+    def render_spectral(self, camera, X, Y, eps, length, n_wavelengths=16, max_bounces=8, seed=19, threads=None,
+                        x_begin=0, x_end=None, x_stride=1):
+        """EXTENSION (no reference implementation): CPU restatement of ft_render_spectral
+        (only the columns x_begin, x_begin + x_stride, ... < x_end of the full-size array are written)"""
         cam = camera.to_c() if hasattr(camera, "to_c") else camera
         rgb = np.zeros((X, Y, 3), np.float32)
         st = lib().fto_render_spectral(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), n_wavelengths,
-                                       max_bounces, C.c_uint64(seed), threads or os.cpu_count() or 1, _ptr(rgb))
+                                       max_bounces, C.c_uint64(seed), x_begin, X if x_end is None else x_end, x_stride,
+                                       threads or os.cpu_count() or 1, _ptr(rgb))
         assert st == 0, st
         return rgb
 
-    def render_cloud(self, camera, X, Y, eps, length, cloud, spp=64, seed=19, threads=None):
+    def render_cloud(self, camera, X, Y, eps, length, cloud, spp=64, seed=19, threads=None, x_begin=0, x_end=None,
+                     x_stride=1):
         """EXTENSION (no reference implementation): CPU restatement of ft_render_cloud.
         Returns (rgb [X,Y,3], dict(secondary, track_steps, scattered))"""
         cam = camera.to_c() if hasattr(camera, "to_c") else camera
@@ -194,7 +198,8 @@ class OracleScene:
         rgb = np.zeros((X, Y, 3), np.float32)
         ctr = np.zeros(3, np.int64)
         st = lib().fto_render_cloud(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), C.byref(cp), spp,
-                                    C.c_uint64(seed), threads or os.cpu_count() or 1, _ptr(rgb), _ptr(ctr))
+                                    C.c_uint64(seed), x_begin, X if x_end is None else x_end, x_stride,
+                                    threads or os.cpu_count() or 1, _ptr(rgb), _ptr(ctr))
         assert st == 0, st
         return rgb, dict(secondary=int(ctr[0]), track_steps=int(ctr[1]), scattered=int(ctr[2]))
 

@@ -173,3 +173,23 @@ def test_gpu_other_entry_points_reject_cloud_scenes():
         tracer.render_spectral(_camera(), ImageSize(16, 16), 0.01, 30.0)
     assert ei.value.code == A.FT_ERR_UNSUPPORTED_NODE
     tracer.close()
+
+
+@pytest.mark.gpu
+def test_gpu_config4_full_size_columns_bit_exact():
+    """BASELINE config 4 at its full size (1920x1080, 64 samples per pixel): every 80th column of the GPU frame equals the
+    CPU restatement bit for bit; re-rendering is idempotent"""
+    w = scenes.cloud_scene()
+    X, Y = w.size.X, w.size.Y
+    cp = CloudParams()
+    tracer = ft.SceneTracer(w.scene, device=0)
+    img, st = tracer.render_cloud(w.camera, w.size, w.epsilon, w.length, cp, 64, 19)
+    again, st2 = tracer.render_cloud(w.camera, w.size, w.epsilon, w.length, cp, 64, 19)
+    assert np.array_equal(bits(img), bits(again)) and st["capped_rays"] == 0
+    assert (st["shadow_rays"], st["march_steps"], st["reserved"]) == (st2["shadow_rays"], st2["march_steps"], st2["reserved"])
+    assert st["primary_rays"] == X * Y * 64
+    stride = 80
+    ref, _ = O.OracleScene(tracer.description).render_cloud(w.camera, X, Y, w.epsilon, w.length, cp, 64, 19, x_stride=stride)
+    cols = np.arange(0, X, stride)
+    assert np.array_equal(bits(img[cols]), bits(ref[cols]))
+    tracer.close()

@@ -174,3 +174,22 @@ def test_gpu_plain_render_rejects_glass_and_spectral_is_deterministic():
     b, _ = tracer.render_spectral(_camera(), ImageSize(200, 120), 0.01, 30.0, 16, 8, 7)
     assert np.array_equal(bits(a), bits(b))
     tracer.close()
+
+
+@pytest.mark.gpu
+def test_gpu_config3_full_size_columns_bit_exact():
+    """BASELINE config 3 at its full size (3840x2160, 16 wavelengths): every 96th column of the GPU frame equals the CPU
+    restatement bit for bit; re-rendering is idempotent; glass pixels are exactly those that go black with no bounce"""
+    w = scenes.spectral_glass_scene()
+    X, Y = w.size.X, w.size.Y
+    tracer = ft.SceneTracer(w.scene, device=0)
+    img, st = tracer.render_spectral(w.camera, w.size, w.epsilon, w.length, 16, 8, 19)
+    again, _ = tracer.render_spectral(w.camera, w.size, w.epsilon, w.length, 16, 8, 19)
+    assert np.array_equal(bits(img), bits(again)) and st["capped_rays"] == 0
+    stride = 96
+    ref = O.OracleScene(tracer.description).render_spectral(w.camera, X, Y, w.epsilon, w.length, 16, 8, 19, x_stride=stride)
+    cols = np.arange(0, X, stride)
+    assert np.array_equal(bits(img[cols]), bits(ref[cols]))
+    black, st0 = tracer.render_spectral(w.camera, w.size, w.epsilon, w.length, 16, 0, 19)
+    assert int((np.abs(black).max(axis=2) == 0.0).sum()) == st["reserved"] == st0["reserved"]
+    tracer.close()
