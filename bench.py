@@ -2,6 +2,7 @@
 """bench.py -- Mrays/s (primary + shadow rays) of the per-ray hot path, the metric BASELINE.json names.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config2|config1|config5]
+                    (--workload config3|config4: the extension workloads, not BASELINE bench lines -- see bench_extension)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -179,6 +180,79 @@ def bench_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the F# path (oracle/ft_oracle.c); .NET unavailable"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def bench_extension(args):
+    """--workload config3 | config4: the builder-defined extension workloads (spectral glass, volumetric clouds).
+    The reference has NO implementation of either, so these are not BASELINE bench lines; the same JSON
+    shape is printed for convenience.  Single GPU; the entry points take host buffers, so `value` is rays / device time of the
+    call's kernels (CUDA events inside the library) and `e2e` rays / wall time of the call with a page-locked output."""
+    import numpy as np
+
+    import fraytracer_b200 as ft
+    from fraytracer_b200 import _abi as A
+    from fraytracer_b200 import scenes
+    from oracle import oracle as O
+
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("the extension workloads are single-GPU (the path shards by pixel like Image.render, not built)")
+    lib = ft.load_library()
+    spectral = args.workload == "config3"
+    w = scenes.spectral_glass_scene() if spectral else scenes.cloud_scene()
+    X, Y = w.size.X, w.size.Y
+    tracer = ft.SceneTracer(w.scene, device=0)
+    cp = ft.CloudParams()
+    host = C.c_void_p()
+    A.check(lib.ft_host_alloc(C.byref(host), X * Y * 12))
+    out = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(X, Y, 3))
+
+    def call():
+        if spectral:
+            return tracer.render_spectral(w.camera, w.size, w.epsilon, w.length, 16, 8, 19, out=out)[1]
+        return tracer.render_cloud(w.camera, w.size, w.epsilon, w.length, cp, 64, 19, out=out)[1]
+
+    sampler = ClockSampler(0)
+    for _ in range(max(args.warmup, 3)):
+        call()
+    kern_ms = wall = 0.0
+    t_begin = time.time()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        st = call()
+        wall += time.perf_counter() - t0
+        kern_ms += st["kernel_ms"]
+    clocks = sampler.stop(t_begin, time.time())
+    rays = st["primary_rays"] + st["shadow_rays"]
+    cpu = None
+    if not args.no_cpu:
+        orc = O.OracleScene(tracer.description)
+        threads = os.cpu_count() or 1
+        stride = 1 if spectral else 2  # 10-20 s of CPU work on 16 cores
+        t0 = time.perf_counter()
+        if spectral:
+            orc.render_spectral(w.camera, X, Y, w.epsilon, w.length, 16, 8, 19, threads=threads, x_stride=stride)
+        else:
+            orc.render_cloud(w.camera, X, Y, w.epsilon, w.length, cp, 64, 19, threads=threads, x_stride=stride)
+        dt = time.perf_counter() - t0
+        frac = len(range(0, X, stride)) / X
+        cpu = {"value": rays * frac / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"every {stride}th column of the {X}x{Y} frame ({dt:.1f} s; rays = the GPU frame's count x {frac:.4f})",
+               "note": "CPU restatement of this repository's own extension spec; the reference has no such path"}
+    A.check(lib.ft_host_free(host))
+    print(json.dumps({
+        "metric": METRIC, "value": rays * args.steps / kern_ms / 1e3, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": kern_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if spectral else "f32 (+ f64 lattice noise)", "data": "synthetic",
+        "config": {"workload": w.name, "image": f"{X}x{Y}", "rays_per_step": rays,
+                   "extension": "no reference implementation exists (DESIGN.md 4.6 / 4.7): parity is against this "
+                                "repository's own CPU restatement",
+                   "parameters": "16 wavelengths, <= 8 glass interactions" if spectral else "64 samples per pixel",
+                   "capped_rays": st["capped_rays"], "mode": "strict"},
+        "clocks": clocks,
+        "e2e": {"value": rays * args.steps / wall / 1e6, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(A.ft_camera) + 32,
+                "d2h_bytes_per_step": X * Y * 12, "ms_per_step": 1e3 * wall / args.steps},
+        "gpu_launches": args.steps * st["launches"], "roofline": None, "cpu_baseline": cpu,
     }))
 
 
@@ -377,13 +451,20 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config5"])
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config5", "config3", "config4"])
     ap.add_argument("--fast", action="store_true", help="FT_FLAG_FAST_MATH (FMA contraction, not bit-exact)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--gather", default=None, choices=["p2p", "nccl"],
                     help="N > 1: how the framebuffer is gathered (default p2p: peer stores fused into the render kernel)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload in ("config3", "config4"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "config3 / config4 are builder-defined extensions: the "
+                              "reference has no such path (SURVEY.md section 0)"}))
+            return
+        args.steps = min(args.steps, 5)
+        bench_extension(args)
+    elif args.impl == "reference":
         bench_reference(args)
     else:
         bench_b200(args)
