@@ -367,25 +367,39 @@ def bench_b200(args):
     else:
         # N > 1: the FColor[X,Y] lives in shared page-locked host memory; every rank's kernel stores its own strips there
         # over its own PCIe link (no device framebuffer, no gather, no device->host copy); a 4-byte all-reduce ends the frame
-        host = renderer.host_frame()
+        try:
+            host = renderer.host_frame()
+            host_ok = 1.0
+        except Exception as e:  # noqa: BLE001  (shared memory / registration unavailable on this box)
+            print(f"[bench] shared host framebuffer unavailable on rank {rank}: {e}", file=sys.stderr)
+            host, host_ok = None, 0.0
+        host_ok = allreduce(host_ok, dist.ReduceOp.MIN) > 0.5  # every rank or none
+        pinned = torch.empty((X, Y, 3), dtype=torch.float32, pin_memory=True) if (rank == 0 and not host_ok) else None
         e2e_s = 0.0
         for it in range(args.steps + 2):
             flush.zero_()
             barrier()
             t0 = time.perf_counter()
-            renderer.render_to_host(w.camera, w.epsilon, w.length, flags)
+            if host_ok:
+                renderer.render_to_host(w.camera, w.epsilon, w.length, flags)
+            else:  # device gather, then one copy of the whole frame from rank 0
+                final = renderer.render(w.camera, w.epsilon, w.length, flags)
+                if rank == 0:
+                    pinned.copy_(final, non_blocking=True)
+                torch.cuda.synchronize()
             if it >= 2:
                 e2e_s += time.perf_counter() - t0
         e2e_s = allreduce(e2e_s, dist.ReduceOp.MAX)
-        checksum = float(host[::97, ::89].sum()) if rank == 0 else 0.0
-        if rank == 0:  # the host frame is the device-gathered frame, bit for bit
+        if host_ok:
+            checksum = float(host[::97, ::89].sum()) if rank == 0 else 0.0
             final = renderer.render(w.camera, w.epsilon, w.length, flags)
             torch.cuda.synchronize()
-            assert np.array_equal(final.cpu().numpy().view(np.uint32), host.view(np.uint32)), "host frame differs"
+            if rank == 0:  # the host frame is the device-gathered frame, bit for bit
+                assert np.array_equal(final.cpu().numpy().view(np.uint32), host.view(np.uint32)), "host frame differs"
         else:
-            renderer.render(w.camera, w.epsilon, w.length, flags)
+            checksum = float(pinned[::97, ::89].sum()) if rank == 0 else 0.0
         h2d = C.sizeof(A.ft_camera) + 16
-        e2e_launches = 1
+        e2e_launches = 1 if host_ok else renderer.launches_per_frame
     e2e_value = total_rays * args.steps / e2e_s / 1e6
 
     if rank == 0:

@@ -86,30 +86,55 @@ class DistributedRenderer:
             # stream has moved past that frame.
             lib, nbytes = tracer.lib, X * Y * 12
             self.frames, self.dst = [], []
+            problem = None
             for parity in range(2):
-                ptr = C.c_void_p()
-                A.check(lib.ft_device_alloc(tracer.device, nbytes, C.byref(ptr)))
-                self._owned.append(ptr)
-                handle = (C.c_uint8 * 64)()
-                A.check(lib.ft_ipc_export(tracer.device, ptr, handle))
+                ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+                try:
+                    A.check(lib.ft_device_alloc(tracer.device, nbytes, C.byref(ptr)))
+                    self._owned.append(ptr)
+                    A.check(lib.ft_ipc_export(tracer.device, ptr, handle))
+                except A.FrayTracerError as e:
+                    problem = problem or str(e)
                 handles = [None] * self.world
-                dist.all_gather_object(handles, bytes(handle), group=group)
+                dist.all_gather_object(handles, (bytes(handle), problem), group=group)  # collective: every rank takes part
+                problem = problem or next((p for _, p in handles if p), None)
                 ptrs = []
-                for r, h in enumerate(handles):
+                for r, (h, _) in enumerate(handles):
+                    if problem:
+                        break
                     if r == self.rank:
                         ptrs.append(ptr.value)
-                    else:
-                        peer = C.c_void_p()
+                        continue
+                    peer = C.c_void_p()
+                    try:
                         A.check(lib.ft_ipc_import(tracer.device, (C.c_uint8 * 64).from_buffer_copy(h), C.byref(peer)))
                         self._imported.append(peer)
                         ptrs.append(peer.value)
+                    except A.FrayTracerError as e:
+                        problem = str(e)
                 self.dst.append(ptrs)
-                self.frames.append(torch.as_tensor(_DeviceArray(ptr.value, (X, Y, 3)), device=dev))
-            self.final = self.frames[0]
-            self._done = torch.zeros(1, dtype=torch.int32, device=dev)
-            self._frame = 0
-            self.launches_per_frame = 1
-            return
+                if not problem:
+                    self.frames.append(torch.as_tensor(_DeviceArray(ptr.value, (X, Y, 3)), device=dev))
+            # peer mapping must work on EVERY rank; otherwise all ranks use the NCCL all-gather (still a GPU path)
+            votes = [None] * self.world
+            dist.all_gather_object(votes, problem, group=group)
+            problem = next((p for p in votes if p), None)
+            if problem is None:
+                self.final = self.frames[0]
+                self._done = torch.zeros(1, dtype=torch.int32, device=dev)
+                self._frame = 0
+                self.launches_per_frame = 1
+                return
+            import warnings
+
+            warnings.warn(f"CUDA IPC peer mapping unavailable ({problem}); gathering the framebuffer with NCCL instead")
+            for p in self._imported:
+                lib.ft_ipc_close(tracer.device, p)
+            dist.barrier(group=group)
+            for p in self._owned:
+                lib.ft_device_free(tracer.device, p)
+            self._owned, self._imported, self.frames, self.dst = [], [], [], []
+            self.gather = "nccl"
         self.final = torch.empty((X, Y, 3), dtype=torch.float32, device=dev)
         if self.world > 1:
             chunks = max(1, min(int(chunks), self.spr))
