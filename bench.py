@@ -455,6 +455,7 @@ def bench_b200(args):
             "roofline": roofline, "cpu_baseline": cpu,
         }))
     if world > 1:
+        renderer.close()  # IPC mappings, shared host framebuffer
         dist.barrier()
         dist.destroy_process_group()
 
