@@ -18,6 +18,7 @@
 // instructions: the divergence this config stresses is confined to the (cheap) transition code.
 #include <cuda_runtime.h>
 
+#define FT_WITH_CONE 1
 #define FT_NS ft_cloud
 #include "cloud.h"
 #include "kernels.h"
@@ -103,8 +104,9 @@ __global__ void __launch_bounds__(CB, 4) cloud_kernel(const __grid_constant__ De
     const V3 cam = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
     const V3 bg = V3{S.bg[0], S.bg[1], S.bg[2]};
     Acc acc{0ull, 0ull};
+    uint32_t best_dummy = 0u;  // eval_chain's arg-min note, unused here
     // Distance at the common origin of all camera rays, once per warp
-    const float d0 = CHAIN ? eval_chain<false>(S, cam, acc) : eval_form<false>(S, S.root_word, cam, acc);
+    const float d0 = CHAIN ? eval_chain<false>(S, cam, acc, best_dummy) : eval_form<false>(S, S.root_word, cam, acc);
 
     int phase = C_FETCH;
     bool have_tile = false, active = false, cloud_mode = false;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(CB, 4) cloud_kernel(const __grid_constant__ De
         }
         // ------------------------------------------------------------------ the one distance evaluation
         if (phase > C_FETCH && event == 0) {
-            const float dist = CHAIN ? eval_chain<false>(S, p, acc) : eval_form<false>(S, S.root_word, p, acc);
+            const float dist = CHAIN ? eval_chain<false>(S, p, acc, best_dummy) : eval_form<false>(S, S.root_word, p, acc);
             if (phase <= C_SHADOW) {
                 steps++;
                 if (dist < eps) {

@@ -94,6 +94,13 @@ struct DevScene {
     // records [1..3] of U (aabbMin | cellBase, cellSizeInv, counts): kernel-parameter copies, so that the chain
     // evaluator's cell lookup starts from the constant bank instead of three dependent global loads
     float4 chain_g1, chain_g2, chain_g3;
+    // When the object tree above U is subtract / intersect objects over ONE SdfObject.union whose form is U (the shape of
+    // the reference's scenes), the material arg-min of SdfObject.fs:27-46 at the hit point is the candidate that set the
+    // running minimum of the hit's own Distance evaluation (same grid, same order, same two pruning tests, and `d < min`
+    // updates exactly when Min(min, d) changes): the chain evaluator notes it and no second scan is needed.
+    // obj_links[chain_mat_links + child position] is the leaf object.
+    int32_t chain_mat_valid;
+    int32_t chain_mat_links;
 };
 enum : uint32_t {
     FT_OP_INTERSECT = 1,  // if v < dist(C,p)+R then v = Max(v, D(p))      SdfForm.fs:62-63

@@ -19,6 +19,13 @@ namespace {
 
 constexpr unsigned kCounterRing = 256;
 
+// Three builds of the hot-path kernels: strict without the extension cone primitive (the reference's own primitives: the
+// default and benchmarked path -- even an untaken cone branch inside the one evaluator call site cost scenes without cones
+// 4 %, measured), strict with it (chosen only when the scene holds a cone), and the contracted (FMA) build.
+#define FT_DISPATCH(FAST, FN, ...)                                                           \
+    ((FAST) ? ft_fast::FN(__VA_ARGS__)                                                       \
+            : (scene->host.has_cone ? ft_strict_cone::FN(__VA_ARGS__) : ft_strict::FN(__VA_ARGS__)))
+
 thread_local std::string g_last_error;
 
 int fail(int code, const std::string &msg) {
@@ -319,6 +326,9 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
     s->dev.chain_union = h.chain_union;
     s->dev.chain_n_ops = h.chain_n_ops;
     s->dev.chain_ops = h.chain_ops;
+    s->dev.chain_mat_valid = h.chain_mat_valid;
+    s->dev.chain_mat_links = h.chain_mat_links;
+    if (getenv("FT_NO_CHAIN_MAT")) s->dev.chain_mat_valid = 0;  // experiments / tests of the separate arg-min scan
     if (h.chain_valid) {
         s->dev.chain_g1 = h.nodes[(size_t)h.chain_union + 1];
         s->dev.chain_g2 = h.nodes[(size_t)h.chain_union + 2];
@@ -491,9 +501,7 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
     if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     unsigned long long *wc;
     CU(fresh_counter(scene, s, &wc));
-    cudaError_t e = (flags & FT_FLAG_FAST_MATH)
-                        ? ft_fast::launch_render(scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, scene->d_stats, count, scene->sm_count, s)
-                        : ft_strict::launch_render(scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, scene->d_stats, count, scene->sm_count, s);
+    cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render, scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, scene->d_stats, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -536,9 +544,7 @@ FT_API int ft_render_gather_device(ft_scene *scene, const ft_camera *camera, int
     if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     unsigned long long *wc;
     CU(fresh_counter(scene, s, &wc));
-    cudaError_t e = (flags & FT_FLAG_FAST_MATH)
-                        ? ft_fast::launch_render_gather(scene->dev, *camera, P, d_dst, n_dst, wc, scene->d_stats, count, scene->sm_count, s)
-                        : ft_strict::launch_render_gather(scene->dev, *camera, P, d_dst, n_dst, wc, scene->d_stats, count, scene->sm_count, s);
+    cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render_gather, scene->dev, *camera, P, d_dst, n_dst, wc, scene->d_stats, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "render-gather kernel launch");
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -643,8 +649,7 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
             RenderParams P = make_params(width, height, epsilon, length, width, 0, 1);
             unsigned long long *wc;
             CU(fresh_counter(scene, s, &wc));
-            cudaError_t e = fast ? ft_fast::launch_render(scene->dev, *camera, P, m_rgb, m_leaf, wc, scene->d_stats, count, scene->sm_count, s)
-                                 : ft_strict::launch_render(scene->dev, *camera, P, m_rgb, m_leaf, wc, scene->d_stats, count, scene->sm_count, s);
+            cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, m_rgb, m_leaf, wc, scene->d_stats, count, scene->sm_count, s);
             if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
             CU(cudaEventRecord(scene->ev[1], s));
             CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -685,8 +690,7 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
         int32_t *band_leaf = d_leaf ? d_leaf + (size_t)x0 * height : nullptr;
         unsigned long long *wc;
         CU(fresh_counter(scene, bs, &wc));
-        cudaError_t e = fast ? ft_fast::launch_render(scene->dev, *camera, P, band_rgb, band_leaf, wc, scene->d_stats, count, scene->sm_count, bs)
-                             : ft_strict::launch_render(scene->dev, *camera, P, band_rgb, band_leaf, wc, scene->d_stats, count, scene->sm_count, bs);
+        cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, band_rgb, band_leaf, wc, scene->d_stats, count, scene->sm_count, bs);
         if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
         launches++;
         CU(cudaEventRecord((launches & 1) ? scene->ev[1] : scene->ev[3], bs));  // end of the last kernel on each stream
@@ -769,9 +773,7 @@ FT_API int ft_trace_rays(ft_scene *scene, int64_t n, const ft_ray *rays, uint32_
     CU(cudaEventRecord(scene->ev[3], s));
     unsigned long long *wc;
     CU(fresh_counter(scene, s, &wc));
-    cudaError_t e = (flags & FT_FLAG_FAST_MATH)
-                        ? ft_fast::launch_trace_rays(scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, wc, scene->d_stats, count, scene->sm_count, s)
-                        : ft_strict::launch_trace_rays(scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, wc, scene->d_stats, count, scene->sm_count, s);
+    cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_trace_rays, scene->dev, d_rays, n, d_rgb, d_leaf, d_steps, d_shadow, wc, scene->d_stats, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "trace_rays kernel launch");
     CU(cudaEventRecord(scene->ev[1], s));
     if (out_rgb) CU(cudaMemcpyAsync(out_rgb, d_rgb, rgb_bytes, cudaMemcpyDeviceToHost, s));
@@ -805,8 +807,7 @@ FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint3
     float *d_out = d_pts + 3 * N;
     cudaStream_t s = scene->stream;
     CU(cudaMemcpyAsync(d_pts, positions, N * 12, cudaMemcpyHostToDevice, s));
-    cudaError_t e = (flags & FT_FLAG_FAST_MATH) ? ft_fast::launch_distance(scene->dev, d_pts, n, d_out, s)
-                                                : ft_strict::launch_distance(scene->dev, d_pts, n, d_out, s);
+    cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_distance, scene->dev, d_pts, n, d_out, s);
     if (e != cudaSuccess) return cuda_fail(e, "distance kernel launch");
     CU(cudaMemcpyAsync(out_distance, d_out, N * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));

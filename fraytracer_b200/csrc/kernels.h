@@ -42,6 +42,7 @@ struct RenderParams {
     }
 
 FT_DECLARE_LAUNCHERS(ft_strict)
+FT_DECLARE_LAUNCHERS(ft_strict_cone)
 FT_DECLARE_LAUNCHERS(ft_fast)
 
 // util_kernels.cu

@@ -376,6 +376,7 @@ class Compiler {
                     return fail(FT_ERR_INVALID_ARGUMENT, "cone: From and To must differ and the radii must be >= 0");
                 const float h = distance(from, to) * 0.5f, rm = ra > rb ? ra : rb;
                 nd.b = Bnd{lerp(from, to, 0.5f), sqrtf(h * h + rm * rm) * 1.000001f};  // rim of the larger cap, a hair of slack
+                out_->has_cone = 1;
                 nodes_.push_back(nd);
                 idx = (int)nodes_.size() - 1;
                 break;
@@ -719,6 +720,22 @@ class Compiler {
         }
         if (o.obj_links.empty()) o.obj_links.push_back(0);
         o.root_object = obj_node_[(size_t)d_->root_object];
+        if (o.chain_valid) {  // material arg-min from the hit evaluation (device_scene.h)
+            int ob = o.root_object;
+            int guard = 0;
+            while ((objs_[(size_t)ob].kind == FT_OBJECT_SUBTRACT || objs_[(size_t)ob].kind == FT_OBJECT_INTERSECT) && guard++ < 1024)
+                ob = objs_[(size_t)ob].base;
+            const ObjNode &u = objs_[(size_t)ob];
+            if (u.kind == FT_OBJECT_UNION && FT_WORD_OFF(nodes_[(size_t)u.form].word) == o.chain_union &&
+                nodes_[(size_t)u.form].kind == FT_FORM_UNION && u.kids.size() == nodes_[(size_t)u.form].kids.size()) {
+                bool leaves = true;
+                for (int k : u.kids) leaves = leaves && objs_[(size_t)k].kind == FT_OBJECT_LEAF;
+                if (leaves) {
+                    o.chain_mat_valid = 1;
+                    o.chain_mat_links = o.objects[(size_t)ob].z;
+                }
+            }
+        }
         o.root_word = nodes_[(size_t)objs_[(size_t)o.root_object].form].word;
         // 5. materials, lights, background
         for (int i = 0; i < d_->n_materials; i++)

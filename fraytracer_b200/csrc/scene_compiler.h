@@ -44,9 +44,11 @@ struct CompiledScene {
     float esc_lo[3] = {0, 0, 0}, esc_hi[3] = {0, 0, 0};  // escape box (device_scene.h)
     int32_t esc_valid = 0;
     int32_t chain_valid = 0, chain_n_ops = 0;
+    int32_t chain_mat_valid = 0, chain_mat_links = 0;  // device_scene.h
     uint32_t chain_union = 0, chain_ops = 0;
     int32_t n_nodes = 0, n_primitives = 0, max_depth = 0;
     int32_t grids_built_on_gpu = 0;
+    int32_t has_cone = 0;   // a form is FT_FORM_CONE (extension primitive): selects the kernel build that evaluates it
     int32_t has_cloud = 0;  // a leaf uses FT_MATERIAL_CLOUD (volumetric extension): only ft_render_cloud renders it
     int32_t has_glass = 0;  // a leaf uses FT_MATERIAL_GLASS (spectral extension): only ft_render_spectral renders it
 };

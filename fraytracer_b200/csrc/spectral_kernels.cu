@@ -21,6 +21,7 @@
 // deterministic.
 #include <cuda_runtime.h>
 
+#define FT_WITH_CONE 1
 #define FT_NS ft_spectral
 #include "kernels.h"
 #include "philox.h"
@@ -139,10 +140,11 @@ __global__ void __launch_bounds__(SB, 4) spectral_trace_kernel(const __grid_cons
     constexpr int NB = PRIMARY ? 6 : 1;
 
     Acc acc{0ull, 0ull};
+    uint32_t best_dummy = 0u;  // eval_chain's arg-min note, unused here
     float d0 = 0.f;
     if (PRIMARY) {  // Distance at the common origin of all primary rays, once per warp
         const V3 c = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
-        d0 = CHAIN ? eval_chain<false>(S, c, acc) : eval_form<false>(S, S.root_word, c, acc);
+        d0 = CHAIN ? eval_chain<false>(S, c, acc, best_dummy) : eval_form<false>(S, S.root_word, c, acc);
     }
 
     int phase = SP_FETCH;
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(SB, 4) spectral_trace_kernel(const __grid_cons
             else if (phase == SP_N2) p.z = q.z + h;
         }
         if (phase > SP_FETCH && event == 0) {
-            const float dist = CHAIN ? eval_chain<false>(S, p, acc) : eval_form<false>(S, S.root_word, p, acc);
+            const float dist = CHAIN ? eval_chain<false>(S, p, acc, best_dummy) : eval_form<false>(S, S.root_word, p, acc);
             if (phase == SP_MARCH) {
                 if (!armed) sign = dist < 0.0f ? -1.0f : 1.0f;  // the medium: inside glass the march runs on -Distance
                 const float sd = sign * dist;

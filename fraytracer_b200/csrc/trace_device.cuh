@@ -40,6 +40,14 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #ifndef FT_SCAN_UNROLL
 #define FT_SCAN_UNROLL 2  // candidates per round of the scan loop (2 or 4).  Measured on B200: 4 is 2 % faster on config 2 and 5, 2.5 % slower on config 1
 #endif
+#ifndef FT_CHAIN_MAT
+#define FT_CHAIN_MAT 0  // 1: the chain evaluator notes its arg-min candidate, so the material lookup of a hit needs no second scan.
+                       // Bit-exact (all parity tests), but measured on B200: config 1 -2.4 %, config 2 -2.8 %, config 5 +2 % -- the
+                       // note costs a register in the scan loop; off
+#endif
+#ifndef FT_WITH_CONE
+#define FT_WITH_CONE 0
+#endif
 #ifndef FT_INLINE_PRIM
 #define FT_INLINE_PRIM 0  // 1: primitives met by the candidate scan are evaluated inside the scan loop
 #endif
@@ -58,6 +66,31 @@ __device__ __forceinline__ void add_flops(Acc &a, int n) {
 
 __device__ __forceinline__ float4 ld4(const float4 *p) { return __ldg(p); }
 __device__ __forceinline__ V3 xyz(float4 v) { return V3{v.x, v.y, v.z}; }
+
+// ---- EXTENSION primitive, no reference implementation: exact capped-cone distance.  Compiled only into
+// the builds that define FT_WITH_CONE: inside the one evaluator call site even the untaken branch cost scenes WITHOUT cones
+// 4 % (config 1 and 5, measured on B200 -- code size and register allocation of the hot loop), inlined or as a call.
+#if FT_WITH_CONE
+__device__ __forceinline__ float cone_distance(const float4 *rec, V3 p) {
+    const float4 r1 = ld4(rec + 1), r2 = ld4(rec + 2), r3 = ld4(rec + 3);
+    const V3 ba = xyz(r2), pa = p - xyz(r1);
+    const float ra = r1.w, rb = r2.w, baba = r3.x, rba = r3.y, k = r3.z;
+    const float papa = dot(pa, pa);
+    const float paba = dot(pa, ba) / baba;
+    const float x2 = papa - (paba * paba) * baba;
+    const float x = sqrtf(x2 > 0.0f ? x2 : 0.0f);
+    const float cx = x - (paba < 0.5f ? ra : rb);
+    const float cax = cx > 0.0f ? cx : 0.0f;
+    const float cay = fabsf(paba - 0.5f) - 0.5f;
+    const float fr = (rba * (x - ra) + paba * baba) / k;
+    const float f = fr < 0.0f ? 0.0f : (fr > 1.0f ? 1.0f : fr);
+    const float cbx = (x - ra) - f * rba;
+    const float cby = paba - f;
+    const float da = cax * cax + (cay * cay) * baba, db = cbx * cbx + (cby * cby) * baba;
+    const float dm = sqrtf(da < db ? da : db);
+    return (cbx < 0.0f && cay < 0.0f) ? -dm : dm;
+}
+#endif
 
 // ---- primitives (SdfForm.fs:117-268); b0 = record[0] = bounding sphere, already loaded
 template <bool COUNT>
@@ -88,26 +121,12 @@ __device__ __forceinline__ float prim_distance(const DevScene &S, uint32_t word,
         else d = distance(diff, xyz(r2) * t);
         return d - r1.w;
     }
-    if (kind == FT_K_CONE) {  // EXTENSION, no reference implementation: exact capped-cone distance
+#if FT_WITH_CONE
+    if (kind == FT_K_CONE) {  // EXTENSION primitive
         add_flops<COUNT>(acc, FLOPS_CONE);
-        const float4 r1 = ld4(rec + 1), r2 = ld4(rec + 2), r3 = ld4(rec + 3);
-        const V3 ba = xyz(r2), pa = p - xyz(r1);
-        const float ra = r1.w, rb = r2.w, baba = r3.x, rba = r3.y, k = r3.z;
-        const float papa = dot(pa, pa);
-        const float paba = dot(pa, ba) / baba;
-        const float x2 = papa - (paba * paba) * baba;
-        const float x = sqrtf(x2 > 0.0f ? x2 : 0.0f);
-        const float cx = x - (paba < 0.5f ? ra : rb);
-        const float cax = cx > 0.0f ? cx : 0.0f;
-        const float cay = fabsf(paba - 0.5f) - 0.5f;
-        const float fr = (rba * (x - ra) + paba * baba) / k;
-        const float f = fr < 0.0f ? 0.0f : (fr > 1.0f ? 1.0f : fr);
-        const float cbx = (x - ra) - f * rba;
-        const float cby = paba - f;
-        const float da = cax * cax + (cay * cay) * baba, db = cbx * cbx + (cby * cby) * baba;
-        const float dm = sqrtf(da < db ? da : db);
-        return (cbx < 0.0f && cay < 0.0f) ? -dm : dm;
+        return cone_distance(rec, p);
     }
+#endif
     {  // triangle :227-250
         const float4 r1 = ld4(rec + 1);
         const V3 p1 = p - xyz(r1), p2 = p - xyz(ld4(rec + 2)), p3 = p - xyz(ld4(rec + 3));
@@ -367,8 +386,10 @@ __device__ __forceinline__ float eval_form(const DevScene &S, uint32_t root, V3 
 //   v = U(p)  (SdfForm.fs:22-34),  then  v = op_k(v)  for the intersect / subtract operations above U.
 // Bit-identical to eval_form on such scenes; it only drops the interpreter's dispatch.  The candidate loop is
 // "scan until a child must be evaluated, converge, evaluate": lanes share the primitive-evaluation code.
+// `best_lo` receives the low 32 address bits of the candidate record that set the running minimum last (the arg-min
+// of SdfObject.fs:27-46, see DevScene::chain_mat_valid); callers that do not need it pass a dummy and the stores vanish.
 template <bool COUNT>
-__device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
+__device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, uint32_t &best_lo) {
     uint32_t i;
     float dtc;
     add_flops<COUNT>(acc, FLOPS_CELL_LOOKUP);
@@ -380,8 +401,14 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
     // an exit notes K in `kx` and `ep` is brought up to date outside.
     const float4 *ep = S.entries + 2ull * i;
 #define FT_LD_ENTRY(K) Entry{__ldg(ep + 2 * (K)), __ldg(ep + 2 * (K) + 1)}
+#if FT_CHAIN_MAT
+#define FT_NOTE_BEST(K) best_lo = (uint32_t)(uintptr_t)(ep + 2 * (K))
+#else
+#define FT_NOTE_BEST(K) (void)0
+#endif
 #else
 #define FT_LD_ENTRY(K) ld_entry(S, i + (K))
+#define FT_NOTE_BEST(K) best_lo = (uint32_t)(uintptr_t)(S.entries + 2ull * (i + (K)))
 #endif
     for (;;) {
         uint32_t w = 0u;
@@ -402,6 +429,7 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
         if (bound_test(m, (E).bound(), p, bd)) {                              \
             if (FT_WORD_KIND((E).word()) == FT_K_SPHERE) {                    \
                 m = bd;                                                       \
+                FT_NOTE_BEST(K);                                              \
                 add_flops<COUNT>(acc, FLOPS_MINMAX);                          \
             } else {                                                          \
                 need = true;                                                  \
@@ -445,7 +473,13 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
 #endif
 #undef FT_CHAIN_ONE
         if (!need) break;
-        m = fminf(m, prim_distance<COUNT>(S, w, b0, p, acc));  // SdfForm.fs:33
+        {
+            const float dprim = prim_distance<COUNT>(S, w, b0, p, acc);
+            if (dprim < m) {  // == Min(m, dprim) (SdfForm.fs:33); `d < min` is also the arg-min's update rule (SdfObject.fs:41)
+                m = dprim;
+                FT_NOTE_BEST(kx);
+            }
+        }
         add_flops<COUNT>(acc, FLOPS_MINMAX);
 #if FT_SCAN_PTR
         ep += 2 * (kx + 1);
@@ -454,6 +488,7 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc) {
 #endif
     }
 #undef FT_LD_ENTRY
+#undef FT_NOTE_BEST
     float v = m;
     // (measured: also serving the chain operations' operands from the constant bank, unrolled, made config 1 4 % slower
     // -- four inlined copies of the primitive evaluator)
@@ -521,6 +556,17 @@ __device__ int material_leaf(const DevScene &S, V3 p, Acc &acc) {
         }
         o = __ldg(S.obj_links + rec.z + ld_entry(S, best).child());
     }
+}
+
+// ---- the leaf object from the hit evaluation's arg-min candidate (DevScene::chain_mat_valid): `best_lo` are the low address
+// bits of that candidate's record, p the hit point (its cell is looked up again to anchor the 32-bit difference)
+__device__ __forceinline__ int chain_leaf_from_best(const DevScene &S, V3 p, uint32_t best_lo) {
+    uint32_t begin;
+    float dtc;
+    grid_cell_from(S, S.chain_g1, S.chain_g2, S.chain_g3, p, begin, dtc);
+    const uint32_t first_lo = (uint32_t)(uintptr_t)(S.entries + 2ull * begin);
+    const uint32_t idx = begin + ((best_lo - first_lo) >> 5);  // 32-byte records; a cell's list is far shorter than 2^27
+    return __ldg(S.obj_links + S.chain_mat_links + ld_entry(S, idx).child());
 }
 
 // ---- escape proof (device_scene.h "Escape box"): true when the half-line {o + t d, t >= 0} certainly stays

@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         const bool run_long = m_short == 0u || __popc(m_long) >= FT_LONG_BATCH;
         if (wants && is_long == run_long) {
             const unsigned long long f0 = acc.flops;
-            const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc) : eval_form<COUNT>(S, S.root_word, p, acc);
+            uint32_t best_lo = 0u;
+            const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
             if (COUNT) {
                 acc.evals++;
                 if (is_long) {
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                 if (COUNT) acc.steps++;
                 if (dist < eps) {
                     event = phase == PH_PRIMARY ? 2 : 4;
+                    if (FT_CHAIN_MAT && CHAIN && phase == PH_PRIMARY) leaf_obj = (int)best_lo;  // the hit evaluation's arg-min candidate (event 5)
                 } else {
                     o = o + d * dist;  // Ray.move
                     len = len - dist;
@@ -333,7 +335,8 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                 phase = PH_N0;
             } else if (event == 5) {
                 // Material.Color at the un-moved hit origin `o` (SdfObject.fs:75-77)
-                leaf_obj = material_leaf<COUNT>(S, o, acc);
+                leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, o, (uint32_t)leaf_obj)
+                                                        : material_leaf<COUNT>(S, o, acc);
                 lc = V3{S.bg[0], S.bg[1], S.bg[2]};  // SdfScene.fs:12
                 shadow_mask = 0;
                 light = 0;
