@@ -177,6 +177,12 @@ void sum_stats(const unsigned long long *h, ft_render_stats *st) {
     st->eval_flops = (int64_t)flops;
 }
 
+int check_frame(int64_t width, int64_t height) {
+    if (width <= 0 || height <= 0 || width * height >= ((int64_t)1 << 29))
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size (a frame holds at most 2^29 pixels)");
+    return FT_OK;
+}
+
 int check_ray_params(float epsilon, float length) {
     if (!(epsilon > 0.0f))
         return fail(FT_ERR_INVALID_ARGUMENT,
@@ -473,7 +479,9 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
     if (!scene || !camera || !d_out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
     if (width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || rank < 0 || rank >= world)
         return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size or strip partition");
-    int st = check_ray_params(epsilon, length);
+    int st = check_frame(width, height);
+    if (st != FT_OK) return st;
+    st = check_ray_params(epsilon, length);
     if (st != FT_OK) return st;
     if (scene->device == FT_DEVICE_NONE)
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
@@ -526,6 +534,7 @@ FT_API int ft_render_gather_device(ft_scene *scene, const ft_camera *camera, int
     if (!scene || !camera || !d_dst) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
     if (width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || rank < 0 || rank >= world || n_dst < 1 || n_dst > 16)
         return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size, strip partition or destination count");
+    if (check_frame(width, height) != FT_OK) return FT_ERR_INVALID_ARGUMENT;
     for (int k = 0; k < n_dst; k++)
         if (!d_dst[k]) return fail(FT_ERR_INVALID_ARGUMENT, "null destination framebuffer");
     int st = check_ray_params(epsilon, length);
@@ -606,8 +615,9 @@ FT_API int ft_ipc_close(int device, void *d_ptr) {
 FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon, float length,
                      uint32_t flags, float *out_rgb, int32_t *out_leaf, ft_render_stats *stats) {
     if (!scene || !camera || !out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
-    if (width <= 0 || height <= 0) return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size");
-    int st = check_ray_params(epsilon, length);
+    int st = check_frame(width, height);
+    if (st != FT_OK) return st;
+    st = check_ray_params(epsilon, length);
     if (st != FT_OK) return st;
     if (scene->device == FT_DEVICE_NONE)
         return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
