@@ -214,7 +214,11 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     int steps = 0, primary_steps = 0, light = 0, leaf_obj = 0;
     unsigned shadow_mask = 0;
     // per-lane totals for the stats flush
-    unsigned n_hits = 0, n_shadow = 0, n_capped = 0, n_escaped = 0;
+    // event counters live in shared memory (one row per warp, RED.shared on the rare transition paths)
+    __shared__ unsigned sh_stats[MB / 32][4];
+    unsigned *const wstats = sh_stats[threadIdx.x >> 5];
+    if (lane < 4) wstats[lane] = 0u;
+    __syncwarp();
     Acc acc{0ull, 0ull};
 
     for (;;) {
@@ -239,10 +243,10 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         int event = 0;  // 1 primary miss, 2 primary hit, 3 shadow finished (miss), 4 shadow finished (hit), 5 normal done
         if (phase == PH_PRIMARY || phase == PH_SHADOW) {
             if (len <= 0.0f || steps >= S.step_cap) {
-                if (!(len <= 0.0f)) n_capped++;
+                if (!(len <= 0.0f)) atomicAdd(wstats + 2, 1u);
                 event = phase == PH_PRIMARY ? 1 : 3;
             } else if (ESCAPE && S.esc_valid && outside_box(S.esc_lo, S.esc_hi, o) && ray_escapes(S, o, d, FT_EPS)) {
-                n_escaped++;
+                atomicAdd(wstats + 3, 1u);
                 event = phase == PH_PRIMARY ? 1 : 3;
             }
         }
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                 finish = true;
             } else if (event == 2) {  // primary hit: SdfObject.fs:70-73
                 primary_steps = steps;
-                n_hits++;
+                atomicAdd(wstats + 0, 1u);
                 q = o + d * (-FT_EPS);  // Ray.get (-epsilon): the normal's probe point and result.Ray's origin
                 phase = PH_N0;
             } else if (event == 5) {
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                             add_flops<COUNT>(acc, FLOPS_POINT_LIGHT);
                         }
                         steps = 0;
-                        n_shadow++;
+                        atomicAdd(wstats + 1, 1u);
                         phase = PH_SHADOW;
                         finish = false;
                         break;
@@ -391,10 +395,8 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     }
 
     // ---------------------------------------------------------------------- stats
-    const unsigned hits = __reduce_add_sync(FULL, n_hits);
-    const unsigned shadows = __reduce_add_sync(FULL, n_shadow);
-    const unsigned capped = __reduce_add_sync(FULL, n_capped);
-    const unsigned escaped = __reduce_add_sync(FULL, n_escaped);
+    __syncwarp();
+    const unsigned hits = wstats[0], shadows = wstats[1], capped = wstats[2], escaped = wstats[3];
     unsigned long long st = acc.steps, fl = acc.flops, lf = acc.long_flops, le = acc.long_evals, ev = acc.evals;
     if (COUNT) {
         for (int k = 16; k > 0; k >>= 1) {
