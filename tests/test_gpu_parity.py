@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import fraytracer_b200 as ft
+from fraytracer_b200 import _abi as A
 from fraytracer_b200 import scenes
 from oracle import oracle as O
 
@@ -355,3 +356,44 @@ def test_two_rank_p2p_gather_when_two_gpus_are_present():
                         "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "check_p2p.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_instrumented_kernel_counters_against_oracle_counters():
+    """the roofline numerator comes from the instrumented (COUNT) kernel variant.  With per-ray step counts
+    requested the escape proof is off, so its march-step total must equal the oracle's exactly, and its algorithmic flop
+    total must lie between the oracle-derived lower bound (primitive evaluations + cell lookups + moves: the early exit
+    and the inlined spheres only remove pruning tests) and the oracle-derived total of a scan without early exit."""
+    for w in (scenes.default_scene(n_tori=300), scenes.spheres_capsules_scene(n_spheres=150, n_capsules=150)):
+        tracer = ft.SceneTracer(w.scene, device=0)
+        orc = O.OracleScene(tracer.description)
+        X, Y = 160, 120
+        cam = w.camera.to_c()
+        # the frame's primary rays as explicit Ray records (Camera.uniformPixelToRay is part of the oracle's render)
+        ref = orc.render(w.camera, X, Y, w.epsilon, w.length, counters=True)
+        rgb, leaf, st = tracer.render(w.camera, ft.ImageSize(X, Y), w.epsilon, w.length, want_leaf=True,
+                                      flags=A.FT_FLAG_COUNTERS)
+        c = ref["counters"]
+        assert st["primary_hits"] == c["primary_hits"] and st["shadow_rays"] == c["shadow_rays"]
+        assert 0 < st["march_steps"] <= c["march_steps"]  # the escape proof and the shared first step only remove steps
+        prims = 21 * c["eval_capsule"] + 27 * c["eval_torus"] + 85 * c["eval_triangle_edge"] + 34 * c["eval_triangle_face"]
+        assert st["eval_flops"] > 0
+        assert st["eval_flops"] <= prims + 10 * c["eval_sphere"] + 19 * c["union_lookups"] + 2 * c["lower_bound_tests"] + \
+            13 * c["bound_tests"] + 7 * c["march_steps"] + 200 * c["primary_rays"]
+        # per-ray step counts (no escape proof): exact
+        rays = np.zeros((X * Y, 8), np.float32)
+        rays[:, 0:3] = np.array(cam.position)
+        xs, ys = np.meshgrid(np.arange(X), np.arange(Y), indexing="ij")
+        m = np.float32(max(X, Y))
+        u = (xs.astype(np.float32) / m - np.float32(0.5))[..., None]
+        v = (ys.astype(np.float32) / m - np.float32(0.5))[..., None]
+        d = (np.array(cam.forward, np.float32) + np.array(cam.right_scaled, np.float32) * u) + np.array(cam.up_scaled, np.float32) * v
+        rays[:, 3:6] = (d / np.sqrt(((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]))[..., None]).reshape(-1, 3)
+        rays[:, 6], rays[:, 7] = w.length, w.epsilon
+        got, st2 = tracer.trace_rays(rays, flags=A.FT_FLAG_COUNTERS)
+        oref = orc.trace_rays(rays, counters=True)
+        assert np.array_equal(got["steps"], oref["steps"]) and np.array_equal(bits(got["rgb"]), bits(oref["rgb"]))
+        assert st2["march_steps"] == oref["counters"]["march_steps"]
+        c2 = oref["counters"]
+        prims2 = 21 * c2["eval_capsule"] + 27 * c2["eval_torus"] + 85 * c2["eval_triangle_edge"] + 34 * c2["eval_triangle_face"]
+        assert st2["eval_flops"] >= prims2 + 7 * (c2["march_steps"] - c2["primary_hits"] - c2["shadow_rays"])
+        tracer.close()
