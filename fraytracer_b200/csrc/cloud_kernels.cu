@@ -28,6 +28,9 @@
 namespace ft_cloud {
 
 constexpr int CB = 128;
+#ifndef FT_CLOUD_MINB
+#define FT_CLOUD_MINB 4  // <= 128 registers.  Measured (config 4, 16 spp): 2 or 3 CTAs/SM 94 ms, 4: 81.4, 6: 84.9, 8: 87.5
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 enum : int {
@@ -91,7 +94,7 @@ __device__ __forceinline__ void cloud_rnd(const CloudParams &P, uint32_t pixel, 
 }
 
 template <bool CHAIN>
-__global__ void __launch_bounds__(CB, 4) cloud_kernel(const __grid_constant__ DevScene S, const __grid_constant__ CloudParams P) {
+__global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_constant__ DevScene S, const __grid_constant__ CloudParams P) {
     __shared__ NoiseTab tab;
     for (int i = threadIdx.x; i < 256; i += CB) tab.perm[i] = P.perm[i];
     for (int i = threadIdx.x; i < 768; i += CB) tab.grad[i] = P.gradients[i];

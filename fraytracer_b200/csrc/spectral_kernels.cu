@@ -31,6 +31,9 @@
 namespace ft_spectral {
 
 constexpr int SB = 128;  // threads per CTA
+#ifndef FT_SPEC_MINB
+#define FT_SPEC_MINB 8  // <= 64 registers.  Measured (config 3, 4K): 4 CTAs/SM 139.8 ms, 6: 114.9, 8: 108.1, 10: 115.6
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 enum : int {
@@ -133,7 +136,7 @@ __device__ __forceinline__ void store_path(float4 *q, unsigned idx, const Contin
 // One distance-evaluation call site; every lane runs a small state machine (march -> 4 normal probes -> light
 // loop with shadow marches), whole 32-item chunks in lockstep like the hot path's ray machine.
 template <bool CHAIN, bool PRIMARY>
-__global__ void __launch_bounds__(SB, 4) spectral_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ SpectralParams P) {
+__global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ SpectralParams P) {
     const int lane = threadIdx.x & 31;
     const float eps = P.epsilon;
     const long long total = PRIMARY ? P.n_items : (long long)__ldg(P.in_count);
