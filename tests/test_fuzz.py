@@ -76,3 +76,47 @@ def test_fuzz_gpu_smooth_unions_within_tolerance(seed):
         return
     pts = (np.random.default_rng(seed).normal(size=(20000, 3)) * 2.5).astype(np.float32)
     assert np.allclose(tracer.distance(pts), orc.distance(pts), rtol=5e-5, atol=5e-6)
+
+
+def _swap_materials(obj, rng, make):
+    """the same object tree with about a third of its leaves' materials replaced by make()"""
+    from fraytracer_b200 import SdfObject
+
+    if obj.kind == A.FT_OBJECT_LEAF:
+        return SdfObject.create(make() if rng.random() < 0.35 else obj.material, obj.form)
+    if obj.kind == A.FT_OBJECT_UNION:
+        return SdfObject.union([_swap_materials(c, rng, make) for c in obj.children])
+    if obj.kind == A.FT_OBJECT_SUBTRACT:
+        return SdfObject.subtract(_swap_materials(obj.base, rng, make), obj.form)
+    return SdfObject.intersect(_swap_materials(obj.base, rng, make), list(obj.forms))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_gpu_extension_paths_bit_exact(seed):
+    """EXTENSIONS (no reference implementation): random composite scenes with a third of the materials turned into glass /
+    cloud -- the CUDA pipelines equal this repository's CPU restatements bit for bit, counters included"""
+    from fraytracer_b200 import CloudParams, SdfMaterial, SdfScene
+
+    cam = scenes.default_camera()
+    base = random_scene(3000 + seed)
+    rng = np.random.default_rng(seed)
+    X, Y = 72, 54
+    for kind in ("glass", "cloud"):
+        make = (lambda: SdfMaterial.createGlass(1.45 + 0.1 * rng.random(), 0.02 + 0.03 * rng.random())) if kind == "glass" \
+            else (lambda: SdfMaterial.createCloud(rng.uniform(0.5, 1.0, size=3)))
+        scene = SdfScene(Object=_swap_materials(base.Object, rng, make), BackgroundColor=base.BackgroundColor, Lights=base.Lights)
+        tracer, orc = build_both(scene, 0)
+        if tracer is None:
+            return
+        if kind == "glass":
+            img, st = tracer.render_spectral(cam, ft.ImageSize(X, Y), 0.01, 30.0, 8, 6, seed)
+            ref = orc.render_spectral(cam, X, Y, 0.01, 30.0, 8, 6, seed)
+        else:
+            cp = CloudParams(density=8.0, step=0.04)
+            img, st = tracer.render_cloud(cam, ft.ImageSize(X, Y), 0.01, 30.0, cp, 6, seed)
+            ref, ctr = orc.render_cloud(cam, X, Y, 0.01, 30.0, cp, 6, seed)
+            assert (st["shadow_rays"], st["march_steps"], st["reserved"]) == (ctr["secondary"], ctr["track_steps"], ctr["scattered"])
+        assert st["capped_rays"] == 0
+        assert np.array_equal(bits(img), bits(ref)), f"{kind}: {(bits(img) != bits(ref)).any(axis=2).sum()} pixels differ"
+        tracer.close()
