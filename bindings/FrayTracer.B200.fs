@@ -145,13 +145,94 @@ module SdfLight =
     let point position color = Point (position, color)
 
 /// A scene compiled onto one B200.  `SdfScene.trace scene` of the reference becomes `new CompiledScene(scene, 0)`.
+/// The node graph is flattened into the tables of ft_scene_desc (children before parents, one shared `children`
+/// index array) -- the same walk as fraytracer_b200/api.py : SceneDescription.__init__, the tested binding.
 type CompiledScene(scene:SceneNode, device:int) =
     let mutable handle = 0n
     do
-        // Flatten the node graph into the blittable tables of ft_scene_desc (children before parents, one
-        // shared `children` index array), pin them, call ft_scene_create, unpin.  Omitted here for brevity:
-        // it is the same walk as fraytracer_b200/api.py : SceneDescription.__init__.
-        ()
+        let forms = ResizeArray<int * int * int * float32[]>()        // kind, firstChild, childCount, p[10]
+        let objects = ResizeArray<int * int * int * int * int>()      // kind, form, material, firstChild, childCount
+        let children = ResizeArray<int>()
+        let materials = ResizeArray<FColor>()
+        let v (a:Vector3) = [ a.X; a.Y; a.Z ]
+        let pad (xs:float32 list) = Array.append (Array.ofList xs) (Array.zeroCreate (10 - xs.Length))
+        let rec addForm (f:FormNode) : int =
+            let prim kind p = forms.Add((kind, 0, 0, pad p)); forms.Count - 1
+            let composite kind (kids:FormNode[]) p =
+                let ids = kids |> Array.map addForm
+                let first = children.Count
+                children.AddRange ids
+                forms.Add((kind, first, ids.Length, pad p))
+                forms.Count - 1
+            match f with
+            | Sphere s -> prim 1 (v s.Center @ [ s.Radius ])                                         // FT_FORM_SPHERE
+            | Capsule c -> prim 2 (v c.From @ v c.To @ [ c.Radius ])                                 // FT_FORM_CAPSULE
+            | Torus t -> prim 3 (v t.Center @ v t.Normal @ [ t.MajorRadius; t.MinorRadius ])         // FT_FORM_TORUS
+            | Triangle t -> prim 4 (v t.V1 @ v t.V2 @ v t.V3 @ [ t.Radius ])                         // FT_FORM_TRIANGLE
+            | Union fs -> composite 16 fs []
+            | Subtract (a, b) -> composite 17 [| a; b |] []
+            | Intersect fs -> composite 18 fs []
+            | UnionSmooth (k, fs) -> composite 19 fs [ k ]
+        let rec addObject (o:ObjectNode) : int =
+            match o with
+            | Leaf (Solid color, form) ->
+                let fid = addForm form
+                materials.Add color
+                objects.Add((1, fid, materials.Count - 1, 0, 0))                                     // FT_OBJECT_LEAF
+            | ObjUnion os ->
+                let ids = os |> Array.map addObject
+                let first = children.Count
+                children.AddRange ids
+                objects.Add((2, -1, -1, first, ids.Length))                                          // FT_OBJECT_UNION
+            | ObjSubtract (b, form) ->
+                let bid = addObject b
+                let fid = addForm form
+                let first = children.Count
+                children.Add bid
+                objects.Add((3, fid, -1, first, 1))                                                  // FT_OBJECT_SUBTRACT
+            | ObjIntersect (b, fs) ->
+                let bid = addObject b
+                let fids = fs |> Array.map addForm
+                let first = children.Count
+                children.Add bid
+                children.AddRange fids
+                objects.Add((4, -1, -1, first, 1 + fids.Length))                                     // FT_OBJECT_INTERSECT
+            objects.Count - 1
+        let root = addObject scene.Object
+        // unmanaged copies of the tables (ft_form_desc is 52 bytes, ft_object_desc 20, ft_material_desc 16, ft_light_desc 28)
+        let alloc n = Marshal.AllocHGlobal(max 1 n)
+        let pForms, pObjects = alloc (52 * forms.Count), alloc (20 * objects.Count)
+        let pChildren, pMaterials = alloc (4 * children.Count), alloc (16 * materials.Count)
+        let lights = List.toArray scene.Lights
+        let pLights = alloc (28 * lights.Length)
+        let f32 (p:nativeint) (off:int) (x:float32) = Marshal.WriteInt32(p, off, BitConverter.SingleToInt32Bits x)
+        try
+            forms |> Seq.iteri (fun i (kind, first, count, p) ->
+                Marshal.WriteInt32(pForms, 52 * i, kind)
+                Marshal.WriteInt32(pForms, 52 * i + 4, first)
+                Marshal.WriteInt32(pForms, 52 * i + 8, count)
+                Marshal.Copy(p, 0, pForms + nativeint (52 * i + 12), 10))
+            objects |> Seq.iteri (fun i (kind, form, material, first, count) ->
+                [ kind; form; material; first; count ] |> List.iteri (fun k x -> Marshal.WriteInt32(pObjects, 20 * i + 4 * k, x)))
+            children |> Seq.iteri (fun i c -> Marshal.WriteInt32(pChildren, 4 * i, c))
+            materials |> Seq.iteri (fun i m ->
+                Marshal.WriteInt32(pMaterials, 16 * i, 1)                                            // FT_MATERIAL_SOLID
+                f32 pMaterials (16 * i + 4) m.R; f32 pMaterials (16 * i + 8) m.G; f32 pMaterials (16 * i + 12) m.B)
+            lights |> Array.iteri (fun i l ->
+                let kind, (vec:Vector3), (c:FColor) =
+                    match l with
+                    | Directional (d, c) -> 1, d, c                                                  // FT_LIGHT_DIRECTIONAL
+                    | Point (p, c) -> 2, p, c                                                        // FT_LIGHT_POINT
+                Marshal.WriteInt32(pLights, 28 * i, kind)
+                [ vec.X; vec.Y; vec.Z; c.R; c.G; c.B ] |> List.iteri (fun k x -> f32 pLights (28 * i + 4 + 4 * k) x))
+            let mutable desc : Native.SceneDesc =
+                { forms = pForms; objects = pObjects; children = pChildren; materials = pMaterials; lights = pLights
+                  nForms = forms.Count; nObjects = objects.Count; nChildren = children.Count
+                  nMaterials = materials.Count; nLights = lights.Length; rootObject = root
+                  bgR = scene.BackgroundColor.R; bgG = scene.BackgroundColor.G; bgB = scene.BackgroundColor.B }
+            Native.ft_scene_create(&desc, device, &handle) |> Native.check      // the tables are copied: free them below
+        finally
+            for p in [ pForms; pObjects; pChildren; pMaterials; pLights ] do Marshal.FreeHGlobal p
     member _.Handle = handle
     interface IDisposable with
         member _.Dispose() = if handle <> 0n then Native.ft_scene_destroy handle |> ignore
