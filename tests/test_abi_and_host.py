@@ -176,3 +176,56 @@ def test_strip_layout_matches_python_mirror():
         assert (spr.value, fl.value) == D.strip_layout(w_, h_, sw, world)
         cols = sorted(x for r in range(world) for _, x0, n in D.owned_columns(w_, sw, r, world) for x in range(x0, x0 + n))
         assert cols == list(range(w_))  # every column owned exactly once
+
+
+def test_every_compute_entry_point_refuses_a_compile_only_handle_and_bad_arguments():
+    """no CPU fallback anywhere: the extension and multi-GPU entry points too answer FT_ERR_NO_DEVICE without a device,
+    and validate their arguments before touching one"""
+    w = scenes.default_scene(n_tori=30, size=16)
+    tr = _compile_only(w.scene)
+    cp = ft.CloudParams()
+    calls = {
+        "spectral": lambda: tr.render_spectral(w.camera, w.size, w.epsilon, w.length),
+        "cloud": lambda: tr.render_cloud(w.camera, w.size, w.epsilon, w.length, cp, 4),
+        "gather": lambda: tr.render_gather_device(w.camera, w.size, w.epsilon, w.length, [0x1000]),
+        "device": lambda: tr.render_device(w.camera, w.size, w.epsilon, w.length, 0x1000),
+    }
+    for name, call in calls.items():
+        with pytest.raises(ft.FrayTracerError) as e:
+            call()
+        assert e.value.code == A.FT_ERR_NO_DEVICE, name
+    bad = {
+        "epsilon <= 0": lambda: tr.render_spectral(w.camera, w.size, 0.0, w.length),
+        "wavelengths": lambda: tr.render_spectral(w.camera, w.size, w.epsilon, w.length, n_wavelengths=65),
+        "bounces": lambda: tr.render_spectral(w.camera, w.size, w.epsilon, w.length, max_bounces=-1),
+        "spp": lambda: tr.render_cloud(w.camera, w.size, w.epsilon, w.length, cp, 0),
+        "cloud step": lambda: tr.render_cloud(w.camera, w.size, w.epsilon, w.length, ft.CloudParams(step=0.0), 4),
+        "perm range": lambda: tr.render_cloud(w.camera, w.size, w.epsilon, w.length,
+                                              ft.CloudParams(perm=np.full(256, 300, np.int32)), 4),
+        "no destination": lambda: tr.render_gather_device(w.camera, w.size, w.epsilon, w.length, []),
+        "frame too large": lambda: tr.render(w.camera, ft.ImageSize(1 << 15, 1 << 15), w.epsilon, w.length,
+                                             out=np.empty(3, np.float32)) if False else
+        A.check(tr.lib.ft_render(tr.handle, C.byref(w.camera.to_c()), 1 << 15, 1 << 15, C.c_float(0.01), C.c_float(30.0), 0,
+                                 C.c_void_p(0x1000), None, None)),
+    }
+    for name, call in bad.items():
+        with pytest.raises(ft.FrayTracerError) as e:
+            call()
+        assert e.value.code == A.FT_ERR_INVALID_ARGUMENT, name
+    tr.close()
+
+
+def test_cloud_noise_tables_are_the_reference_generator():
+    """CloudParams.default_tables regenerates Noise.gradientTable exactly as Noise.fs:31-33,72-76 draws it"""
+    from fraytracer_b200.dotnet_random import DotNetRandom
+    import math
+
+    perm, grad = ft.CloudParams.default_tables()
+    r = DotNetRandom(666)
+    for _ in range(256):
+        r.NextDouble()
+    z = r.NextDouble() * 2.0 - 1.0
+    rr = math.sqrt(1.0 - z * z)
+    th = 2.0 * math.pi * r.NextDouble()
+    assert grad[0].tolist() == [rr * math.cos(th), rr * math.sin(th), z]
+    assert sorted(perm.tolist()) == list(range(256))
