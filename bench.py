@@ -46,9 +46,11 @@ METRIC = "Mrays/s (primary+secondary)"
 UNIT = "Mrays/s"
 
 
-def workload(name: str, world: int):
+def workload(name: str, world: int, strong: bool = False):
     from fraytracer_b200 import scenes
 
+    if strong:  # --scaling strong: one fixed frame cut over all ranks (BASELINE config 5 is worded this way: ONE 8K frame)
+        world = {"config1": 1, "config2": 1, "config5": 4}[name]  # 1000x1000, 1920x1080, 7680x4320
     s = math.sqrt(world)
     if name == "config1":
         n = int(round(1000 * s / 8)) * 8 if world > 1 else 1000
@@ -276,7 +278,7 @@ def bench_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     flags = A.FT_FLAG_FAST_MATH if args.fast else 0
 
-    w = workload(args.workload, world)
+    w = workload(args.workload, world, args.scaling == "strong")
     tracer = ft.SceneTracer(w.scene, device=local_rank)  # scene compile: outside the timed region (Program.fs:67-93)
     renderer = DistributedRenderer(tracer, w.size, strip_width=8, gather=args.gather)
     X, Y = w.size.X, w.size.Y
@@ -442,7 +444,7 @@ def bench_b200(args):
         info = tracer.info()
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "image": f"{X}x{Y}", "rays_per_step": int(total_rays),
                        "primitives": info["n_primitives"], "grid_entries": info["n_entries"],
@@ -473,6 +475,8 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config5", "config3", "config4"])
     ap.add_argument("--fast", action="store_true", help="FT_FLAG_FAST_MATH (FMA contraction, not bit-exact)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): 1080p worth of pixels per GPU; strong: one fixed frame (config5: 7680x4320) over all GPUs")
     ap.add_argument("--gather", default=None, choices=["p2p", "nccl"],
                     help="N > 1: how the framebuffer is gathered (default p2p: peer stores fused into the render kernel)")
     args = ap.parse_args()
