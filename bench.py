@@ -280,7 +280,8 @@ def bench_b200(args):
 
     w = workload(args.workload, world, args.scaling == "strong")
     tracer = ft.SceneTracer(w.scene, device=local_rank)  # scene compile: outside the timed region (Program.fs:67-93)
-    renderer = DistributedRenderer(tracer, w.size, strip_width=8, gather=args.gather)
+    renderer = DistributedRenderer(tracer, w.size, gather=args.gather)  # strip width: distributed.auto_strip_width
+    sw = renderer.strip_width
     X, Y = w.size.X, w.size.Y
     lib = tracer.lib
 
@@ -292,11 +293,11 @@ def bench_b200(args):
         return float(t.item())
 
     # ---- work of one step (deterministic): rays and algorithmic flops of this rank's strips
-    spr_floats = ft.distributed.strip_layout(X, Y, 8, world)[1]
+    spr_floats = ft.distributed.strip_layout(X, Y, sw, world)[1]
     buf = torch.empty(spr_floats, dtype=torch.float32, device=dev) if world > 1 else renderer.final
     st = tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(),
                               stream=torch.cuda.current_stream().cuda_stream, flags=flags | A.FT_FLAG_COUNTERS,
-                              strip_width=8, rank=rank, world=world, want_stats=True)
+                              strip_width=sw, rank=rank, world=world, want_stats=True)
     my_rays = st["primary_rays"] + st["shadow_rays"]
     my_flops = st["eval_flops"]
     total_rays = allreduce(float(my_rays), dist.ReduceOp.SUM if world > 1 else None)
@@ -324,7 +325,7 @@ def bench_b200(args):
         k0, k1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
         k0.record()
         tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(),
-                             stream=torch.cuda.current_stream().cuda_stream, flags=flags, strip_width=8, rank=rank,
+                             stream=torch.cuda.current_stream().cuda_stream, flags=flags, strip_width=sw, rank=rank,
                              world=world)
         k1.record()
         if it >= 3:
@@ -448,7 +449,7 @@ def bench_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w.name, "image": f"{X}x{Y}", "rays_per_step": int(total_rays),
                        "primitives": info["n_primitives"], "grid_entries": info["n_entries"],
-                       "parallelism": f"image strips x{world}" + (
+                       "parallelism": f"image strips ({sw} columns wide, round-robin) x{world}" + (
                            "" if world == 1 else " + P2P stores from the render kernel (CUDA IPC over NVLink), 4-byte NCCL all-reduce"
                            if renderer.gather == "p2p" else " + NCCL all-gather + de-interleave"),
                        "l2": "flushed between timed iterations (512 MiB write)", "capped_rays": int(capped),

@@ -21,13 +21,13 @@ for w, (X, Y) in ((scenes.default_scene(n_tori=300), (333, 251)), (scenes.sphere
     size = ft.ImageSize(X, Y)
     tr = ft.SceneTracer(w.scene, device=local)
     ref, _, _ = tr.render(w.camera, size, w.epsilon, w.length)
-    for mode in ("p2p", "nccl"):
-        r = DistributedRenderer(tr, size, strip_width=8, gather=mode)
+    for mode, sw in (("p2p", None), ("p2p", 8), ("nccl", None)):
+        r = DistributedRenderer(tr, size, strip_width=sw, gather=mode)
         for frame in range(3):
             img = r.render(w.camera, w.epsilon, w.length).cpu().numpy()
             same = np.array_equal(img.view(np.uint32), ref.view(np.uint32))
             ok &= same
-            print(f"rank {rank}/{world} {w.name} {X}x{Y} {mode} frame {frame}: identical={same}", flush=True)
+            print(f"rank {rank}/{world} {w.name} {X}x{Y} {mode} strip {r.strip_width} frame {frame}: identical={same}", flush=True)
         if mode == "p2p":  # shared host framebuffer: every rank's kernel stores its strips over its own PCIe link
             for frame in range(2):
                 host = r.render_to_host(w.camera, w.epsilon, w.length)
