@@ -22,8 +22,10 @@ constexpr int MB = 128;             // threads per CTA
 #define FT_TILE_W 4  // pixel tile of one warp: FT_TILE_W (x) by FT_TILE_H (y), 32 pixels
 #define FT_TILE_H 8
 #endif
-#ifndef FT_REFILL_MIN
-#define FT_REFILL_MIN 32  // measured: whole tiles in lockstep beat per-lane refill by 1.5-2.9x (coherent cells and trip counts)
+#ifndef FT_LONG_VOTE
+#define FT_LONG_VOTE 0  // 1: the warp runs evaluations outside / inside the largest grid's box in separate iterations.  It paid
+                       // before the escape proof and whole-tile lockstep (outside lookups were 27 % of all); now they are 2.6 %
+                       // and the two ballots per iteration cost more than they save: off is 2.5-4 % faster (measured)
 #endif
 #ifndef FT_LONG_BATCH
 #define FT_LONG_BATCH 1  // run the long class as soon as any lane has one (measured best with whole-tile lockstep)
@@ -267,9 +269,13 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         const bool wants = phase > PH_FETCH && event == 0;
         const bool is_long = p.x < S.pg_lo[0] || p.y < S.pg_lo[1] || p.z < S.pg_lo[2] || p.x >= S.pg_hi[0] ||
                              p.y >= S.pg_hi[1] || p.z >= S.pg_hi[2];
+#if FT_LONG_VOTE
         const unsigned m_long = __ballot_sync(FULL, wants && is_long), m_short = __ballot_sync(FULL, wants && !is_long);
         const bool run_long = m_short == 0u || __popc(m_long) >= FT_LONG_BATCH;
         if (wants && is_long == run_long) {
+#else
+        if (wants) {
+#endif
             const unsigned long long f0 = acc.flops;
             uint32_t best_lo = 0u;
             const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
