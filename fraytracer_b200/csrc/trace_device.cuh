@@ -153,12 +153,17 @@ __device__ __forceinline__ float prim_distance(const DevScene &S, uint32_t word,
 }
 
 // ---- spatial lookup (SdfBoundary.fs:276-282): returns the cell's first entry index and dist(p, centre)
+// MathI.clamp 0 m (MathF.floor_i x) (SdfBoundary.fs:276-282, Math.fs:23,57) in five instructions: floor(x) lies in [0, 2^31)
+// exactly when x does, the float -> int conversion is then exact, and everything else -- negative, too large (cvttss2si
+// gives INT_MIN), NaN (INT_MIN as well) -- clamps to 0.  Same values as clamp_int(0, m, floor_to_int(x)) for every float.
+__device__ __forceinline__ int cell_index(float x, int m) {
+    const int i = __float2int_rd(x);
+    return (x >= 0.0f && x < 2147483648.0f) ? (i < m ? i : m) : 0;
+}
 __device__ __forceinline__ void grid_cell_from(const DevScene &S, float4 g1, float4 g2, float4 g3, V3 p, uint32_t &begin, float &dtc) {
     const V3 c = (p - xyz(g1)) * xyz(g2);
     const int mx = __float_as_int(g3.x), my = __float_as_int(g3.y), mz = __float_as_int(g3.z);
-    const int ix = clamp_int(0, mx, floor_to_int(c.x));
-    const int iy = clamp_int(0, my, floor_to_int(c.y));
-    const int iz = clamp_int(0, mz, floor_to_int(c.z));
+    const int ix = cell_index(c.x, mx), iy = cell_index(c.y, my), iz = cell_index(c.z, mz);
     const uint32_t ci = __float_as_uint(g1.w) + (uint32_t)(ix * __float_as_int(g3.w) + iy * (mz + 1) + iz);
     const float4 cell = ld4(S.cells + ci);
     dtc = distance(p, xyz(cell));  // SdfForm.fs:25
