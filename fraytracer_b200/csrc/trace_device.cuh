@@ -38,7 +38,7 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #define FT_SCAN_PTR 1  // the candidate scan walks a pointer (immediate offsets, one 64-bit add per two records) instead of re-deriving the address from an index
 #endif
 #ifndef FT_SCAN_UNROLL
-#define FT_SCAN_UNROLL 2  // candidates per round of the scan loop (2 or 4).  Measured on B200: 4 is 2 % faster on config 2 and 5, 2.5 % slower on config 1
+#define FT_SCAN_UNROLL 4  // candidates per round of the scan loop (2 or 4).  Measured on B200 with the lean lane state (no spills either way): 4 is 1-2 % faster on configs 1, 2 and 5
 #endif
 #ifndef FT_CHAIN_MAT
 #define FT_CHAIN_MAT 0  // 1: the chain evaluator notes its arg-min candidate, so the material lookup of a hit needs no second scan.
