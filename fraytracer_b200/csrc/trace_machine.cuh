@@ -5,10 +5,12 @@
 //     FETCH -> primary march -> (hit) 4 normal probes -> material arg-min -> per light: shadow march -> store
 //
 // so that lanes of one warp that are in different phases of SdfScene.trace (one still marching its primary
-// ray, one probing its normal, one following a shadow ray) still execute the same instructions.  Lanes that
-// finish pull the next work item from a warp-private chunk (ballot + popc prefix ranks, no atomics); the
-// warp leader refills the chunk from one global counter (one atomic per FT_CHUNK items).  The grid is
-// persistent: resident-CTAs-per-SM x SM count, sized by the occupancy API.
+// ray, one probing its normal, one following a shadow ray) still execute the same instructions.  A warp works on
+// one chunk of FT_CHUNK items -- a 4 x 8 pixel tile -- at a time, all lanes in lockstep, and takes the next chunk from
+// one global counter (one atomic per chunk) when every lane is idle: what an SM pays for is warp instructions and an
+// iteration costs the maximum over its active lanes, so adjacent pixels (same cells, same candidate lists, similar
+// trip counts) are worth more than busy lanes (per-lane refill was built first and measured 1.5-2.9x slower).
+// The grid is persistent: resident-CTAs-per-SM x SM count, sized by the occupancy API.
 #pragma once
 #include "trace_device.cuh"
 
