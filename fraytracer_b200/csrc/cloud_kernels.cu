@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #define FT_WITH_CONE 1
+#define FT_SCAN_UNROLL 2  // these kernels are larger and instruction-cache sensitive: four records per round measured slower here
 #define FT_NS ft_cloud
 #include "cloud.h"
 #include "kernels.h"
