@@ -565,6 +565,31 @@ class SceneTracer:
                                                  C.byref(stats) if want_stats else None))
         return stats.as_dict() if want_stats else None
 
+    def render_extension_gather_device(self, kind: str, camera: Camera, size: ImageSize, epsilon: float, length: float, dst_ptrs,
+                                       stream: int = 0, strip_width: int = 8, rank: int = 0, world: int = 1, seed: int = 19,
+                                       n_wavelengths: int = 16, max_bounces: int = 8, cloud: "CloudParams | None" = None,
+                                       samples_per_pixel: int = 64):
+        """EXTENSIONS over several GPUs: the strips `rank` owns of a spectral (kind="spectral") or cloud (kind="cloud")
+        frame, every pixel stored at its final position in each framebuffer of `dst_ptrs`.  Returns the stats dict."""
+        cam = camera.to_c()
+        stats = A.ft_render_stats()
+        arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        st = C.c_void_p(stream) if stream else None
+        if kind == "spectral":
+            A.check(self.lib.ft_render_spectral_gather_device(self.handle, C.byref(cam), int(size.X), int(size.Y), C.c_float(epsilon),
+                                                              C.c_float(length), int(n_wavelengths), int(max_bounces), C.c_uint64(seed),
+                                                              int(strip_width), int(rank), int(world), arr, len(dst_ptrs), st,
+                                                              C.byref(stats)))
+        elif kind == "cloud":
+            cp = (cloud or CloudParams()).to_c()
+            A.check(self.lib.ft_render_cloud_gather_device(self.handle, C.byref(cam), int(size.X), int(size.Y), C.c_float(epsilon),
+                                                           C.c_float(length), C.byref(cp), int(samples_per_pixel), C.c_uint64(seed),
+                                                           int(strip_width), int(rank), int(world), arr, len(dst_ptrs), st,
+                                                           C.byref(stats)))
+        else:
+            raise ValueError("kind must be 'spectral' or 'cloud'")
+        return stats.as_dict()
+
     def trace_rays(self, rays: np.ndarray, flags: int = 0):
         """Batched SdfScene.trace: rays float32 [n,8] = origin, direction, length, epsilon."""
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)

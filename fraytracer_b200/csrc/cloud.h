@@ -11,11 +11,11 @@ struct CloudParams {
     float epsilon, length, max_size;
     int spp;
     uint32_t seed_lo, seed_hi;
-    long long n_tiles;  // 4 x 8 pixel tiles
+    long long n_tiles;  // 4 x 8 pixel tiles of the rank's compact strip space
     float density, frequency, step, fade, bias, gain;  // ft_cloud_params
     const int *perm;          // device, 256
     const double *gradients;  // device, 768
-    float *out_rgb;           // device FColor[X,Y]
+    StripTarget T;            // the rank's strips and the destination framebuffers
     unsigned long long *work_counter;
     unsigned long long *stats;
 };

@@ -127,18 +127,17 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
         if (__all_sync(FULL, phase == C_FETCH && s >= spp_eff)) {
             if (have_tile && active) {
                 const float inv = (float)P.spp;
-                P.out_rgb[3ull * pixel + 0] = sum.x / inv;
-                P.out_rgb[3ull * pixel + 1] = sum.y / inv;
-                P.out_rgb[3ull * pixel + 2] = sum.z / inv;
+                P.T.store(pixel, sum.x / inv, sum.y / inv, sum.z / inv);
             }
             unsigned long long tile = 0;
             if (lane == 0) tile = atomicAdd(P.work_counter, 1ull);
             tile = __shfl_sync(FULL, tile, 0);
             if ((long long)tile >= P.n_tiles) break;
             const int tx = (int)(tile / tiles_y), ty = (int)(tile - (unsigned long long)tx * tiles_y);
-            x = tx * 4 + (lane >> 3);
+            const int xl = tx * 4 + (lane >> 3);  // column of the rank's compact strip space
+            x = P.T.image_column(xl);
             y = ty * 8 + (lane & 7);
-            active = x < P.width && y < P.height;
+            active = xl < P.T.local_cols && x < P.width && y < P.height;
             pixel = (uint32_t)((long long)x * P.height + y);
             s = 0;
             spp_eff = active ? P.spp : 0;

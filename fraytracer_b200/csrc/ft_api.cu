@@ -210,6 +210,237 @@ RenderParams make_params(int width, int height, float eps, float length, int str
     return P;
 }
 
+
+// pixels of the frame the strips of `T` cover (padding columns of the last strip excluded)
+int64_t owned_pixels(const StripTarget &T, int width, int height) {
+    int64_t cols = 0;
+    for (int xl = 0; xl < T.local_cols; xl++) {
+        const int strip = xl / T.strip_width;
+        cols += (strip * T.world + T.rank) * T.strip_width + (xl - strip * T.strip_width) < width;
+    }
+    return cols * height;
+}
+
+StripTarget whole_frame(int width) {
+    StripTarget T{};
+    T.strip_width = 8;
+    T.rank = 0;
+    T.world = 1;
+    T.local_cols = width;
+    return T;
+}
+
+int make_target(int width, int strip_width, int rank, int world, float *const *d_dst, int n_dst, StripTarget *out) {
+    if (strip_width <= 0 || world <= 0 || rank < 0 || rank >= world || !d_dst || n_dst < 1 || n_dst > FT_MAX_DST)
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid strip partition or destination count");
+    StripTarget T{};
+    T.strip_width = strip_width;
+    T.rank = rank;
+    T.world = world;
+    const int strips = (width + strip_width - 1) / strip_width, spr = (strips + world - 1) / world;
+    T.local_cols = world == 1 ? width : spr * strip_width;
+    T.n_dst = n_dst;
+    for (int k = 0; k < n_dst; k++) {
+        if (!d_dst[k]) return fail(FT_ERR_INVALID_ARGUMENT, "null destination framebuffer");
+        T.dst[k] = d_dst[k];
+    }
+    *out = T;
+    return FT_OK;
+}
+
+// Spectral wavefront pipeline for the strips `T` describes.  host_out != NULL: the frame is rendered into the scene's scratch
+// image (T.dst[0] is set here) and copied to the host; otherwise every pixel goes to T's destination framebuffers.
+int spectral_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon, float length,
+                  int32_t n_wavelengths, int32_t max_bounces, uint64_t seed, StripTarget T, cudaStream_t s, float *out_rgb,
+                  ft_render_stats *stats) {
+    if (!scene || !camera) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (width <= 0 || height <= 0 || (int64_t)width * height >= ((int64_t)1 << 31))
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size");
+    if (n_wavelengths < 1 || n_wavelengths > 64) return fail(FT_ERR_INVALID_ARGUMENT, "n_wavelengths must be in 1..64");
+    if (max_bounces < 0 || max_bounces > 256) return fail(FT_ERR_INVALID_ARGUMENT, "max_bounces must be in 0..256");
+    int st = check_ray_params(epsilon, length);
+    if (st != FT_OK) return st;
+    if (scene->host.n_lights > FT_SPECTRAL_MAX_LIGHTS)
+        return fail(FT_ERR_INVALID_ARGUMENT, "ft_render_spectral supports at most FT_SPECTRAL_MAX_LIGHTS lights");
+    if (scene->host.has_cloud)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_CLOUD (volumetric extension): render it with ft_render_cloud");
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    const size_t npix = (size_t)width * height, npix_local = (size_t)T.local_cols * height;
+    const size_t rgb_bytes = out_rgb ? (npix * 3 * sizeof(float) + 255) & ~(size_t)255 : 0;
+    CU(scene->reserve(rgb_bytes + npix_local * 3 * sizeof(float4)));  // (image +) worst-case hit queue of this rank's strips
+    if (!scene->d_spec_counts) {
+        CU(cudaMalloc(&scene->d_spec_counts, 512 * sizeof(unsigned)));
+        CU(cudaMallocHost(&scene->h_spec_counts, 512 * sizeof(unsigned)));
+    }
+    SpectralParams P{};
+    P.cam = *camera;
+    P.width = width;
+    P.height = height;
+    P.epsilon = epsilon;
+    P.length = length;
+    P.max_size = (float)std::max(width, height);
+    P.nl = n_wavelengths;
+    P.max_bounces = max_bounces;
+    P.seed_lo = (uint32_t)seed;
+    P.seed_hi = (uint32_t)(seed >> 32);
+    P.n_items = (long long)((T.local_cols + 3) / 4) * ((height + 7) / 8) * 32;
+    if (out_rgb) {
+        T.n_dst = 1;
+        T.dst[0] = (float *)scene->d_scratch;
+    }
+    P.T = T;
+    P.hit_q = (float4 *)((char *)scene->d_scratch + rgb_bytes);
+    unsigned *counts = scene->d_spec_counts;  // [0] glass hits, [1 + w] live paths entering wave w
+    P.hit_count = counts;
+    P.stats = scene->d_stats;
+    CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(counts, 0, 512 * sizeof(unsigned), s));
+    CU(cudaEventRecord(scene->ev[0], s));
+    int launches = 0;
+    // ---- wave 0: primary rays
+    P.wave = 0;
+    CU(fresh_counter(scene, s, &P.work_counter));
+    cudaError_t e = spectral_launch_primary(scene->dev, P, scene->sm_count, s);
+    if (e != cudaSuccess) return cuda_fail(e, "spectral primary kernel launch");
+    launches++;
+    CU(cudaMemcpyAsync(scene->h_spec_counts, counts, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));  // the one host round trip: the path queues are sized by the glass hit count
+    const unsigned n_hits = scene->h_spec_counts[0];
+    const unsigned long long n_paths0 = (unsigned long long)n_hits * (unsigned)n_wavelengths;
+    if (n_paths0 >= (1ull << 31)) return fail(FT_ERR_INVALID_ARGUMENT, "too many spectral paths for one call (>= 2^31)");
+    if (n_hits > 0) {
+        const size_t slot_bytes = (n_paths0 * sizeof(float) + 255) & ~(size_t)255;
+        const size_t q_bytes = max_bounces > 0 ? n_paths0 * 3 * sizeof(float4) : 0;
+        CU(scene->reserve2(slot_bytes + 2 * q_bytes));
+        P.slots = (float *)scene->d_scratch2;
+        float4 *qa = (float4 *)((char *)scene->d_scratch2 + slot_bytes), *qb = (float4 *)((char *)qa + q_bytes);
+        // ---- the material stage of wave 0
+        P.out_q = qa;
+        e = spectral_launch_spawn(scene->dev, P, n_hits, s);
+        if (e != cudaSuccess) return cuda_fail(e, "spectral spawn kernel launch");
+        launches++;
+        if (max_bounces > 0) {
+            scene->h_spec_counts[1] = (unsigned)n_paths0;  // pinned
+            CU(cudaMemcpyAsync(counts + 1, scene->h_spec_counts + 1, sizeof(unsigned), cudaMemcpyHostToDevice, s));
+            // ---- waves 1 .. max_bounces (a wave whose queue is empty exits at once)
+            for (int w = 1; w <= max_bounces; w++) {
+                P.wave = w;
+                P.in_q = (w & 1) ? qa : qb;
+                P.out_q = (w & 1) ? qb : qa;
+                P.in_count = counts + w;
+                P.out_count = counts + w + 1;
+                CU(fresh_counter(scene, s, &P.work_counter));
+                e = spectral_launch_wave(scene->dev, P, (long long)n_paths0, scene->sm_count, s);
+                if (e != cudaSuccess) return cuda_fail(e, "spectral wave kernel launch");
+                launches++;
+            }
+        }
+        e = spectral_launch_resolve(P, n_hits, s);
+        if (e != cudaSuccess) return cuda_fail(e, "spectral resolve kernel launch");
+        launches++;
+    }
+    CU(cudaEventRecord(scene->ev[1], s));
+    if (out_rgb) CU(cudaMemcpyAsync(out_rgb, T.dst[0], npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(scene->ev[2], s));
+    CU(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        sum_stats(scene->h_stats, stats);
+        unsigned long long paths = 0;
+        for (int k = 0; k < FT_STAT_SLOTS; k++) paths += scene->h_stats[(size_t)k * FT_STAT_STRIDE + FT_STAT_PATHS];
+        stats->primary_rays = owned_pixels(T, width, height);
+        stats->shadow_rays += (int64_t)paths;  // every secondary ray: shadow rays + continuation segments
+        stats->reserved = (int32_t)n_hits;     // pixels whose primary ray hit glass
+        stats->launches = launches;
+        cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
+        cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
+    }
+    return FT_OK;
+}
+
+
+// Volumetric cloud kernel for the strips `T` describes; host_out as in spectral_core.
+int cloud_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon, float length,
+               const ft_cloud_params *cloud, int32_t samples_per_pixel, uint64_t seed, StripTarget T, cudaStream_t s,
+               float *out_rgb, ft_render_stats *stats) {
+    if (!scene || !camera || !cloud || !cloud->perm || !cloud->gradients) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    if (width <= 0 || height <= 0 || (int64_t)width * height >= ((int64_t)1 << 31))
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size");
+    if (samples_per_pixel < 1 || samples_per_pixel > 65536) return fail(FT_ERR_INVALID_ARGUMENT, "samples_per_pixel must be in 1..65536");
+    if (!(cloud->step > 0.0f) || !(cloud->fade > 0.0f)) return fail(FT_ERR_INVALID_ARGUMENT, "cloud step and fade must be > 0");
+    for (int i = 0; i < 256; i++)
+        if (cloud->perm[i] < 0 || cloud->perm[i] > 255) return fail(FT_ERR_INVALID_ARGUMENT, "cloud perm entries must be in 0..255");
+    int st = check_ray_params(epsilon, length);
+    if (st != FT_OK) return st;
+    if (scene->host.has_glass)
+        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
+    if (scene->device == FT_DEVICE_NONE)
+        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    DeviceGuard guard(scene->device);
+    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
+    const size_t npix = (size_t)width * height;
+    if (out_rgb) {
+        CU(scene->reserve(npix * 3 * sizeof(float)));
+        T.n_dst = 1;
+        T.dst[0] = (float *)scene->d_scratch;
+    }
+    if (!scene->d_cloud_perm) {
+        CU(cudaMalloc(&scene->d_cloud_perm, 256 * sizeof(int)));
+        CU(cudaMalloc(&scene->d_cloud_grad, 768 * sizeof(double)));
+    }
+    CU(cudaMemcpyAsync(scene->d_cloud_perm, cloud->perm, 256 * sizeof(int), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(scene->d_cloud_grad, cloud->gradients, 768 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CloudParams P{};
+    P.cam = *camera;
+    P.width = width;
+    P.height = height;
+    P.epsilon = epsilon;
+    P.length = length;
+    P.max_size = (float)std::max(width, height);
+    P.spp = samples_per_pixel;
+    P.seed_lo = (uint32_t)seed;
+    P.seed_hi = (uint32_t)(seed >> 32);
+    P.n_tiles = (long long)((T.local_cols + 3) / 4) * ((height + 7) / 8);
+    P.density = cloud->density;
+    P.frequency = cloud->frequency;
+    P.step = cloud->step;
+    P.fade = cloud->fade;
+    P.bias = cloud->bias;
+    P.gain = cloud->gain;
+    P.perm = scene->d_cloud_perm;
+    P.gradients = scene->d_cloud_grad;
+    P.T = T;
+    P.stats = scene->d_stats;
+    CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
+    CU(fresh_counter(scene, s, &P.work_counter));
+    CU(cudaEventRecord(scene->ev[0], s));
+    cudaError_t e = cloud_launch(scene->dev, P, scene->sm_count, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cloud kernel launch");
+    CU(cudaEventRecord(scene->ev[1], s));
+    if (out_rgb) CU(cudaMemcpyAsync(out_rgb, T.dst[0], npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(scene->ev[2], s));
+    CU(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        sum_stats(scene->h_stats, stats);
+        unsigned long long scattered = 0;
+        for (int k = 0; k < FT_STAT_SLOTS; k++) scattered += scene->h_stats[(size_t)k * FT_STAT_STRIDE + FT_STAT_PATHS];
+        stats->primary_rays = owned_pixels(T, width, height) * samples_per_pixel;
+        stats->reserved = (int32_t)std::min<unsigned long long>(scattered, 0x7fffffffull);
+        stats->launches = 1;
+        cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
+        cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
+    }
+    return FT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -827,184 +1058,39 @@ FT_API int ft_distance(ft_scene *scene, int64_t n, const float *positions, uint3
 FT_API int ft_render_spectral(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
                               float length, int32_t n_wavelengths, int32_t max_bounces, uint64_t seed, float *out_rgb,
                               ft_render_stats *stats) {
-    if (!scene || !camera || !out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
-    if (width <= 0 || height <= 0 || (int64_t)width * height >= ((int64_t)1 << 31))
-        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size");
-    if (n_wavelengths < 1 || n_wavelengths > 64) return fail(FT_ERR_INVALID_ARGUMENT, "n_wavelengths must be in 1..64");
-    if (max_bounces < 0 || max_bounces > 256) return fail(FT_ERR_INVALID_ARGUMENT, "max_bounces must be in 0..256");
-    int st = check_ray_params(epsilon, length);
+    if (!scene || !out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    return spectral_core(scene, camera, width, height, epsilon, length, n_wavelengths, max_bounces, seed, whole_frame(width),
+                         scene->stream, out_rgb, stats);
+}
+
+FT_API int ft_render_spectral_gather_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                                            float length, int32_t n_wavelengths, int32_t max_bounces, uint64_t seed,
+                                            int32_t strip_width, int32_t rank, int32_t world, float *const *d_dst, int32_t n_dst,
+                                            void *stream, ft_render_stats *stats) {
+    StripTarget T;
+    int st = make_target(width, strip_width, rank, world, d_dst, n_dst, &T);
     if (st != FT_OK) return st;
-    if (scene->host.n_lights > FT_SPECTRAL_MAX_LIGHTS)
-        return fail(FT_ERR_INVALID_ARGUMENT, "ft_render_spectral supports at most FT_SPECTRAL_MAX_LIGHTS lights");
-    if (scene->host.has_cloud)
-        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_CLOUD (volumetric extension): render it with ft_render_cloud");
-    if (scene->device == FT_DEVICE_NONE)
-        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
-    std::lock_guard<std::mutex> lock(scene->mu);
-    DeviceGuard guard(scene->device);
-    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
-    const size_t npix = (size_t)width * height;
-    const size_t rgb_bytes = (npix * 3 * sizeof(float) + 255) & ~(size_t)255;
-    CU(scene->reserve(rgb_bytes + npix * 3 * sizeof(float4)));  // image + worst-case hit queue
-    if (!scene->d_spec_counts) {
-        CU(cudaMalloc(&scene->d_spec_counts, 512 * sizeof(unsigned)));
-        CU(cudaMallocHost(&scene->h_spec_counts, 512 * sizeof(unsigned)));
-    }
-    cudaStream_t s = scene->stream;
-    SpectralParams P{};
-    P.cam = *camera;
-    P.width = width;
-    P.height = height;
-    P.epsilon = epsilon;
-    P.length = length;
-    P.max_size = (float)std::max(width, height);
-    P.nl = n_wavelengths;
-    P.max_bounces = max_bounces;
-    P.seed_lo = (uint32_t)seed;
-    P.seed_hi = (uint32_t)(seed >> 32);
-    P.n_items = (long long)((width + 3) / 4) * ((height + 7) / 8) * 32;
-    P.out_rgb = (float *)scene->d_scratch;
-    P.hit_q = (float4 *)((char *)scene->d_scratch + rgb_bytes);
-    unsigned *counts = scene->d_spec_counts;  // [0] glass hits, [1 + w] live paths entering wave w
-    P.hit_count = counts;
-    P.stats = scene->d_stats;
-    CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
-    CU(cudaMemsetAsync(counts, 0, 512 * sizeof(unsigned), s));
-    CU(cudaEventRecord(scene->ev[0], s));
-    int launches = 0;
-    // ---- wave 0: primary rays
-    P.wave = 0;
-    CU(fresh_counter(scene, s, &P.work_counter));
-    cudaError_t e = spectral_launch_primary(scene->dev, P, scene->sm_count, s);
-    if (e != cudaSuccess) return cuda_fail(e, "spectral primary kernel launch");
-    launches++;
-    CU(cudaMemcpyAsync(scene->h_spec_counts, counts, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));  // the one host round trip: the path queues are sized by the glass hit count
-    const unsigned n_hits = scene->h_spec_counts[0];
-    const unsigned long long n_paths0 = (unsigned long long)n_hits * (unsigned)n_wavelengths;
-    if (n_paths0 >= (1ull << 31)) return fail(FT_ERR_INVALID_ARGUMENT, "too many spectral paths for one call (>= 2^31)");
-    if (n_hits > 0) {
-        const size_t slot_bytes = (n_paths0 * sizeof(float) + 255) & ~(size_t)255;
-        const size_t q_bytes = max_bounces > 0 ? n_paths0 * 3 * sizeof(float4) : 0;
-        CU(scene->reserve2(slot_bytes + 2 * q_bytes));
-        P.slots = (float *)scene->d_scratch2;
-        float4 *qa = (float4 *)((char *)scene->d_scratch2 + slot_bytes), *qb = (float4 *)((char *)qa + q_bytes);
-        // ---- the material stage of wave 0
-        P.out_q = qa;
-        e = spectral_launch_spawn(scene->dev, P, n_hits, s);
-        if (e != cudaSuccess) return cuda_fail(e, "spectral spawn kernel launch");
-        launches++;
-        if (max_bounces > 0) {
-            scene->h_spec_counts[1] = (unsigned)n_paths0;  // pinned
-            CU(cudaMemcpyAsync(counts + 1, scene->h_spec_counts + 1, sizeof(unsigned), cudaMemcpyHostToDevice, s));
-            // ---- waves 1 .. max_bounces (a wave whose queue is empty exits at once)
-            for (int w = 1; w <= max_bounces; w++) {
-                P.wave = w;
-                P.in_q = (w & 1) ? qa : qb;
-                P.out_q = (w & 1) ? qb : qa;
-                P.in_count = counts + w;
-                P.out_count = counts + w + 1;
-                CU(fresh_counter(scene, s, &P.work_counter));
-                e = spectral_launch_wave(scene->dev, P, (long long)n_paths0, scene->sm_count, s);
-                if (e != cudaSuccess) return cuda_fail(e, "spectral wave kernel launch");
-                launches++;
-            }
-        }
-        e = spectral_launch_resolve(P, n_hits, s);
-        if (e != cudaSuccess) return cuda_fail(e, "spectral resolve kernel launch");
-        launches++;
-    }
-    CU(cudaEventRecord(scene->ev[1], s));
-    CU(cudaMemcpyAsync(out_rgb, P.out_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(scene->ev[2], s));
-    CU(cudaStreamSynchronize(s));
-    if (stats) {
-        std::memset(stats, 0, sizeof(*stats));
-        sum_stats(scene->h_stats, stats);
-        unsigned long long paths = 0;
-        for (int k = 0; k < FT_STAT_SLOTS; k++) paths += scene->h_stats[(size_t)k * FT_STAT_STRIDE + FT_STAT_PATHS];
-        stats->primary_rays = (int64_t)npix;
-        stats->shadow_rays += (int64_t)paths;  // every secondary ray: shadow rays + continuation segments
-        stats->reserved = (int32_t)n_hits;     // pixels whose primary ray hit glass
-        stats->launches = launches;
-        cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
-        cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
-    }
-    return FT_OK;
+    return spectral_core(scene, camera, width, height, epsilon, length, n_wavelengths, max_bounces, seed, T, (cudaStream_t)stream,
+                         nullptr, stats);
 }
 
 FT_API int ft_render_cloud(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
                            float length, const ft_cloud_params *cloud, int32_t samples_per_pixel, uint64_t seed,
                            float *out_rgb, ft_render_stats *stats) {
-    if (!scene || !camera || !out_rgb || !cloud || !cloud->perm || !cloud->gradients) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
-    if (width <= 0 || height <= 0 || (int64_t)width * height >= ((int64_t)1 << 31))
-        return fail(FT_ERR_INVALID_ARGUMENT, "invalid image size");
-    if (samples_per_pixel < 1 || samples_per_pixel > 65536) return fail(FT_ERR_INVALID_ARGUMENT, "samples_per_pixel must be in 1..65536");
-    if (!(cloud->step > 0.0f) || !(cloud->fade > 0.0f)) return fail(FT_ERR_INVALID_ARGUMENT, "cloud step and fade must be > 0");
-    for (int i = 0; i < 256; i++)
-        if (cloud->perm[i] < 0 || cloud->perm[i] > 255) return fail(FT_ERR_INVALID_ARGUMENT, "cloud perm entries must be in 0..255");
-    int st = check_ray_params(epsilon, length);
+    if (!scene || !out_rgb) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    return cloud_core(scene, camera, width, height, epsilon, length, cloud, samples_per_pixel, seed, whole_frame(width),
+                      scene->stream, out_rgb, stats);
+}
+
+FT_API int ft_render_cloud_gather_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
+                                         float length, const ft_cloud_params *cloud, int32_t samples_per_pixel, uint64_t seed,
+                                         int32_t strip_width, int32_t rank, int32_t world, float *const *d_dst, int32_t n_dst,
+                                         void *stream, ft_render_stats *stats) {
+    StripTarget T;
+    int st = make_target(width, strip_width, rank, world, d_dst, n_dst, &T);
     if (st != FT_OK) return st;
-    if (scene->host.has_glass)
-        return fail(FT_ERR_UNSUPPORTED_NODE, "the scene uses FT_MATERIAL_GLASS (spectral extension): render it with ft_render_spectral");
-    if (scene->device == FT_DEVICE_NONE)
-        return fail(FT_ERR_NO_DEVICE, "compile-only scene handle (FT_DEVICE_NONE): fraytracer_b200 has no CPU fallback");
-    std::lock_guard<std::mutex> lock(scene->mu);
-    DeviceGuard guard(scene->device);
-    if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
-    const size_t npix = (size_t)width * height;
-    CU(scene->reserve(npix * 3 * sizeof(float)));
-    if (!scene->d_cloud_perm) {
-        CU(cudaMalloc(&scene->d_cloud_perm, 256 * sizeof(int)));
-        CU(cudaMalloc(&scene->d_cloud_grad, 768 * sizeof(double)));
-    }
-    cudaStream_t s = scene->stream;
-    CU(cudaMemcpyAsync(scene->d_cloud_perm, cloud->perm, 256 * sizeof(int), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(scene->d_cloud_grad, cloud->gradients, 768 * sizeof(double), cudaMemcpyHostToDevice, s));
-    CloudParams P{};
-    P.cam = *camera;
-    P.width = width;
-    P.height = height;
-    P.epsilon = epsilon;
-    P.length = length;
-    P.max_size = (float)std::max(width, height);
-    P.spp = samples_per_pixel;
-    P.seed_lo = (uint32_t)seed;
-    P.seed_hi = (uint32_t)(seed >> 32);
-    P.n_tiles = (long long)((width + 3) / 4) * ((height + 7) / 8);
-    P.density = cloud->density;
-    P.frequency = cloud->frequency;
-    P.step = cloud->step;
-    P.fade = cloud->fade;
-    P.bias = cloud->bias;
-    P.gain = cloud->gain;
-    P.perm = scene->d_cloud_perm;
-    P.gradients = scene->d_cloud_grad;
-    P.out_rgb = (float *)scene->d_scratch;
-    P.stats = scene->d_stats;
-    CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
-    CU(fresh_counter(scene, s, &P.work_counter));
-    CU(cudaEventRecord(scene->ev[0], s));
-    cudaError_t e = cloud_launch(scene->dev, P, scene->sm_count, s);
-    if (e != cudaSuccess) return cuda_fail(e, "cloud kernel launch");
-    CU(cudaEventRecord(scene->ev[1], s));
-    CU(cudaMemcpyAsync(out_rgb, P.out_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CU(cudaEventRecord(scene->ev[2], s));
-    CU(cudaStreamSynchronize(s));
-    if (stats) {
-        std::memset(stats, 0, sizeof(*stats));
-        sum_stats(scene->h_stats, stats);
-        unsigned long long scattered = 0;
-        for (int k = 0; k < FT_STAT_SLOTS; k++) scattered += scene->h_stats[(size_t)k * FT_STAT_STRIDE + FT_STAT_PATHS];
-        stats->primary_rays = (int64_t)npix * samples_per_pixel;
-        stats->reserved = (int32_t)std::min<unsigned long long>(scattered, 0x7fffffffull);
-        stats->launches = 1;
-        cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
-        cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
-    }
-    return FT_OK;
+    return cloud_core(scene, camera, width, height, epsilon, length, cloud, samples_per_pixel, seed, T, (cudaStream_t)stream,
+                      nullptr, stats);
 }
 
 FT_API int ft_image_max_device(const float *d_rgb, int64_t n_floats, float *d_max, void *stream) {

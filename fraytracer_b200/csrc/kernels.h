@@ -27,6 +27,32 @@ struct RenderParams {
     float epsilon, length, max_size;
 };
 
+// Which pixels a rank renders and where they go (multi-GPU): column strips dealt round-robin
+// (strip s -> rank s % world) and a list of destination framebuffers -- the rank's own, its peers' (CUDA IPC) or mapped
+// host memory -- that receive every finished pixel at its final x-major position.  world == 1: the whole frame.
+#define FT_MAX_DST 16
+struct StripTarget {
+    int strip_width, rank, world;
+    int local_cols;  // columns of the rank's compact strip space (strips_per_rank * strip_width; width when world == 1)
+    int n_dst;
+    float *dst[FT_MAX_DST];
+#if defined(__CUDACC__)
+    // column of the compact strip space -> image column (may be >= width: padding of the last strip)
+    __device__ __forceinline__ int image_column(int xl) const {
+        const int strip = xl / strip_width;
+        return (strip * world + rank) * strip_width + (xl - strip * strip_width);
+    }
+    __device__ __forceinline__ void store(unsigned long long pixel, float r, float g, float b) const {
+        for (int k = 0; k < n_dst; k++) {
+            float *out = dst[k] + 3ull * pixel;
+            out[0] = r;
+            out[1] = g;
+            out[2] = b;
+        }
+    }
+#endif
+};
+
 #define FT_DECLARE_LAUNCHERS(NS)                                                                                      \
     namespace NS {                                                                                                    \
     cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb,         \

@@ -13,8 +13,8 @@ struct SpectralParams {
     int max_bounces;  // glass interactions allowed per path
     int wave;         // glass interactions the paths of this launch have behind them
     uint32_t seed_lo, seed_hi;
-    long long n_items;  // wave 0: pixel tiles * 32
-    float *out_rgb;     // device FColor[X,Y]
+    long long n_items;  // wave 0: pixel tiles of the rank's compact strip space * 32
+    StripTarget T;      // the rank's strips and the destination framebuffers
     float4 *hit_q;      // glass hits of wave 0: {origin, Length} {direction, bits(pixel)} {normal, bits(material)}
     unsigned *hit_count;
     const float4 *in_q;  // live paths: {origin, dir.x} {dir.y, dir.z, Length, bits(pixel)} {bits(slot), bits(k), -, -}

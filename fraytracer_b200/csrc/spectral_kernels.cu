@@ -73,7 +73,7 @@ __device__ __forceinline__ float pick6(const float (&a)[6], int b) {
 }
 
 // pixel RGB = sum_k w(nu_k) L_k / sum_k w(nu_k), accumulated in k order; Lb[b] is L for the band of nu_k
-__device__ __forceinline__ void write_pixel_from_bands(float *out_rgb, long long pixel, int nl, const float (&Lb)[6]) {
+__device__ __forceinline__ void write_pixel_from_bands(const StripTarget &T, long long pixel, int nl, const float (&Lb)[6]) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
     for (int k = 0; k < nl; k++) {
         const int b = band_of(wavelength_nu(k, nl));
@@ -83,9 +83,7 @@ __device__ __forceinline__ void write_pixel_from_bands(float *out_rgb, long long
         a0 = a0 + w0 * L; a1 = a1 + w1 * L; a2 = a2 + w2 * L;
         d0 = d0 + w0; d1 = d1 + w1; d2 = d2 + w2;
     }
-    out_rgb[3 * pixel + 0] = d0 > 0.0f ? a0 / d0 : 0.0f;
-    out_rgb[3 * pixel + 1] = d1 > 0.0f ? a1 / d1 : 0.0f;
-    out_rgb[3 * pixel + 2] = d2 > 0.0f ? a2 / d2 : 0.0f;
+    T.store((unsigned long long)pixel, d0 > 0.0f ? a0 / d0 : 0.0f, d1 > 0.0f ? a1 / d1 : 0.0f, d2 > 0.0f ? a2 / d2 : 0.0f);
 }
 
 // ---- the glass interaction: Light.fresnel n1 n2 N direction (Light.fs:30-59) as written, N = the surface normal
@@ -175,8 +173,9 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                     const long long tile = i >> 5;
                     const int tiles_y = (P.height + 7) / 8;
                     const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
-                    const int x = tx * 4 + (lane >> 3), y = ty * 8 + (lane & 7);
-                    if (x < P.width && y < P.height) {
+                    const int xl = tx * 4 + (lane >> 3), y = ty * 8 + (lane & 7);  // xl: column of the rank's compact strip space
+                    const int x = P.T.image_column(xl);
+                    if (xl < P.T.local_cols && x < P.width && y < P.height) {
                         pixel = (uint32_t)((long long)x * P.height + y);
                         o = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
                         d = pixel_direction(P.cam, x, y, P.max_size);
@@ -286,7 +285,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                     float Lb[6];
 #pragma unroll
                     for (int b = 0; b < 6; b++) Lb[b] = spec(bg, b);
-                    write_pixel_from_bands(P.out_rgb, pixel, P.nl, Lb);
+                    write_pixel_from_bands(P.T, pixel, P.nl, Lb);
                 } else {
                     P.slots[slot] = spec(bg, band);
                 }
@@ -368,7 +367,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                         float Lb[6];
 #pragma unroll
                         for (int b = 0; b < 6; b++) Lb[b] = spec(albedo, b) * (lcb[b < NB ? b : 0] * pi_inv);
-                        write_pixel_from_bands(P.out_rgb, pixel, P.nl, Lb);
+                        write_pixel_from_bands(P.T, pixel, P.nl, Lb);
                     } else {
                         P.slots[slot] = spec(albedo, band) * (lcb[0] * pi_inv);
                     }
@@ -440,9 +439,7 @@ __global__ void __launch_bounds__(SB) spectral_resolve_kernel(const __grid_const
         a0 = a0 + w0 * L; a1 = a1 + w1 * L; a2 = a2 + w2 * L;
         d0 = d0 + w0; d1 = d1 + w1; d2 = d2 + w2;
     }
-    P.out_rgb[3ull * pixel + 0] = d0 > 0.0f ? a0 / d0 : 0.0f;
-    P.out_rgb[3ull * pixel + 1] = d1 > 0.0f ? a1 / d1 : 0.0f;
-    P.out_rgb[3ull * pixel + 2] = d2 > 0.0f ? a2 / d2 : 0.0f;
+    P.T.store(pixel, d0 > 0.0f ? a0 / d0 : 0.0f, d1 > 0.0f ? a1 / d1 : 0.0f, d2 > 0.0f ? a2 / d2 : 0.0f);
 }
 
 template <class K>

@@ -158,6 +158,27 @@ class DistributedRenderer:
                              for _, n in self.chunk_ranges]
         self.launches_per_frame = 1 if self.world == 1 else 2 * len(self.chunk_ranges)
 
+    # ---- the extension paths (configs 3 and 4: no reference implementation) over the same strips and peer framebuffers
+    def render_extension(self, kind: str, camera, epsilon: float, length: float, **kw):
+        """kind = "spectral" | "cloud": one frame on all ranks, every rank ends with the full framebuffer (P2P gather only).
+        Returns (frame tensor, this rank's stats)."""
+        torch = self.torch
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.world == 1:
+            dst = [self.final.data_ptr()]
+        else:
+            if self.gather != "p2p":
+                raise RuntimeError("the extension paths gather through peer framebuffers only (gather='p2p')")
+            parity = self._frame & 1
+            self._frame += 1
+            dst = self.dst[parity]
+        st = self.tracer.render_extension_gather_device(kind, camera, self.size, epsilon, length, dst, stream=stream,
+                                                        strip_width=self.strip_width, rank=self.rank, world=self.world, **kw)
+        if self.world > 1:
+            self.dist.all_reduce(self._done, group=self.group)
+            self.final = self.frames[parity]
+        return self.final, st
+
     # ---- framebuffer in shared, page-locked host memory: every GPU delivers its own strips over its own PCIe link
     def host_frame(self):
         """Creates (once) a FColor[X,Y] in POSIX shared memory, mapped and page-locked by every rank's process.

@@ -352,6 +352,14 @@ FT_API int ft_render_spectral(ft_scene *scene, const ft_camera *camera, int32_t 
                               float length, int32_t n_wavelengths, int32_t max_bounces, uint64_t seed,
                               float *out_rgb, ft_render_stats *stats);
 
+/* the same for the strips `rank` of `world` owns, every finished pixel stored at its final position in each of the n_dst
+ * destination framebuffers (DEVICE pointers, see ft_render_gather_device).  Synchronous on `stream` (the pipeline sizes its
+ * path queues from a count read back after wave 0).                                                                    */
+FT_API int ft_render_spectral_gather_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
+                                            float epsilon, float length, int32_t n_wavelengths, int32_t max_bounces,
+                                            uint64_t seed, int32_t strip_width, int32_t rank, int32_t world,
+                                            float *const *d_dst, int32_t n_dst, void *stream, ft_render_stats *stats);
+
 /* ---- EXTENSION: volumetric cloud material (BASELINE config 4) ----------------------------------------------------
  * No reference implementation exists: builder-defined spec in DESIGN.md 4.7.  The density field
  * is the reference's dead-code lattice noise Noise.gradient (Noise.fs:78-110, float64, used as written including the
@@ -377,6 +385,14 @@ typedef struct ft_cloud_params {
 FT_API int ft_render_cloud(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
                            float length, const ft_cloud_params *cloud, int32_t samples_per_pixel, uint64_t seed,
                            float *out_rgb, ft_render_stats *stats);
+
+/* the same for the strips `rank` of `world` owns into n_dst destination framebuffers (see ft_render_gather_device);
+ * returns after the kernel has finished.                                                                            */
+FT_API int ft_render_cloud_gather_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
+                                         float epsilon, float length, const ft_cloud_params *cloud,
+                                         int32_t samples_per_pixel, uint64_t seed, int32_t strip_width, int32_t rank,
+                                         int32_t world, float *const *d_dst, int32_t n_dst, void *stream,
+                                         ft_render_stats *stats);
 
 /* ---- post-process: Image.toColors / toBitmap / saveBitmap (Image.fs:37-90) -- */
 /* max over the n_floats values of an FColor image (Array2D.Parallel.maxWith FColor.getMaxColor, Image.fs:40-42);

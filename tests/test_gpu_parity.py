@@ -397,3 +397,33 @@ def test_instrumented_kernel_counters_against_oracle_counters():
         prims2 = 21 * c2["eval_capsule"] + 27 * c2["eval_torus"] + 85 * c2["eval_triangle_edge"] + 34 * c2["eval_triangle_face"]
         assert st2["eval_flops"] >= prims2 + 7 * (c2["march_steps"] - c2["primary_hits"] - c2["shadow_rays"])
         tracer.close()
+
+
+def test_extension_strip_rendering_equals_whole_frame():
+    """EXTENSIONS: the strips of 3 'ranks' rendered one after the other into two destination framebuffers reproduce the
+    whole-frame spectral / cloud render bit for bit (the multi-GPU path minus the second GPU)"""
+    import torch
+
+    from fraytracer_b200 import CloudParams
+
+    cases = (("spectral", scenes.spectral_glass_scene(width=150, height=90), dict(n_wavelengths=8, max_bounces=5, seed=3)),
+             ("cloud", scenes.cloud_scene(width=150, height=90), dict(samples_per_pixel=5, seed=3)))
+    for kind, w, kw in cases:
+        tracer = ft.SceneTracer(w.scene, device=0)
+        if kind == "spectral":
+            ref, st = tracer.render_spectral(w.camera, w.size, w.epsilon, w.length, 8, 5, 3)
+        else:
+            ref, st = tracer.render_cloud(w.camera, w.size, w.epsilon, w.length, CloudParams(), 5, 3)
+        X, Y = w.size.X, w.size.Y
+        for world, sw in ((1, 8), (3, 8), (2, 20)):
+            dsts = [torch.full((X, Y, 3), -7.0, dtype=torch.float32, device="cuda") for _ in range(2)]
+            rays = 0
+            for rank in range(world):
+                s = tracer.render_extension_gather_device(kind, w.camera, w.size, w.epsilon, w.length, [d.data_ptr() for d in dsts],
+                                                          strip_width=sw, rank=rank, world=world, **kw)
+                rays += s["primary_rays"] + s["shadow_rays"]
+            torch.cuda.synchronize()
+            for d in dsts:
+                assert np.array_equal(bits(d.cpu().numpy()), bits(ref)), (kind, world, sw)
+            assert rays == st["primary_rays"] + st["shadow_rays"]
+        tracer.close()

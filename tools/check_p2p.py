@@ -36,6 +36,22 @@ for w, (X, Y) in ((scenes.default_scene(n_tori=300), (333, 251)), (scenes.sphere
                 print(f"rank {rank}/{world} {w.name} {X}x{Y} host frame {frame}: identical={same}", flush=True)
         r.close()
     tr.close()
+# the extension paths (no reference implementation): N-rank frame == 1-rank frame
+for kind, w, kw in (("spectral", scenes.spectral_glass_scene(width=320, height=180), dict(n_wavelengths=8, max_bounces=6, seed=5)),
+                    ("cloud", scenes.cloud_scene(width=320, height=180), dict(samples_per_pixel=6, seed=5))):
+    tr = ft.SceneTracer(w.scene, device=local)
+    if kind == "spectral":
+        ref, _ = tr.render_spectral(w.camera, w.size, w.epsilon, w.length, 8, 6, 5)
+    else:
+        ref, _ = tr.render_cloud(w.camera, w.size, w.epsilon, w.length, ft.CloudParams(), 6, 5)
+    r = DistributedRenderer(tr, w.size, gather="p2p")
+    for frame in range(2):
+        img, _ = r.render_extension(kind, w.camera, w.epsilon, w.length, **kw)
+        same = np.array_equal(img.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+        ok &= same
+        print(f"rank {rank}/{world} {w.name} {kind} strip {r.strip_width} frame {frame}: identical={same}", flush=True)
+    r.close()
+    tr.close()
 t = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(t)
 dist.destroy_process_group()
