@@ -133,11 +133,19 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             if (lane == 0) tile = atomicAdd(P.work_counter, 1ull);
             tile = __shfl_sync(FULL, tile, 0);
             if ((long long)tile >= P.n_tiles) break;
-            const int tx = (int)(tile / tiles_y), ty = (int)(tile - (unsigned long long)tx * tiles_y);
-            const int xl = tx * 4 + (lane >> 3);  // column of the rank's compact strip space
-            x = P.T.image_column(xl);
-            y = ty * 8 + (lane & 7);
-            active = xl < P.T.local_cols && x < P.width && y < P.height;
+            if (P.T.strip_width == 0) {  // tiles dealt round-robin over the ranks: the finest balance (cloud pixels cost ~50x)
+                const unsigned long long gt = tile * (unsigned)P.T.world + (unsigned)P.T.rank;
+                const int tx = (int)(gt / tiles_y), ty = (int)(gt - (unsigned long long)tx * tiles_y);
+                x = tx * 4 + (lane >> 3);
+                y = ty * 8 + (lane & 7);
+                active = x < P.width && y < P.height;
+            } else {
+                const int tx = (int)(tile / tiles_y), ty = (int)(tile - (unsigned long long)tx * tiles_y);
+                const int xl = tx * 4 + (lane >> 3);  // column of the rank's compact strip space
+                x = P.T.image_column(xl);
+                y = ty * 8 + (lane & 7);
+                active = xl < P.T.local_cols && x < P.width && y < P.height;
+            }
             pixel = (uint32_t)((long long)x * P.height + y);
             s = 0;
             spp_eff = active ? P.spp : 0;

@@ -213,12 +213,31 @@ RenderParams make_params(int width, int height, float eps, float length, int str
 
 // pixels of the frame the strips of `T` cover (padding columns of the last strip excluded)
 int64_t owned_pixels(const StripTarget &T, int width, int height) {
+    if (T.strip_width == 0) {  // tiles dealt round-robin
+        const int64_t tiles_y = (height + 7) / 8, total = (int64_t)((width + 3) / 4) * tiles_y;
+        int64_t n = 0;
+        for (int64_t t = T.rank; t < total; t += T.world) {
+            const int x0 = (int)(t / tiles_y) * 4, y0 = (int)(t % tiles_y) * 8;
+            n += (int64_t)std::min(4, width - x0) * std::min(8, height - y0);
+        }
+        return n;
+    }
     int64_t cols = 0;
     for (int xl = 0; xl < T.local_cols; xl++) {
         const int strip = xl / T.strip_width;
         cols += (strip * T.world + T.rank) * T.strip_width + (xl - strip * T.strip_width) < width;
     }
     return cols * height;
+}
+
+// 4 x 8 pixel tiles this rank renders
+long long local_tiles(const StripTarget &T, int width, int height) {
+    const long long tiles_y = (height + 7) / 8;
+    if (T.strip_width == 0) {
+        const long long total = (long long)((width + 3) / 4) * tiles_y;
+        return total > T.rank ? (total - T.rank + T.world - 1) / T.world : 0;
+    }
+    return (long long)((T.local_cols + 3) / 4) * tiles_y;
 }
 
 StripTarget whole_frame(int width) {
@@ -231,14 +250,18 @@ StripTarget whole_frame(int width) {
 }
 
 int make_target(int width, int strip_width, int rank, int world, float *const *d_dst, int n_dst, StripTarget *out) {
-    if (strip_width <= 0 || world <= 0 || rank < 0 || rank >= world || !d_dst || n_dst < 1 || n_dst > FT_MAX_DST)
+    if (strip_width < 0 || world <= 0 || rank < 0 || rank >= world || !d_dst || n_dst < 1 || n_dst > FT_MAX_DST)
         return fail(FT_ERR_INVALID_ARGUMENT, "invalid strip partition or destination count");
     StripTarget T{};
     T.strip_width = strip_width;
     T.rank = rank;
     T.world = world;
-    const int strips = (width + strip_width - 1) / strip_width, spr = (strips + world - 1) / world;
-    T.local_cols = world == 1 ? width : spr * strip_width;
+    if (strip_width > 0) {
+        const int strips = (width + strip_width - 1) / strip_width, spr = (strips + world - 1) / world;
+        T.local_cols = world == 1 ? width : spr * strip_width;
+    } else {
+        T.local_cols = width;  // tiles dealt round-robin: sizes below come from local_tiles()
+    }
     T.n_dst = n_dst;
     for (int k = 0; k < n_dst; k++) {
         if (!d_dst[k]) return fail(FT_ERR_INVALID_ARGUMENT, "null destination framebuffer");
@@ -269,7 +292,7 @@ int spectral_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32
     std::lock_guard<std::mutex> lock(scene->mu);
     DeviceGuard guard(scene->device);
     if (!guard.ok) return fail(FT_ERR_NO_DEVICE, "cudaSetDevice failed");
-    const size_t npix = (size_t)width * height, npix_local = (size_t)T.local_cols * height;
+    const size_t npix = (size_t)width * height, npix_local = (size_t)local_tiles(T, width, height) * 32;
     const size_t rgb_bytes = out_rgb ? (npix * 3 * sizeof(float) + 255) & ~(size_t)255 : 0;
     CU(scene->reserve(rgb_bytes + npix_local * 3 * sizeof(float4)));  // (image +) worst-case hit queue of this rank's strips
     if (!scene->d_spec_counts) {
@@ -287,7 +310,7 @@ int spectral_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32
     P.max_bounces = max_bounces;
     P.seed_lo = (uint32_t)seed;
     P.seed_hi = (uint32_t)(seed >> 32);
-    P.n_items = (long long)((T.local_cols + 3) / 4) * ((height + 7) / 8) * 32;
+    P.n_items = local_tiles(T, width, height) * 32;
     if (out_rgb) {
         T.n_dst = 1;
         T.dst[0] = (float *)scene->d_scratch;
@@ -406,7 +429,7 @@ int cloud_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t 
     P.spp = samples_per_pixel;
     P.seed_lo = (uint32_t)seed;
     P.seed_hi = (uint32_t)(seed >> 32);
-    P.n_tiles = (long long)((T.local_cols + 3) / 4) * ((height + 7) / 8);
+    P.n_tiles = local_tiles(T, width, height);
     P.density = cloud->density;
     P.frequency = cloud->frequency;
     P.step = cloud->step;

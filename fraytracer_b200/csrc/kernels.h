@@ -32,7 +32,7 @@ struct RenderParams {
 // host memory -- that receive every finished pixel at its final x-major position.  world == 1: the whole frame.
 #define FT_MAX_DST 16
 struct StripTarget {
-    int strip_width, rank, world;
+    int strip_width, rank, world;  // strip_width == 0: 4 x 8 pixel tiles dealt round-robin instead (tile t -> rank t % world)
     int local_cols;  // columns of the rank's compact strip space (strips_per_rank * strip_width; width when world == 1)
     int n_dst;
     float *dst[FT_MAX_DST];

@@ -170,12 +170,13 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
             const long long i = (long long)base + lane;
             if (i < total) {
                 if (PRIMARY) {  // 4 (x) by 8 (y) pixel tiles, like Image.render's machine
-                    const long long tile = i >> 5;
                     const int tiles_y = (P.height + 7) / 8;
+                    const bool by_tile = P.T.strip_width == 0;  // tiles dealt round-robin over the ranks instead of column strips
+                    const long long tile = by_tile ? (i >> 5) * P.T.world + P.T.rank : (i >> 5);
                     const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
                     const int xl = tx * 4 + (lane >> 3), y = ty * 8 + (lane & 7);  // xl: column of the rank's compact strip space
-                    const int x = P.T.image_column(xl);
-                    if (xl < P.T.local_cols && x < P.width && y < P.height) {
+                    const int x = by_tile ? xl : P.T.image_column(xl);
+                    if ((by_tile || xl < P.T.local_cols) && x < P.width && y < P.height) {
                         pixel = (uint32_t)((long long)x * P.height + y);
                         o = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
                         d = pixel_direction(P.cam, x, y, P.max_size);

@@ -172,8 +172,11 @@ class DistributedRenderer:
             parity = self._frame & 1
             self._frame += 1
             dst = self.dst[parity]
+        # strip_width 0: 4 x 8 pixel tiles dealt round-robin -- glass and cloud pixels cost tens of times a solid one, column
+        # strips balance them badly (measured on 8 GPUs)
         st = self.tracer.render_extension_gather_device(kind, camera, self.size, epsilon, length, dst, stream=stream,
-                                                        strip_width=self.strip_width, rank=self.rank, world=self.world, **kw)
+                                                        strip_width=kw.pop("strip_width", 0), rank=self.rank, world=self.world,
+                                                        **kw)
         if self.world > 1:
             self.dist.all_reduce(self._done, group=self.group)
             self.final = self.frames[parity]

@@ -354,7 +354,9 @@ FT_API int ft_render_spectral(ft_scene *scene, const ft_camera *camera, int32_t 
 
 /* the same for the strips `rank` of `world` owns, every finished pixel stored at its final position in each of the n_dst
  * destination framebuffers (DEVICE pointers, see ft_render_gather_device).  Synchronous on `stream` (the pipeline sizes its
- * path queues from a count read back after wave 0).                                                                    */
+ * path queues from a count read back after wave 0).  strip_width == 0 deals 4 x 8 pixel tiles round-robin instead of
+ * column strips (tile t, counted down the columns of tiles, belongs to rank t % world): the finest balance, which these
+ * workloads need -- a glass or cloud pixel costs tens of times a solid one.                                             */
 FT_API int ft_render_spectral_gather_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
                                             float epsilon, float length, int32_t n_wavelengths, int32_t max_bounces,
                                             uint64_t seed, int32_t strip_width, int32_t rank, int32_t world,

@@ -415,7 +415,7 @@ def test_extension_strip_rendering_equals_whole_frame():
         else:
             ref, st = tracer.render_cloud(w.camera, w.size, w.epsilon, w.length, CloudParams(), 5, 3)
         X, Y = w.size.X, w.size.Y
-        for world, sw in ((1, 8), (3, 8), (2, 20)):
+        for world, sw in ((1, 8), (3, 8), (2, 20), (3, 0), (1, 0)):
             dsts = [torch.full((X, Y, 3), -7.0, dtype=torch.float32, device="cuda") for _ in range(2)]
             rays = 0
             for rank in range(world):
