@@ -41,9 +41,9 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #define FT_SCAN_UNROLL 4  // candidates per round of the scan loop (2 or 4).  Measured on B200 with the lean lane state (no spills either way): 4 is 1-2 % faster on configs 1, 2 and 5
 #endif
 #ifndef FT_CHAIN_MAT
-#define FT_CHAIN_MAT 0  // 1: the chain evaluator notes its arg-min candidate, so the material lookup of a hit needs no second scan.
-                       // Bit-exact (all parity tests), but measured on B200: config 1 -2.4 %, config 2 -2.8 %, config 5 +2 % -- the
-                       // note costs a register in the scan loop; off
+#define FT_CHAIN_MAT 1  // the chain evaluator notes its arg-min candidate, so the material lookup of a hit needs no second scan.
+                       // Bit-exact (all parity tests).  Measured on B200: while the kernel spilled 170 B the note's register cost
+                       // more than the scan it saves (config 2 -2.8 %); with the lean lane state it is config 2 +9 %, config 5 +5 %
 #endif
 #ifndef FT_WITH_CONE
 #define FT_WITH_CONE 0
