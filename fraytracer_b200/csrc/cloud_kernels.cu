@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
     const V3 cam = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
     const V3 bg = V3{S.bg[0], S.bg[1], S.bg[2]};
     Acc acc{0ull, 0ull};
-    uint32_t best_dummy = 0u;  // eval_chain's arg-min note, unused here
+    uint32_t best_dummy = 0u, hit_best = 0u;  // eval_chain's arg-min note: kept at a hit, it names the material's leaf (FT_CHAIN_MAT)
     // Distance at the common origin of all camera rays, once per warp
     const float d0 = CHAIN ? eval_chain<false>(S, cam, acc, best_dummy) : eval_form<false>(S, S.root_word, cam, acc);
 
@@ -206,11 +206,13 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
         }
         // ------------------------------------------------------------------ the one distance evaluation
         if (phase > C_FETCH && event == 0) {
-            const float dist = CHAIN ? eval_chain<false>(S, p, acc, best_dummy) : eval_form<false>(S, S.root_word, p, acc);
+            uint32_t best_lo = 0u;
+            const float dist = CHAIN ? eval_chain<false>(S, p, acc, best_lo) : eval_form<false>(S, S.root_word, p, acc);
             if (phase <= C_SHADOW) {
                 steps++;
                 if (dist < eps) {
                     event = phase == C_MARCH ? 2 : 4;
+                    if (phase == C_MARCH) hit_best = best_lo;  // the hit evaluation's arg-min candidate
                 } else {
                     o = o + d * dist;
                     len = len - dist;
@@ -293,7 +295,8 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                 n_hits++;
                 phase = C_N0;
             } else if (event == 5) {
-                const int leaf_obj = material_leaf<false>(S, ho, acc);
+                const int leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, ho, hit_best)
+                                                                                  : material_leaf<false>(S, ho, acc);
                 mat = __ldg(S.objects + leaf_obj).z;
                 if (__float_as_uint(ld4(S.materials + mat).w) == (uint32_t)FT_MATERIAL_CLOUD) {
                     stream = 1u + seg * nstreams;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
     constexpr int NB = PRIMARY ? 6 : 1;
 
     Acc acc{0ull, 0ull};
-    uint32_t best_dummy = 0u;  // eval_chain's arg-min note, unused here
+    uint32_t best_dummy = 0u, hit_best = 0u;  // eval_chain's arg-min note: kept at a hit, it names the material's leaf (FT_CHAIN_MAT)
     float d0 = 0.f;
     if (PRIMARY) {  // Distance at the common origin of all primary rays, once per warp
         const V3 c = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
             else if (phase == SP_N2) p.z = q.z + h;
         }
         if (phase > SP_FETCH && event == 0) {
-            const float dist = CHAIN ? eval_chain<false>(S, p, acc, best_dummy) : eval_form<false>(S, S.root_word, p, acc);
+            uint32_t best_lo = 0u;
+            const float dist = CHAIN ? eval_chain<false>(S, p, acc, best_lo) : eval_form<false>(S, S.root_word, p, acc);
             if (phase == SP_MARCH) {
                 if (!armed) sign = dist < 0.0f ? -1.0f : 1.0f;  // the medium: inside glass the march runs on -Distance
                 const float sd = sign * dist;
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 if (armed) {
                     if (sd < eps) {
                         event = 2;
+                        hit_best = best_lo;  // the hit evaluation's arg-min candidate
                     } else {
                         o = o + d * sd;
                         len = len - sd;
@@ -300,7 +302,8 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 n_hits++;
                 phase = SP_N0;
             } else if (event == 5) {  // normal done: Material arg-min at the un-moved hit origin (SdfObject.fs:75-77)
-                const int leaf_obj = material_leaf<false>(S, ho, acc);
+                const int leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, ho, hit_best)
+                                                                                  : material_leaf<false>(S, ho, acc);
                 mat = __ldg(S.objects + leaf_obj).z;
                 const float4 m = ld4(S.materials + mat);
                 if (__float_as_uint(m.w) == (uint32_t)FT_MATERIAL_GLASS) {
