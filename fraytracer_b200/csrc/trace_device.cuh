@@ -32,7 +32,7 @@ constexpr int FLOPS_FINAL = 6;
 constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 
 #ifndef FT_FMA_PREFILTER
-#define FT_FMA_PREFILTER 0  // measured on B200: no gain (2.395 vs 2.408 ms; with the pointer walk 2.345 vs 2.275 ms). contracted sum of squares in the certain-fail filter of the second pruning test (exact value recomputed when open)
+#define FT_FMA_PREFILTER 1  // contracted sum of squares in the certain-fail filter of the second pruning test (the exact value is recomputed when the outcome is open).  Measured on B200: nothing while the kernel spilled (2.395 vs 2.408 ms); -2.6 % on config 2 with the lean lane state
 #endif
 #ifndef FT_SCAN_PTR
 #define FT_SCAN_PTR 1  // the candidate scan walks a pointer (immediate offsets, one 64-bit add per two records) instead of re-deriving the address from an index

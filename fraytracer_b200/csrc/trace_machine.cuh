@@ -17,7 +17,8 @@
 namespace FT_NS {
 
 #ifndef FT_MINB
-#define FT_MINB 8  // <= 64 registers: 32 resident warps per SM (measured faster than 96 regs without spills)
+#define FT_MINB 9  // <= 56 registers: 36 resident warps per SM.  Measured (config 2): 6 CTAs/SM (80 registers, no spill) 2.25 ms,
+                   // 8 (64) 1.88 ms, 9 (56) 1.83 ms
 #endif
 constexpr int MB = 128;             // threads per CTA
 #ifndef FT_TILE_W
