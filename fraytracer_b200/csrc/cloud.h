@@ -16,8 +16,9 @@ struct CloudParams {
     const int *perm;          // device, 256
     const double *gradients;  // device, 768
     StripTarget T;            // the rank's strips and the destination framebuffers
+    float *partials;          // [local tile][lane][FT_CLOUD_SAMPLE_GROUPS][3] group sums, combined by cloud_resolve_kernel
     unsigned long long *work_counter;
     unsigned long long *stats;
 };
 
-cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, int sm_count, cudaStream_t stream);
+cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, int sm_count, cudaStream_t stream);  // trace + resolve

@@ -94,6 +94,36 @@ __device__ __forceinline__ void cloud_rnd(const CloudParams &P, uint32_t pixel, 
     u1 = __uint2float_rn(c[1]) * 2.3283064365386963e-10f;
 }
 
+// pixel of lane `lane` in local tile `tile`; false when it lies outside the frame (padding)
+__device__ __forceinline__ bool cloud_tile_pixel(const CloudParams &P, int tiles_y, unsigned long long tile, int lane, int &x, int &y) {
+    if (P.T.strip_width == 0) {  // tiles dealt round-robin over the ranks: the finest balance (cloud pixels cost ~50x)
+        const unsigned long long gt = tile * (unsigned)P.T.world + (unsigned)P.T.rank;
+        const int tx = (int)(gt / tiles_y), ty = (int)(gt - (unsigned long long)tx * tiles_y);
+        x = tx * 4 + (lane >> 3);
+        y = ty * 8 + (lane & 7);
+        return x < P.width && y < P.height;
+    }
+    const int tx = (int)(tile / tiles_y), ty = (int)(tile - (unsigned long long)tx * tiles_y);
+    const int xl = tx * 4 + (lane >> 3);  // column of the rank's compact strip space
+    x = P.T.image_column(xl);
+    y = ty * 8 + (lane & 7);
+    return xl < P.T.local_cols && x < P.width && y < P.height;
+}
+
+// pixel = (((P0 + P1) + P2) + P3) / spp, the group sums in group order (FT_CLOUD_SAMPLE_GROUPS), stored to every destination
+__global__ void __launch_bounds__(CB) cloud_resolve_kernel(const __grid_constant__ CloudParams P) {
+    const long long i = (long long)blockIdx.x * CB + threadIdx.x;
+    if (i >= P.n_tiles * 32) return;
+    int x, y;
+    if (!cloud_tile_pixel(P, (P.height + 7) / 8, (unsigned long long)(i >> 5), (int)(i & 31), x, y)) return;
+    const float *pp = P.partials + i * FT_CLOUD_SAMPLE_GROUPS * 3;
+    V3 t = V3{pp[0], pp[1], pp[2]};
+#pragma unroll
+    for (int g = 1; g < FT_CLOUD_SAMPLE_GROUPS; g++) t = t + V3{pp[3 * g], pp[3 * g + 1], pp[3 * g + 2]};
+    const float inv = (float)P.spp;
+    P.T.store((unsigned long long)x * P.height + y, t.x / inv, t.y / inv, t.z / inv);
+}
+
 template <bool CHAIN>
 __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_constant__ DevScene S, const __grid_constant__ CloudParams P) {
     __shared__ NoiseTab tab;
@@ -114,7 +144,8 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
 
     int phase = C_FETCH;
     bool have_tile = false, active = false, cloud_mode = false;
-    int x = 0, y = 0, s = 0, spp_eff = 0;
+    int x = 0, y = 0, s = 0, spp_eff = 0, item_group = 0;  // spp_eff: one past the last sample of this work item
+    long long item_tile = 0;
     uint32_t pixel = 0, seg = 0, stream = 0, k = 0;
     V3 sum{0, 0, 0}, o{0, 0, 0}, d{0, 0, 0}, cd{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, ho{0, 0, 0}, ps{0, 0, 0}, lc{0, 0, 0}, cint{0, 0, 0};
     float len = 0.f, hlen = 0.f, lcos = 0.f, xi0 = 0.f, ucur = 0.f, maxdist = 0.f;
@@ -125,30 +156,26 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
     for (;;) {
         // ------------------------------------------------------------------ tile finished: write it, take the next one
         if (__all_sync(FULL, phase == C_FETCH && s >= spp_eff)) {
-            if (have_tile && active) {
-                const float inv = (float)P.spp;
-                P.T.store(pixel, sum.x / inv, sum.y / inv, sum.z / inv);
+            if (have_tile && active) {  // this work item's group sum; cloud_resolve_kernel adds the groups in order
+                float *pp = P.partials + ((item_tile * 32 + lane) * FT_CLOUD_SAMPLE_GROUPS + item_group) * 3;
+                pp[0] = sum.x;
+                pp[1] = sum.y;
+                pp[2] = sum.z;
             }
-            unsigned long long tile = 0;
-            if (lane == 0) tile = atomicAdd(P.work_counter, 1ull);
-            tile = __shfl_sync(FULL, tile, 0);
-            if ((long long)tile >= P.n_tiles) break;
-            if (P.T.strip_width == 0) {  // tiles dealt round-robin over the ranks: the finest balance (cloud pixels cost ~50x)
-                const unsigned long long gt = tile * (unsigned)P.T.world + (unsigned)P.T.rank;
-                const int tx = (int)(gt / tiles_y), ty = (int)(gt - (unsigned long long)tx * tiles_y);
-                x = tx * 4 + (lane >> 3);
-                y = ty * 8 + (lane & 7);
-                active = x < P.width && y < P.height;
-            } else {
-                const int tx = (int)(tile / tiles_y), ty = (int)(tile - (unsigned long long)tx * tiles_y);
-                const int xl = tx * 4 + (lane >> 3);  // column of the rank's compact strip space
-                x = P.T.image_column(xl);
-                y = ty * 8 + (lane & 7);
-                active = xl < P.T.local_cols && x < P.width && y < P.height;
-            }
+            // work item = (tile, sample group): the groups of one tile are consecutive items, so they run side by side on
+            // different warps instead of one warp running all samples of its 32 pixels
+            unsigned long long item = 0;
+            if (lane == 0) item = atomicAdd(P.work_counter, 1ull);
+            item = __shfl_sync(FULL, item, 0);
+            if ((long long)item >= P.n_tiles * FT_CLOUD_SAMPLE_GROUPS) break;
+            const unsigned long long tile = item / FT_CLOUD_SAMPLE_GROUPS;
+            item_tile = (long long)tile;
+            item_group = (int)(item - tile * FT_CLOUD_SAMPLE_GROUPS);
+            active = cloud_tile_pixel(P, tiles_y, tile, lane, x, y);
             pixel = (uint32_t)((long long)x * P.height + y);
-            s = 0;
-            spp_eff = active ? P.spp : 0;
+            s = (int)(((long long)item_group * P.spp) / FT_CLOUD_SAMPLE_GROUPS);
+            spp_eff = active ? (int)(((long long)(item_group + 1) * P.spp) / FT_CLOUD_SAMPLE_GROUPS) : 0;
+            if (!active) s = 0;
             sum = V3{0.f, 0.f, 0.f};
             have_tile = true;
             continue;
@@ -402,9 +429,11 @@ cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, int sm_count, 
                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cloud_kernel<false>, CB, 0);
     if (e != cudaSuccess) return e;
     long long grid = (long long)(per_sm < 1 ? 1 : per_sm) * sm_count;
-    const long long need = (P.n_tiles + CB / 32 - 1) / (CB / 32);
+    const long long need = (P.n_tiles * FT_CLOUD_SAMPLE_GROUPS + CB / 32 - 1) / (CB / 32);
     if (grid > need) grid = need;
     if (S.chain_valid) cloud_kernel<true><<<(unsigned)grid, CB, 0, stream>>>(S, P);
     else cloud_kernel<false><<<(unsigned)grid, CB, 0, stream>>>(S, P);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    cloud_resolve_kernel<<<(unsigned)((P.n_tiles * 32 + CB - 1) / CB), CB, 0, stream>>>(P);
     return cudaGetLastError();
 }

@@ -430,6 +430,8 @@ int cloud_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t 
     P.seed_lo = (uint32_t)seed;
     P.seed_hi = (uint32_t)(seed >> 32);
     P.n_tiles = local_tiles(T, width, height);
+    CU(scene->reserve2((size_t)std::max<long long>(P.n_tiles, 1) * 32 * FT_CLOUD_SAMPLE_GROUPS * 3 * sizeof(float)));
+    P.partials = (float *)scene->d_scratch2;
     P.density = cloud->density;
     P.frequency = cloud->frequency;
     P.step = cloud->step;
@@ -457,7 +459,7 @@ int cloud_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t 
         for (int k = 0; k < FT_STAT_SLOTS; k++) scattered += scene->h_stats[(size_t)k * FT_STAT_STRIDE + FT_STAT_PATHS];
         stats->primary_rays = owned_pixels(T, width, height) * samples_per_pixel;
         stats->reserved = (int32_t)std::min<unsigned long long>(scattered, 0x7fffffffull);
-        stats->launches = 1;
+        stats->launches = 2;  // trace kernel + resolve kernel
         cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
         cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
     }

@@ -369,7 +369,8 @@ FT_API int ft_render_spectral_gather_device(ft_scene *scene, const ft_camera *ca
  * Noise.permutationTable, Noise.fs:7-23) and `gradients` (256 x 3 doubles, Noise.gradientTable, Noise.fs:72-76).
  * spp stochastic samples per pixel (sub-pixel jitter, fixed-step tracking with Bernoulli collisions, single
  * scattering with tracked visibility), every draw from Philox4x32-10(seed; pixel, sample, step, stream).
- * out_rgb is a HOST FColor[X,Y] holding the mean of the samples (summed in sample order: deterministic).
+ * out_rgb is a HOST FColor[X,Y] holding the mean of the samples (summed in a fixed order, FT_CLOUD_SAMPLE_GROUPS below:
+ * deterministic).
  * stats->shadow_rays counts every secondary march (shadow rays, continuation segments, light tracks),
  * stats->march_steps the tracking steps, stats->reserved the samples that scattered inside a cloud.            */
 typedef struct ft_cloud_params {
@@ -384,6 +385,10 @@ typedef struct ft_cloud_params {
 } ft_cloud_params;
 #define FT_CLOUD_MAX_SEGMENTS 8     /* camera-ray segments per sample (a segment ends where the ray leaves a cloud) */
 #define FT_CLOUD_MAX_TRACK_STEPS 4096
+/* a pixel's samples are summed in FT_CLOUD_SAMPLE_GROUPS consecutive groups (group g = samples [g spp / G, (g+1) spp / G)),
+ * each in sample order, and the group sums are added in group order: (((P0 + P1) + P2) + P3) / spp -- so that the groups of
+ * one tile can run on different warps (a tile full of cloud pixels is otherwise tens of milliseconds of serial work)       */
+#define FT_CLOUD_SAMPLE_GROUPS 4
 FT_API int ft_render_cloud(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height, float epsilon,
                            float length, const ft_cloud_params *cloud, int32_t samples_per_pixel, uint64_t seed,
                            float *out_rgb, ft_render_stats *stats);

@@ -1633,7 +1633,12 @@ static void *cloud_worker(void *arg) {
         int64_t x = j->x0 + i * j->xstride;
         for (int y = 0; y < j->H; y++) {
             v3 sum = V(0.0f, 0.0f, 0.0f);
-            for (int k = 0; k < j->spp; k++) sum = vadd(sum, cloud_sample(j, &st, (int)x, y, (uint32_t)k));
+            for (int g = 0; g < FT_CLOUD_SAMPLE_GROUPS; g++) { /* group sums in sample order, added in group order */
+                int s0 = (int)(((int64_t)g * j->spp) / FT_CLOUD_SAMPLE_GROUPS), s1 = (int)(((int64_t)(g + 1) * j->spp) / FT_CLOUD_SAMPLE_GROUPS);
+                v3 part = V(0.0f, 0.0f, 0.0f);
+                for (int k = s0; k < s1; k++) part = vadd(part, cloud_sample(j, &st, (int)x, y, (uint32_t)k));
+                sum = g == 0 ? part : vadd(sum, part);
+            }
             float *o = j->out + 3 * ((int64_t)x * j->H + y);
             o[0] = sum.x / (float)j->spp; o[1] = sum.y / (float)j->spp; o[2] = sum.z / (float)j->spp;
         }
