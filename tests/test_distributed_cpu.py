@@ -46,3 +46,26 @@ def test_two_rank_strip_gather_equals_single_rank(tmp_path, X, Y, sw):
     port = 29500 + (os.getpid() + X) % 2000
     mp.spawn(_worker, args=(2, port, X, Y, sw, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def test_strip_partition_covers_every_column_exactly_once():
+    """host logic of the multi-GPU partition: for any width / world / strip width the ranks' strips tile the frame"""
+    from fraytracer_b200.distributed import auto_strip_width, owned_columns, strip_layout
+
+    for width in (1, 7, 8, 333, 1920, 2712, 5432, 7680):
+        for world in (1, 2, 3, 4, 8):
+            for sw in (4, 8, 20, 32, auto_strip_width(width, world)):
+                seen = [0] * width
+                for rank in range(world):
+                    spr, floats = strip_layout(width, 10, sw, world)
+                    cols = owned_columns(width, sw, rank, world)
+                    assert len(cols) <= spr
+                    for local, x0, n in cols:
+                        assert local % sw == 0 and 0 < n <= sw
+                        for x in range(x0, x0 + n):
+                            seen[x] += 1
+                    assert floats == (width if world == 1 else spr * sw) * 10 * 3
+                assert seen == [1] * width, (width, world, sw)
+    for width, world in ((7680, 8), (5432, 8), (2712, 2), (640, 8), (100, 16)):
+        sw = auto_strip_width(width, world)
+        assert sw % 4 == 0 and 8 <= sw <= 32
