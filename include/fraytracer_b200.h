@@ -267,8 +267,11 @@ FT_API int ft_scene_grid_read(const ft_scene *scene, int32_t grid, float *cell_c
  * (Image.fs:26-35).  out_rgb is the reference's FColor[X,Y]: element (x,y) at
  * (x*height + y), 3 floats each.  out_leaf (optional) receives the index of
  * the leaf SdfObject whose material coloured the pixel (the arg-min of
- * SdfObject.fs:27-46), -1 for background.  Both are HOST pointers; page-lock
- * them with ft_host_register for full copy bandwidth.                       */
+ * SdfObject.fs:27-46), -1 for background.  Both are HOST pointers.  When they
+ * are page-locked and device-mapped (ft_host_register on the pinned FColor[,],
+ * or ft_host_alloc) the kernel stores every finished pixel straight into them
+ * -- one launch, no staging buffer, no device->host copy; otherwise the frame
+ * is rendered in two column bands whose copies overlap the rendering.        */
 FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
                      float epsilon, float length, uint32_t flags, float *out_rgb, int32_t *out_leaf,
                      ft_render_stats *stats);
