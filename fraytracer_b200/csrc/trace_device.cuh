@@ -37,6 +37,9 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #ifndef FT_SCAN_PTR
 #define FT_SCAN_PTR 1  // the candidate scan walks a pointer (immediate offsets, one 64-bit add per two records) instead of re-deriving the address from an index
 #endif
+#ifndef FT_SCAN_PAIR
+#define FT_SCAN_PAIR 0  // experiment (see eval_chain): not measured yet, off
+#endif
 #ifndef FT_SCAN_UNROLL
 #define FT_SCAN_UNROLL 4  // candidates per round of the scan loop (2 or 4).  Measured on B200 with the lean lane state (no spills either way): 4 is 1-2 % faster on configs 1, 2 and 5
 #endif
@@ -216,6 +219,14 @@ __device__ __forceinline__ bool bound_test(float m, float4 b0, V3 p, float &bd) 
 #endif
     bd = sqrtf(s) - b0.w;
     return m > bd;
+}
+
+// the certain-fail half of bound_test alone (see above): true only when the reference's second pruning test is certainly false
+__device__ __forceinline__ bool bound_certain_fail(float m, float4 b0, V3 p) {
+    const V3 dl = xyz(b0) - p;
+    const float u = fmaxf(m + b0.w, 1e-15f);
+    const float sf = __fmaf_rn(dl.z, dl.z, __fmaf_rn(dl.y, dl.y, dl.x * dl.x));
+    return sf > (u * u) * 1.000244140625f;
 }
 
 // ---- union candidate scan (SdfForm.fs:27-33) from entry i with running minimum m.
@@ -446,7 +457,27 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, u
         }                                                                     \
     }
         Entry e0 = FT_LD_ENTRY(0);
-#if FT_SCAN_UNROLL == 4
+#if FT_SCAN_PAIR
+        // EXPERIMENT, not measured yet (DESIGN.md "What comes next"): two candidates per branch.  When both pass the
+        // LowerBound test and both certainly fail the second pruning test -- the common outcome -- one merged predicate
+        // replaces four branches; every other case falls back to the sequential code below on the same two records.
+        Entry e1 = FT_LD_ENTRY(1);
+        for (;;) {
+            if (!((m > e0.lb() - dtc) & bound_certain_fail(m, e0.bound(), p) & (m > e1.lb() - dtc) & bound_certain_fail(m, e1.bound(), p))) {
+                FT_CHAIN_ONE(e0, 0)
+                FT_CHAIN_ONE(e1, 1)
+            } else {
+                add_flops<COUNT>(acc, 2 * (FLOPS_LB_TEST + FLOPS_BOUND_TEST));
+            }
+            e0 = FT_LD_ENTRY(2);
+            e1 = FT_LD_ENTRY(3);
+#if FT_SCAN_PTR
+            ep += 4;
+#else
+            i += 2;
+#endif
+        }
+#elif FT_SCAN_UNROLL == 4
         Entry e1 = FT_LD_ENTRY(1);
         for (;;) {
             FT_CHAIN_ONE(e0, 0)
