@@ -103,6 +103,11 @@ class ft_grid_info(C.Structure):
                 ("n_entries", C.c_int64)]
 
 
+class ft_subgrid_info(C.Structure):
+    _fields_ = [("resolution", C.c_int32), ("reserved", C.c_int32), ("n_subcells", C.c_int64), ("n_entries", C.c_int64),
+                ("device_bytes", C.c_int64), ("threshold", C.c_float), ("build_ms", C.c_float)]
+
+
 class ft_cloud_params(C.Structure):
     _fields_ = [("density", C.c_float), ("frequency", C.c_float), ("step", C.c_float), ("fade", C.c_float),
                 ("bias", C.c_float), ("gain", C.c_float), ("perm", C.POINTER(C.c_int32)),
@@ -124,7 +129,7 @@ class ft_render_stats(C.Structure):
 EXPORTS = [
     "ft_abi_version", "ft_last_error", "ft_device_count", "ft_lens_create", "ft_camera_look_at",
     "ft_scene_create", "ft_scene_destroy", "ft_scene_info_get", "ft_scene_set_step_cap",
-    "ft_scene_grid_count", "ft_scene_grid_info", "ft_scene_grid_read",
+    "ft_scene_grid_count", "ft_scene_grid_info", "ft_scene_grid_read", "ft_scene_subgrid_info", "ft_scene_set_debug",
     "ft_render", "ft_render_device", "ft_render_strips_device", "ft_render_gather_device",
     "ft_device_alloc", "ft_device_free", "ft_ipc_export", "ft_ipc_import", "ft_ipc_close", "ft_strip_layout", "ft_deinterleave_device",
     "ft_deinterleave_strips_device",
@@ -167,6 +172,8 @@ def load_library(path: str | None = None):
         "ft_scene_destroy": (C.c_int, [vp]),
         "ft_scene_info_get": (C.c_int, [vp, P(ft_scene_info)]),
         "ft_scene_set_step_cap": (C.c_int, [vp, i32]),
+        "ft_scene_subgrid_info": (C.c_int, [vp, P(ft_subgrid_info)]),
+        "ft_scene_set_debug": (C.c_int, [vp, i32]),
         "ft_scene_grid_count": (C.c_int, [vp, P(i32)]),
         "ft_scene_grid_info": (C.c_int, [vp, i32, P(ft_grid_info)]),
         "ft_scene_grid_read": (C.c_int, [vp, i32, vp, vp, vp, vp]),

@@ -461,6 +461,16 @@ class SceneTracer:
         A.check(self.lib.ft_scene_info_get(self.handle, C.byref(out)))
         return {n: getattr(out, n) for n, _ in out._fields_}
 
+    def subgrid_info(self) -> dict:
+        """the nearest-candidate sub-grid built over the chain union's spatial lookup (resolution 0: none)"""
+        out = A.ft_subgrid_info()
+        A.check(self.lib.ft_scene_subgrid_info(self.handle, C.byref(out)))
+        return {n: getattr(out, n) for n, _ in out._fields_ if n != "reserved"}
+
+    def set_debug(self, sub_debug: int):
+        """test hook: bit 0 = distrust every sub-grid certificate (every evaluation also runs the reference's scan)"""
+        A.check(self.lib.ft_scene_set_debug(self.handle, int(sub_debug)))
+
     def set_step_cap(self, max_steps: int):
         A.check(self.lib.ft_scene_set_step_cap(self.handle, int(max_steps)))
 

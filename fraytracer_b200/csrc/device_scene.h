@@ -101,6 +101,20 @@ struct DevScene {
     // obj_links[chain_mat_links + child position] is the leaf object.
     int32_t chain_mat_valid;
     int32_t chain_mat_links;
+    // Nearest-candidate sub-grid of U (subgrid_build.cu, DESIGN.md "sub-grid"): every cell of U's spatial lookup is cut into
+    // sub_res^3 sub-cells; sub_hdr[cell * sub_res^3 + (sx * sub_res + sy) * sub_res + sz] = (first << 8) | count addresses a
+    // short list in sub_idx[] of ABSOLUTE indices into entries[] -- those candidates of the cell's own list that can be the
+    // nearest one for some position inside the sub-cell (all others are provably farther than the nearest by a margin),
+    // nearest first.  Positions inside the lookup's box evaluate only these (eval_chain); the result is certified equal to the
+    // reference's sequential scan, otherwise the scan itself runs.  sub_valid == 0: no sub-grid (the scan always runs).
+    const uint32_t *sub_hdr;
+    const uint32_t *sub_idx;
+    int32_t sub_valid;
+    int32_t sub_res;        // 1, 2, 4 or 8
+    float sub_res_f;        // (float)sub_res
+    float sub_count_f[3];   // (float)countX, countY, countZ of U's lookup: 0 <= c < count is "inside the box"
+    int32_t sub_debug;      // bit 0: distrust every certificate (every evaluation also runs the sequential scan; tests)
+                            // bit 1: COUNT kernels compare the certified result with the scan and count mismatches
 };
 enum : uint32_t {
     FT_OP_INTERSECT = 1,  // if v < dist(C,p)+R then v = Max(v, D(p))      SdfForm.fs:62-63

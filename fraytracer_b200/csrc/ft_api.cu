@@ -14,6 +14,7 @@
 #include "scene_compiler.h"
 #include "spectral.h"
 #include "cloud.h"
+#include "subgrid.h"
 
 namespace {
 
@@ -98,6 +99,7 @@ struct ft_scene {
     void *d_scratch2 = nullptr;
     size_t scratch2_bytes = 0;
     unsigned *d_spec_counts = nullptr, *h_spec_counts = nullptr;
+    SubGrid sub;  // nearest-candidate sub-grid of a chain scene's spatial lookup (subgrid_build.cu)
     std::mutex mu;
 
     cudaError_t reserve(size_t bytes) {
@@ -123,6 +125,8 @@ struct ft_scene {
                               dev.objects, dev.obj_links, dev.materials, dev.lights};
         for (const void *p : ptrs)
             if (p) cudaFree(const_cast<void *>(p));
+        if (sub.hdr) cudaFree(sub.hdr);
+        if (sub.idx) cudaFree(sub.idx);
         if (d_stats) cudaFree(d_stats);
         if (d_counters) cudaFree(d_counters);
         if (h_stats) cudaFreeHost(h_stats);
@@ -597,6 +601,42 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
         s->dev.chain_g3 = h.nodes[(size_t)h.chain_union + 3];
     }
     if (getenv("FT_NO_CHAIN")) s->dev.chain_valid = 0;  // experiments / tests of the generic interpreter
+    // nearest-candidate sub-grid of the chain union's lookup (device_scene.h): built on the device from the uploaded scene
+    s->dev.sub_valid = 0;
+    if (s->dev.chain_valid && !getenv("FT_NO_SUBGRID")) {
+        uint32_t cell_base;
+        std::memcpy(&cell_base, &s->dev.chain_g1.w, sizeof(cell_base));
+        for (const ftc::GridHost &g : h.grids) {
+            if ((uint32_t)g.cell_base != cell_base) continue;
+            SubGridJob job;
+            for (int k = 0; k < 3; k++) {
+                job.amin[k] = g.aabb_min[k];
+                job.cell[k] = g.cell_size[k];
+                job.count[k] = g.count[k];
+            }
+            job.cell_base = cell_base;
+            job.max_res = 8;
+            job.max_subcells = 1ll << 22;
+            if (const char *r = getenv("FT_SUBGRID_RES")) job.max_res = std::max(1, std::min(8, atoi(r)));  // experiments
+            std::string sub_err;
+            if ((e = build_subgrid(s->dev, job, &s->sub, &sub_err)) != cudaSuccess) {
+                g_last_error = sub_err;
+                return bail(e, "sub-grid build");
+            }
+            if (s->sub.hdr) {
+                s->dev.sub_hdr = s->sub.hdr;
+                s->dev.sub_idx = s->sub.idx;
+                s->dev.sub_res = s->sub.res;
+                s->dev.sub_res_f = (float)s->sub.res;
+                for (int k = 0; k < 3; k++) s->dev.sub_count_f[k] = (float)g.count[k];
+                s->dev.sub_valid = 1;
+                s->device_bytes += s->sub.bytes;
+            }
+            break;
+        }
+    }
+    s->dev.sub_debug = 0;
+    if (const char *d = getenv("FT_SUB_DEBUG")) s->dev.sub_debug = atoi(d);  // tests: 1 = distrust every certificate
     if (getenv("FT_NO_ESCAPE")) s->dev.esc_valid = 0;  // experiments only
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
@@ -638,6 +678,25 @@ FT_API int ft_scene_info_get(const ft_scene *scene, ft_scene_info *out) {
     out->grids_built_on_gpu = h.grids_built_on_gpu;
     out->device = scene->device;
     out->sm_count = scene->sm_count;
+    return FT_OK;
+}
+
+FT_API int ft_scene_subgrid_info(const ft_scene *scene, ft_subgrid_info *out) {
+    if (!scene || !out) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    out->resolution = scene->sub.hdr ? scene->sub.res : 0;
+    out->n_subcells = scene->sub.n_subcells;
+    out->n_entries = scene->sub.n_entries;
+    out->device_bytes = scene->sub.bytes;
+    out->threshold = scene->sub.threshold;
+    out->build_ms = scene->sub.build_ms;
+    return FT_OK;
+}
+
+FT_API int ft_scene_set_debug(ft_scene *scene, int32_t sub_debug) {
+    if (!scene) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    scene->dev.sub_debug = sub_debug;
     return FT_OK;
 }
 

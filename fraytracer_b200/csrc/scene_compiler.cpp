@@ -788,7 +788,10 @@ class Compiler {
             float4 b = f4(0, 0, 0, 0);
             if (child >= 0) b = o.nodes[FT_WORD_OFF(en.y)];
             o.fat_entries.push_back(f4(as_float(en.x), as_float(child >= 0 ? en.y : 0u), b.x, b.y));
-            o.fat_entries.push_back(f4(b.z, b.w, as_float((uint32_t)child), 0.f));
+            // .w: the radius inflated by (1 + 2^-12), rounded up -- the certain-fail filter of the sub-grid path forms
+            // (m + R)(1 + 2^-12) with one fma from it (trace_device.cuh certain_fail_up)
+            const float rup = std::nextafter(b.w * 1.000244140625f, std::numeric_limits<float>::infinity());
+            o.fat_entries.push_back(f4(b.z, b.w, as_float((uint32_t)child), rup));
         }
         for (int k = 0; k < 2; k++) {
             o.fat_entries.push_back(f4(std::numeric_limits<float>::infinity(), 0.f, 0.f, 0.f));

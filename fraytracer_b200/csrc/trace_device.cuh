@@ -37,9 +37,6 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #ifndef FT_SCAN_PTR
 #define FT_SCAN_PTR 1  // the candidate scan walks a pointer (immediate offsets, one 64-bit add per two records) instead of re-deriving the address from an index
 #endif
-#ifndef FT_SCAN_PAIR
-#define FT_SCAN_PAIR 0  // experiment (see eval_chain): not measured yet, off
-#endif
 #ifndef FT_SCAN_UNROLL
 #define FT_SCAN_UNROLL 4  // candidates per round of the scan loop (2 or 4).  Measured on B200 with the lean lane state (no spills either way): 4 is 1-2 % faster on configs 1, 2 and 5
 #endif
@@ -221,14 +218,6 @@ __device__ __forceinline__ bool bound_test(float m, float4 b0, V3 p, float &bd) 
     return m > bd;
 }
 
-// the certain-fail half of bound_test alone (see above): true only when the reference's second pruning test is certainly false
-__device__ __forceinline__ bool bound_certain_fail(float m, float4 b0, V3 p) {
-    const V3 dl = xyz(b0) - p;
-    const float u = fmaxf(m + b0.w, 1e-15f);
-    const float sf = __fmaf_rn(dl.z, dl.z, __fmaf_rn(dl.y, dl.y, dl.x * dl.x));
-    return sf > (u * u) * 1.000244140625f;
-}
-
 // ---- union candidate scan (SdfForm.fs:27-33) from entry i with running minimum m.
 // Returns true when the list is exhausted (early exit on the sorted LowerBound, see device_scene.h);
 // false when entry i is a child whose Distance must be evaluated by the caller (anything but a sphere:
@@ -404,13 +393,128 @@ __device__ __forceinline__ float eval_form(const DevScene &S, uint32_t root, V3 
 // "scan until a child must be evaluated, converge, evaluate": lanes share the primitive-evaluation code.
 // `best_lo` receives the low 32 address bits of the candidate record that set the running minimum last (the arg-min
 // of SdfObject.fs:27-46, see DevScene::chain_mat_valid); callers that do not need it pass a dummy and the stores vanish.
+// ---- U(p) through the nearest-candidate sub-grid (device_scene.h, subgrid_build.cu; DESIGN.md "sub-grid").
+//
+// The reference's value (SdfForm.fs:22-34) is  m_seq = min over E_ref of D_i(p),  E_ref the candidates its sequential scan
+// evaluates: the scan ends at the first K with m <= fl(lb_K - dtc) (sorted list, m never grows) and skips i < K with
+// m <= bd_i = fl(|C_i - p| - R_i).  Its arg-min (the material leaf, SdfObject.fs:27-46) is the FIRST index attaining m_seq.
+//
+// Claim: let W be any subset of the cell's list that contains that arg-min i*, M = min over W of D_i(p) and a the smallest
+// index in W attaining M.  If  (1) M >= fl(lb_a - dtc)  and  (2) M >= bd_a  (trivial for a sphere: D = bd),  then M == m_seq
+// bit for bit and a == i*.   Proof: i* in W gives M <= m_seq.  If a < K: either the scan evaluates a (then D_a >= m_seq), or it
+// skips a because m_{a-1} <= bd_a <= D_a (by (2)), and m_{a-1} >= m_seq.  If a >= K: D_a >= fl(lb_a - dtc) (by (1)) >=
+// fl(lb_K - dtc) >= m_{K-1} = m_seq.  So M == m_seq, and a == i* because an index below i* attaining m_seq would either be
+// evaluated by the scan (contradicting "first") or be skipped with m_{a-1} <= D_a = m_seq, i.e. the minimum was already
+// attained even earlier.  No order of evaluation is involved: W may be visited nearest-first.
+//
+// W is the sub-cell's list: subgrid_build.cu drops candidate i only when D_i > D_j + margin for some j of the same cell list
+// everywhere in the sub-cell, and m_seq(p) <= D_j(p) + (a few ulps) for EVERY j of the list (evaluated: the scan takes the
+// minimum; skipped: m <= bd_j <= D_j; beyond K: m_seq <= fl(lb_j - dtc) <= D_j up to rounding), so a dropped candidate cannot
+// be i*.  Certificates (1) and (2) are checked on the final arg-min only, first by a square-root-free sufficient test, then
+// exactly; if one fails -- only possible within rounding of a tie AND of a degenerate configuration -- the scan itself runs.
+//
+// certain_fail_up: true only if  M > bd  is certainly false, i.e. D_i >= bd_i - ulps > M: the candidate cannot lower M (nor tie).
+// `rup` >= R (1 + 2^-12) is stored in the record.  u = fl(M (1 + 2^-12) + rup) >= (M + R)(1 + 2^-12)(1 - 2^-24) whenever
+// M + R >= 0, and sf > fl(u u + 1e-30) then gives sqrt(s) > (M + R)(1 + 2^-13): q = fl(sqrt(fl(s))) > M + R, so fl(q - R) >= M.
+// (1e-30 keeps the comparison meaningful when u u underflows; M + R < 0 makes the reference's test false for every s;
+// M = +inf gives u = +inf and the filter never fires.)  sf is the contracted sum of squares, within 2^-21 of the reference's.
+__device__ __forceinline__ bool certain_fail_up(float M, float4 b0, float rup, V3 p) {
+    const V3 dl = xyz(b0) - p;
+    const float sf = __fmaf_rn(dl.z, dl.z, __fmaf_rn(dl.y, dl.y, dl.x * dl.x));
+    const float u = __fmaf_rn(M, 1.000244140625f, rup);
+    return sf > __fmaf_rn(u, u, 1e-30f);
+}
+
+template <bool COUNT>
+__device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, V3 c, uint32_t ci, int ix, int iy, int iz, float &m_out,
+                                           uint32_t &best_out, Acc &acc) {
+    // sub-cell of p inside its cell: fractional part of the reference's own cell coordinate (exact: Sterbenz), times a power of two
+    const float fx = c.x - (float)ix, fy = c.y - (float)iy, fz = c.z - (float)iz;
+    const int R = S.sub_res;
+    const int sx = (int)(fx * S.sub_res_f), sy = (int)(fy * S.sub_res_f), sz = (int)(fz * S.sub_res_f);
+    const uint32_t cell_local = ci - __float_as_uint(S.chain_g1.w);
+    const uint32_t hdr = __ldg(S.sub_hdr + ((size_t)cell_local * (uint32_t)(R * R * R) + (uint32_t)((sx * R + sy) * R + sz)));
+    const uint32_t n = hdr & 255u;
+    if (n == 0u) return false;  // no list for this sub-cell (too long to encode): the scan runs
+    add_flops<COUNT>(acc, 9);
+    const uint32_t *lp = S.sub_idx + (hdr >> 8);
+    float M = __int_as_float(0x7f800000);
+    uint32_t best = 0xffffffffu;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t idx = __ldg(lp + k);
+        const Entry e = ld_entry(S, idx);
+        add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
+        if (certain_fail_up(M, e.bound(), e.b.w, p)) continue;
+        float d;
+        if (FT_WORD_KIND(e.word()) == FT_K_SPHERE) {
+            d = distance(xyz(e.bound()), p) - e.b.y;  // SdfForm.fs:127-129, the reference's operation order
+        } else {
+            d = prim_distance<COUNT>(S, e.word(), e.bound(), p, acc);
+        }
+        add_flops<COUNT>(acc, FLOPS_MINMAX);
+        if (d < M || (d == M && idx < best)) {
+            M = d;
+            best = idx;
+        }
+    }
+    if (best == 0xffffffffu) return false;  // nothing comparable (NaN positions): the scan decides
+    // certificates on the arg-min
+    const Entry eb = ld_entry(S, best);
+    const float4 cell = ld4(S.cells + ci);
+    add_flops<COUNT>(acc, 12);
+    const float x = eb.lb() - M;
+    bool ok = true;
+    if (x > 0.0f) {  // (1)  M >= fl(lb - dtc): certainly true when |p - centre|^2 > x^2 (1 + 2^-10); else compare exactly
+        const V3 dc = p - xyz(cell);
+        const float dtc2 = __fmaf_rn(dc.z, dc.z, __fmaf_rn(dc.y, dc.y, dc.x * dc.x));
+        if (!(dtc2 > (x * x) * 1.0009765625f)) ok = M >= eb.lb() - distance(p, xyz(cell));
+    }
+    if (FT_WORD_KIND(eb.word()) != FT_K_SPHERE) {  // (2)  M >= bd: certainly true when s < (M + R)^2 (1 - 2^-16), M + R > 0
+        const float4 b0 = eb.bound();
+        const V3 dl = xyz(b0) - p;
+        const float sf = __fmaf_rn(dl.z, dl.z, __fmaf_rn(dl.y, dl.y, dl.x * dl.x));
+        const float y = M + b0.w;
+        if (!(y > 0.0f && sf < (y * y) * 0.9999847412109375f)) ok = ok && (M >= sqrtf(dot(dl, dl)) - b0.w);
+    }
+    if (!ok || (S.sub_debug & 1)) return false;
+    m_out = M;
+    best_out = best;
+    return true;
+}
+
 template <bool COUNT>
 __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, uint32_t &best_lo) {
     uint32_t i;
     float dtc;
     add_flops<COUNT>(acc, FLOPS_CELL_LOOKUP);
-    grid_cell_from(S, S.chain_g1, S.chain_g2, S.chain_g3, p, i, dtc);  // U's header from the constant bank
     float m = __int_as_float(0x7f800000);  // +inf passes both tests: the first entry is evaluated unconditionally (:26)
+    bool certified = false;
+    {
+        // SdfBoundary.fs:276-282 with U's header from the constant bank (see grid_cell_from)
+        const float4 g1 = S.chain_g1, g2 = S.chain_g2, g3 = S.chain_g3;
+        const V3 c = (p - xyz(g1)) * xyz(g2);
+        const int mx = __float_as_int(g3.x), my = __float_as_int(g3.y), mz = __float_as_int(g3.z);
+        const int ix = cell_index(c.x, mx), iy = cell_index(c.y, my), iz = cell_index(c.z, mz);
+        const uint32_t ci = __float_as_uint(g1.w) + (uint32_t)(ix * __float_as_int(g3.w) + iy * (mz + 1) + iz);
+        if (S.sub_valid && c.x >= 0.0f && c.y >= 0.0f && c.z >= 0.0f && c.x < S.sub_count_f[0] && c.y < S.sub_count_f[1] &&
+            c.z < S.sub_count_f[2]) {
+            uint32_t best = 0u;
+            float ms = 0.f;
+            certified = sub_lookup<COUNT>(S, p, c, ci, ix, iy, iz, ms, best, acc);
+            if (certified) {
+                m = ms;
+#if FT_CHAIN_MAT
+                best_lo = (uint32_t)(uintptr_t)(S.entries + 2ull * best);
+#endif
+            }
+        }
+        if (!certified) {
+            const float4 cell = ld4(S.cells + ci);
+            dtc = distance(p, xyz(cell));  // SdfForm.fs:25
+            i = __float_as_uint(cell.w);
+        }
+    }
+    if (!certified) {
 #if FT_SCAN_PTR
     // `ep` points at the record the unrolled loop started its current round with; the record under test is ep + 2 K
     // (K = 0, 1: an immediate offset).  The only pointer arithmetic inside the loop is one 64-bit add per two records;
@@ -457,27 +561,7 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, u
         }                                                                     \
     }
         Entry e0 = FT_LD_ENTRY(0);
-#if FT_SCAN_PAIR
-        // EXPERIMENT, not measured yet (DESIGN.md "What comes next"): two candidates per branch.  When both pass the
-        // LowerBound test and both certainly fail the second pruning test -- the common outcome -- one merged predicate
-        // replaces four branches; every other case falls back to the sequential code below on the same two records.
-        Entry e1 = FT_LD_ENTRY(1);
-        for (;;) {
-            if (!((m > e0.lb() - dtc) & bound_certain_fail(m, e0.bound(), p) & (m > e1.lb() - dtc) & bound_certain_fail(m, e1.bound(), p))) {
-                FT_CHAIN_ONE(e0, 0)
-                FT_CHAIN_ONE(e1, 1)
-            } else {
-                add_flops<COUNT>(acc, 2 * (FLOPS_LB_TEST + FLOPS_BOUND_TEST));
-            }
-            e0 = FT_LD_ENTRY(2);
-            e1 = FT_LD_ENTRY(3);
-#if FT_SCAN_PTR
-            ep += 4;
-#else
-            i += 2;
-#endif
-        }
-#elif FT_SCAN_UNROLL == 4
+#if FT_SCAN_UNROLL == 4
         Entry e1 = FT_LD_ENTRY(1);
         for (;;) {
             FT_CHAIN_ONE(e0, 0)
@@ -525,6 +609,7 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, u
     }
 #undef FT_LD_ENTRY
 #undef FT_NOTE_BEST
+    }  // !certified
     float v = m;
     // (measured: also serving the chain operations' operands from the constant bank, unrolled, made config 1 4 % slower
     // -- four inlined copies of the primitive evaluator)

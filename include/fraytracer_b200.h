@@ -190,6 +190,20 @@ typedef struct ft_scene_info {
     int32_t reserved;
 } ft_scene_info;
 
+/* the nearest-candidate sub-grid the device path builds over the spatial lookup of
+ * a chain-shaped scene (DESIGN.md "sub-grid"): an acceleration structure of this
+ * implementation only -- the reference has no counterpart; results are certified
+ * equal to the reference's sequential candidate scan (SdfForm.fs:22-34)        */
+typedef struct ft_subgrid_info {
+    int32_t resolution;      /* sub-cells per cell and axis (8, 4, 2, 1); 0 = none */
+    int32_t reserved;
+    int64_t n_subcells;
+    int64_t n_entries;       /* candidate references over all sub-cells        */
+    int64_t device_bytes;
+    float threshold;         /* 2 x half diagonal + tolerance (world units)    */
+    float build_ms;          /* device time of the build                       */
+} ft_subgrid_info;
+
 /* per-grid introspection (tests compare this against the oracle's grid) */
 typedef struct ft_grid_info {
     int32_t node;            /* compiled node id of the union                  */
@@ -252,6 +266,12 @@ FT_API int ft_scene_info_get(const ft_scene *scene, ft_scene_info *out);
  * rays that exceed `max_steps` Distance evaluations are stopped as misses and
  * counted in ft_render_stats.capped_rays.  Default 1<<22.                   */
 FT_API int ft_scene_set_step_cap(ft_scene *scene, int32_t max_steps);
+
+FT_API int ft_scene_subgrid_info(const ft_scene *scene, ft_subgrid_info *out);
+/* test hook: bit 0 of `sub_debug` makes the device path distrust every sub-grid
+ * certificate, so that every Distance evaluation also runs the reference's
+ * sequential candidate scan (SdfForm.fs:27-33); results must not change        */
+FT_API int ft_scene_set_debug(ft_scene *scene, int32_t sub_debug);
 
 FT_API int ft_scene_grid_count(const ft_scene *scene, int32_t *count);
 FT_API int ft_scene_grid_info(const ft_scene *scene, int32_t grid, ft_grid_info *out);

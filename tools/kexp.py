@@ -1,0 +1,38 @@
+"""Kernel experiment driver (one tool for every A/B): runs configs 1, 2 and 5 (4K) once per environment setting and prints the
+kernel time, Mrays/s, the sub-grid's shape and a CRC of the frame's bits (equal CRCs = bit-identical frames).
+
+    python tools/kexp.py "" "FT_NO_SUBGRID=1" "FT_SUBGRID_RES=4" "FT_SUB_DEBUG=1 FT_LIB=build/x.so"
+"""
+import os, subprocess, sys, zlib
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    import fraytracer_b200 as ft
+    from fraytracer_b200 import scenes
+
+    which = os.environ.get("KEXP_CONFIGS", "1,2,5").split(",")
+    ws = {"1": scenes.default_scene, "2": scenes.spheres_capsules_scene, "5": lambda: scenes.mixed_scene(width=3840, height=2160),
+          "5f": scenes.mixed_scene}
+    for k in which:
+        w = ws[k]()
+        tr = ft.SceneTracer(w.scene, 0)
+        best = 1e9
+        for it in range(6):
+            rgb, leaf, st = tr.render(w.camera, w.size, w.epsilon, w.length, want_leaf=(it == 0))
+            if it == 0:
+                crc = zlib.crc32(rgb.tobytes()) ^ zlib.crc32(leaf.tobytes())
+            else:
+                best = min(best, st["kernel_ms"])
+        rays = st["primary_rays"] + st["shadow_rays"]
+        sg = tr.subgrid_info()
+        print(f"   {w.name:32s} kernel {best:7.3f} ms {rays / best / 1e3:7.0f} Mrays/s  crc {crc:08x}  sub res {sg['resolution']} "
+              f"cells {sg['n_subcells']} entries {sg['n_entries']} ({sg['device_bytes'] / 1e6:.1f} MB, {sg['build_ms']:.2f} ms)",
+              flush=True)
+    sys.exit(0)
+for setting in (sys.argv[1:] or [""]):
+    env = dict(os.environ, FT_BANDS="1")
+    for kv in setting.split():
+        k, v = kv.split("=", 1)
+        env[k] = os.path.abspath(v) if k == "FT_LIB" else v
+    print(f"[{setting or 'default'}]", flush=True)
+    subprocess.run([sys.executable, __file__, "child"], env=env)

@@ -19,6 +19,7 @@ WANT = [
     "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+    "sm__cycles_active.avg", "sm__cycles_active.max", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
