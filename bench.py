@@ -108,7 +108,7 @@ class ClockSampler:
             except Exception as e:  # noqa: BLE001
                 self.error = str(e)
                 return
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def stop(self, t_begin=None, t_end=None):
         if self.error and not self.rows:
@@ -127,62 +127,102 @@ class ClockSampler:
                 "window": window}
 
 
-def cpu_sample(orc, w, budget_s: float, threads: int):
-    """pick a column stride so that one oracle pass over the sample takes about budget_s"""
+def shared_config(args, w, world: int) -> dict:
+    """`config` of the JSON line: only what BOTH arms know, so that the GPU arm and `--impl reference` print the same dict
+    (the driver compares them).  Per-run details (ray counts, grid sizes, capped rays) live in `workload_detail`."""
+    from fraytracer_b200.distributed import auto_strip_width
+
     X, Y = w.size.X, w.size.Y
+    sw = auto_strip_width(X, world)
+    if args.scaling == "strong":
+        rule = "strong: one fixed frame cut over all GPUs"
+    else:
+        rule = "weak: every GPU renders 1080p worth of pixels of a sqrt(N)-times larger frame of the same scene" if world > 1 \
+            else "one GPU, the configuration's own frame"
+    return {"workload": w.name, "image": f"{X}x{Y}", "primitives": len(w.leaves), "scene_seed": 19, "spp": 1,
+            "epsilon": w.epsilon, "ray_length": w.length, "frame_rule": rule,
+            "mode": "fast" if args.fast else "strict",
+            "parallelism": f"GPU arm: image strips ({sw} columns wide, round-robin) x{world}" + (
+                "" if world == 1 else ", framebuffer gather " + (args.gather or "p2p (peer stores fused into the render kernel over "
+                                                                  "NVLink, 4-byte NCCL all-reduce; NCCL all-gather if peer "
+                                                                  "mapping is unavailable)")) +
+                           "; CPU arm: image columns over host threads (Array2D.Parallel.init, Array2D.fs:30-38)",
+            "l2": "GPU arm: flushed between timed iterations (512 MiB write); CPU arm: not applicable"}
+
+
+def cpu_rays(orc, camera, w, stride: int, threads: int) -> int:
+    """rays (primary + shadow) of the column sample: one UNTIMED pass with the oracle's counters on (deterministic)"""
+    c = orc.render(camera, w.size.X, w.size.Y, w.epsilon, w.length, threads=threads, x_stride=stride, counters=True)["counters"]
+    return int(c["primary_rays"] + c["shadow_rays"])
+
+
+def cpu_sample(orc, camera, w, budget_s: float, threads: int):
+    """pick a column stride so that one oracle pass over the sample takes about budget_s; returns (stride, rays of the sample)"""
+    X, Y = w.size.X, w.size.Y
+    rays64 = cpu_rays(orc, camera, w, 64, threads)
     t0 = time.perf_counter()
-    r = orc.render(w.camera, X, Y, w.epsilon, w.length, threads=threads, x_stride=64, counters=True)
-    dt = time.perf_counter() - t0
-    rays = r["counters"]["primary_rays"] + r["counters"]["shadow_rays"]
-    rate = rays / max(dt, 1e-6)
-    full_rays = rays * 64.0
+    orc.render(camera, X, Y, w.epsilon, w.length, threads=threads, x_stride=64, counters=False)
+    rate = rays64 / max(time.perf_counter() - t0, 1e-6)
     stride = 1
-    while stride < 64 and full_rays / stride / rate > budget_s:
+    while stride < 64 and rays64 * 64.0 / stride / rate > budget_s:
         stride *= 2
-    return stride
+    return stride, (rays64 if stride == 64 else cpu_rays(orc, camera, w, stride, threads))
 
 
-def run_cpu(orc, w, stride: int, threads: int):
-    X, Y = w.size.X, w.size.Y
+def run_cpu(orc, camera, w, stride: int, threads: int) -> float:
+    """seconds of one oracle pass over the sample -- counters OFF inside the timed region"""
     t0 = time.perf_counter()
-    r = orc.render(w.camera, X, Y, w.epsilon, w.length, threads=threads, x_stride=stride, counters=True)
-    dt = time.perf_counter() - t0
-    c = r["counters"]
-    return (c["primary_rays"] + c["shadow_rays"]), dt
+    orc.render(camera, w.size.X, w.size.Y, w.epsilon, w.length, threads=threads, x_stride=stride, counters=False)
+    return time.perf_counter() - t0
+
+
+def oracle_camera():
+    """Program.fs:16-22 through the ORACLE's Lens.create / Camera.lookAt (fto_*), not the product's"""
+    from fraytracer_b200.scenes import CAMERA_SPEC as cs
+    from oracle import oracle as O
+
+    return O.camera_look_at(cs["Position"], cs["LookAt"], cs["Up"], O.lens_create(cs["FieldOfView"]))
 
 
 def bench_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The F# reference
-    cannot run here (no .NET), so this is the oracle port (cpu_baseline.kind = "port")."""
+    cannot run here (no .NET), so this is the oracle port (cpu_baseline.kind = "port").  Same workload, frame and
+    `config` as the GPU arm at this N; rank 0 alone works."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     import fraytracer_b200 as ft
     from oracle import oracle as O
 
-    w = workload(args.workload, 1)
+    w = workload(args.workload, world, args.scaling == "strong")
     orc = O.OracleScene(ft.SceneDescription(w.scene))
+    cam = oracle_camera()
     threads = os.cpu_count() or 1
     per_step = max(1.0, min(10.0, 150.0 / max(1, args.steps + args.warmup)))
-    stride = cpu_sample(orc, w, per_step, threads)
+    stride, rays = cpu_sample(orc, cam, w, per_step, threads)
     for _ in range(args.warmup):
-        run_cpu(orc, w, stride, threads)
-    rays = secs = 0.0
-    for _ in range(args.steps):
-        r, dt = run_cpu(orc, w, stride, threads)
-        rays += r
-        secs += dt
-    value = rays / secs / 1e6
-    sample = f"every {stride}th column of the {w.size.X}x{w.size.Y} frame ({int(rays / args.steps)} rays per step)"
+        run_cpu(orc, cam, w, stride, threads)
+    times = [run_cpu(orc, cam, w, stride, threads) for _ in range(args.steps)]
+    secs = sum(times)
+    value = rays * args.steps / secs / 1e6
+    sample = f"every {stride}th column of the {w.size.X}x{w.size.Y} frame ({rays} rays per step), oracle counters off"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "image": f"{w.size.X}x{w.size.Y}", "sample": sample},
+        "config": shared_config(args, w, world),
+        "step_ms_percentiles": percentiles([1e3 * t for t in times]),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the F# path (oracle/ft_oracle.c); .NET unavailable"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def percentiles(xs):
+    xs = sorted(xs)
+    pick = lambda q: xs[min(len(xs) - 1, int(round(q * (len(xs) - 1))))]
+    return {"p10": pick(0.1), "p50": pick(0.5), "p90": pick(0.9), "min": xs[0], "max": xs[-1], "n": len(xs)}
 
 
 def bench_extension(args):
@@ -256,6 +296,128 @@ def bench_extension(args):
                 "d2h_bytes_per_step": X * Y * 12, "ms_per_step": 1e3 * wall / args.steps},
         "gpu_launches": args.steps * st["launches"], "roofline": None, "cpu_baseline": cpu,
     }))
+
+
+def nrank_equals_1rank(torch, tracer, renderer, w, flags, rank, n_samples: int = 12) -> bool:
+    """rank 0: a sample of strips rendered alone (ft_render_strips_device, world = 1) equals, bit for bit, the same columns of
+    the frame the ranks rendered together (Image.render is a pure function of the pixel, Image.fs:26-35)"""
+    final = renderer.render(w.camera, w.epsilon, w.length, flags)
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        X, Y, sw = w.size.X, w.size.Y, renderer.strip_width
+        strips = (X + sw - 1) // sw
+        buf = torch.empty((sw, Y, 3), dtype=torch.float32, device=final.device)
+        for s in sorted({int(round(k * (strips - 1) / max(1, n_samples - 1))) for k in range(n_samples)}):
+            cols = min(sw, X - s * sw)
+            tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(),
+                                 stream=torch.cuda.current_stream().cuda_stream, flags=flags, strip_width=sw, rank=0, world=1,
+                                 first_local_strip=s, n_local_strips=1)
+            torch.cuda.synchronize()
+            ok = ok and bool(torch.equal(buf[:cols].view(torch.int32), final[s * sw:s * sw + cols].view(torch.int32)))
+    return ok
+
+
+def config5_strong_block(args, torch, dist, ft, A, rank, world, local_rank, flags, flush, frames: int = 5):
+    """BASELINE config 5 as it is worded: ONE 7680x4320 frame of the 1024-primitive mixed scene cut over all N GPUs
+    (strong scaling), gathered on every GPU; reported at every N so that the driver's 1/2/4/8 runs carry the curve."""
+    from fraytracer_b200 import scenes
+    from fraytracer_b200.distributed import DistributedRenderer
+
+    w = scenes.mixed_scene()
+    dev = torch.device("cuda", local_rank)
+    tracer = ft.SceneTracer(w.scene, device=local_rank)
+    renderer = DistributedRenderer(tracer, w.size, gather=args.gather)
+    sw = renderer.strip_width
+    X, Y = w.size.X, w.size.Y
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def allred(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    # rays of this rank's strips and its kernel time alone (no gather target but its own buffer)
+    spr_floats = ft.distributed.strip_layout(X, Y, sw, world)[1]
+    buf = torch.empty(spr_floats, dtype=torch.float32, device=dev)
+    st = tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(), stream=stream, flags=flags,
+                              strip_width=sw, rank=rank, world=world, want_stats=True)
+    rays = allred(float(st["primary_rays"] + st["shadow_rays"]), dist.ReduceOp.SUM if world > 1 else None)
+    kern = []
+    for it in range(4):
+        flush.zero_()
+        k0, k1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        k0.record()
+        tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(), stream=stream, flags=flags, strip_width=sw,
+                             rank=rank, world=world)
+        k1.record()
+        torch.cuda.synchronize()
+        if it:
+            kern.append(k0.elapsed_time(k1))
+    del buf
+    kern_ms = sum(kern) / len(kern)
+    k_min = allred(kern_ms, dist.ReduceOp.MIN if world > 1 else None)
+    k_max = allred(kern_ms, dist.ReduceOp.MAX if world > 1 else None)
+    k_sum = allred(kern_ms, dist.ReduceOp.SUM if world > 1 else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    times = []
+    for it in range(frames + 2):
+        flush.zero_()
+        barrier()
+        e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        e0.record()
+        renderer.render(w.camera, w.epsilon, w.length, flags)
+        e1.record()
+        barrier()
+        if it >= 2:
+            times.append(allred(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None))
+    ms = sum(times) / len(times)
+    equal = nrank_equals_1rank(torch, tracer, renderer, w, flags, rank) if world > 1 else None
+    # end to end: the frame in (shared) page-locked host memory, every GPU over its own PCIe link
+    e2e_ms = None
+    try:
+        if world == 1:
+            host = C.c_void_p()
+            A.check(tracer.lib.ft_host_alloc(C.byref(host), X * Y * 12))
+            import numpy as np
+            out = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(X, Y, 3))
+            ts = []
+            for it in range(4):
+                flush.zero_()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                tracer.render(w.camera, w.size, w.epsilon, w.length, flags=flags, out=out)
+                ts.append(time.perf_counter() - t0)
+            A.check(tracer.lib.ft_host_free(host))
+            e2e_ms = 1e3 * sum(ts[1:]) / 3
+        else:
+            renderer.host_frame()
+            ts = []
+            for it in range(4):
+                flush.zero_()
+                barrier()
+                t0 = time.perf_counter()
+                renderer.render_to_host(w.camera, w.epsilon, w.length, flags)
+                ts.append(time.perf_counter() - t0)
+            e2e_ms = allred(1e3 * sum(ts[1:]) / 3, dist.ReduceOp.MAX)
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] config5 e2e unavailable on rank {rank}: {e}", file=sys.stderr)
+    if world > 1:
+        renderer.close()
+    tracer.close()
+    return {"workload": w.name, "image": f"{X}x{Y}", "primitives": len(w.leaves), "scaling": "strong", "n_gpus": world,
+            "rays_per_frame": int(rays), "ms_per_frame": ms, "value": rays / ms / 1e3, "unit": UNIT, "frames": len(times),
+            "strip_width": sw, "rank_kernel_ms": {"min": k_min, "max": k_max, "mean": k_sum / world,
+                                                  "max_over_mean": k_max / (k_sum / world)},
+            "e2e_ms_per_frame": e2e_ms, "e2e_value": (rays / e2e_ms / 1e3) if e2e_ms else None,
+            "nrank_equals_1rank": equal}
 
 
 def bench_b200(args):
@@ -341,7 +503,8 @@ def bench_b200(args):
     events = [one_step(True) for _ in range(args.steps)]
     barrier()
     t_end = time.time()
-    step_ms = sum(e0.elapsed_time(e2) for e0, _, e2 in events)
+    step_list = [e0.elapsed_time(e2) for e0, _, e2 in events]
+    step_ms = sum(step_list)
     clocks = sampler.stop(t_begin, t_end) if sampler else None
     step_ms = allreduce(step_ms, dist.ReduceOp.MAX if world > 1 else None)
     ms_per_step = step_ms / args.steps
@@ -363,7 +526,32 @@ def bench_b200(args):
             _, _, e2e_stats = tracer.render(w.camera, w.size, w.epsilon, w.length, flags=flags, out=out)  # Image.render
             e2e_s += time.perf_counter() - t0
         checksum = float(out[::97, ::89].sum())
+        first = out[::61].copy()
         A.check(lib.ft_host_free(host))
+        # what an UNMODIFIED caller gets (a plain, pageable array: two column bands staged through device memory) and the
+        # one-off cost of page-locking + mapping a caller's array (ft_host_register), after which ft_render is zero-copy
+        pageable = np.empty((X, Y, 3), np.float32)
+        pageable.fill(0.0)  # touch the pages
+        for _ in range(2):
+            tracer.render(w.camera, w.size, w.epsilon, w.length, flags=flags, out=pageable)
+        pg_s = 0.0
+        n_pg = max(3, min(10, args.steps))
+        for _ in range(n_pg):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tracer.render(w.camera, w.size, w.epsilon, w.length, flags=flags, out=pageable)
+            pg_s += time.perf_counter() - t0
+        assert np.array_equal(pageable[::61].view(np.uint32), first.view(np.uint32)), "pageable path differs from the zero-copy path"
+        reg_ms = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            A.check(lib.ft_host_register(C.c_void_p(pageable.ctypes.data), nbytes))
+            reg_ms.append(1e3 * (time.perf_counter() - t0))
+            A.check(lib.ft_host_unregister(C.c_void_p(pageable.ctypes.data)))
+        e2e_extra = {"e2e_pageable": {"value": total_rays * n_pg / pg_s / 1e6, "unit": UNIT, "ms_per_step": 1e3 * pg_s / n_pg,
+                                      "note": "ft_render into a plain (pageable) host array: staged through device memory"},
+                     "host_register_ms": min(reg_ms)}
         h2d = C.sizeof(A.ft_camera) + 16
         # page-locked + mapped output: the kernel stores finished pixels straight into host memory (one launch, no copy)
         e2e_launches = int(e2e_stats["launches"])
@@ -403,7 +591,17 @@ def bench_b200(args):
             checksum = float(pinned[::97, ::89].sum()) if rank == 0 else 0.0
         h2d = C.sizeof(A.ft_camera) + 16
         e2e_launches = 1 if host_ok else renderer.launches_per_frame
+        e2e_extra = {}
     e2e_value = total_rays * args.steps / e2e_s / 1e6
+
+    # ---- N ranks == 1 rank, bit for bit: rank 0 renders a sample of strips alone (world = 1) and compares them with the
+    # same columns of the frame all ranks produced together
+    nrank_equal = None
+    if world > 1:
+        nrank_equal = nrank_equals_1rank(torch, tracer, renderer, w, flags, rank)
+    c5 = None
+    if not args.no_config5 and args.workload == "config2" and args.scaling == "weak":
+        c5 = config5_strong_block(args, torch, dist, ft, A, rank, world, local_rank, flags, flush)
 
     if rank == 0:
         # ---- FP32 roofline of the dominant kernel
@@ -438,31 +636,35 @@ def bench_b200(args):
 
             orc = O.OracleScene(tracer.description)
             threads = os.cpu_count() or 1
-            stride = cpu_sample(orc, w, 15.0, threads)
+            ocam = oracle_camera()
+            stride, rays_pass = cpu_sample(orc, ocam, w, 15.0, threads)
             rays = secs = 0.0
             passes = 0
             while secs < 10.0 and passes < 64:  # about 10-30 s of CPU work
-                r, dt = run_cpu(orc, w, stride, threads)
-                rays, secs, passes = rays + r, secs + dt, passes + 1
+                dt = run_cpu(orc, ocam, w, stride, threads)
+                rays, secs, passes = rays + rays_pass, secs + dt, passes + 1
             cpu = {"value": rays / secs / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{passes} passes over every {stride}th column of the {X}x{Y} frame "
-                             f"({int(rays)} rays, {secs:.1f} s)",
+                             f"({int(rays)} rays, {secs:.1f} s), oracle counters off",
                    "note": "C restatement of the F# path (oracle/ft_oracle.c); .NET unavailable"}
         info = tracer.info()
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "image": f"{X}x{Y}", "rays_per_step": int(total_rays),
-                       "primitives": info["n_primitives"], "grid_entries": info["n_entries"],
-                       "parallelism": f"image strips ({sw} columns wide, round-robin) x{world}" + (
-                           "" if world == 1 else " + P2P stores from the render kernel (CUDA IPC over NVLink), 4-byte NCCL all-reduce"
-                           if renderer.gather == "p2p" else " + NCCL all-gather + de-interleave"),
-                       "l2": "flushed between timed iterations (512 MiB write)", "capped_rays": int(capped),
-                       "mode": "fast" if args.fast else "strict"},
+            "config": shared_config(args, w, world),
+            "workload_detail": {"rays_per_step": int(total_rays), "primitives": info["n_primitives"],
+                                "grid_entries": info["n_entries"], "subgrid": tracer.subgrid_info(),
+                                "strip_width": sw, "gather": renderer.gather if world > 1 else None,
+                                "capped_rays": int(capped)},
+            "step_ms_percentiles": percentiles(step_list),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": X * Y * 12,
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": checksum},
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "checksum": checksum,
+                    "path": "zero-copy: the kernel stores finished pixels straight into the caller's page-locked, mapped "
+                            "FColor[X,Y]" + ("" if world == 1 else " (one shared host frame, every GPU over its own PCIe link)")},
+            **e2e_extra,
+            "nrank_equals_1rank": nrank_equal, "config5_strong": c5,
             "gpu_launches": args.steps * renderer.launches_per_frame,
             "e2e_gpu_launches": args.steps * e2e_launches,
             "roofline": roofline, "cpu_baseline": cpu,
@@ -482,6 +684,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config5", "config3", "config4"])
     ap.add_argument("--fast", action="store_true", help="FT_FLAG_FAST_MATH (FMA contraction, not bit-exact)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config5_strong block (BASELINE config 5: one 8K frame over all GPUs)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): 1080p worth of pixels per GPU; strong: one fixed frame (config5: 7680x4320) over all GPUs")
     ap.add_argument("--gather", default=None, choices=["p2p", "nccl"],

@@ -237,19 +237,43 @@ type CompiledScene(scene:SceneNode, device:int) =
     interface IDisposable with
         member _.Dispose() = if handle <> 0n then Native.ft_scene_destroy handle |> ignore
 
+/// A reusable FColor[X,Y] that is pinned AND registered with the CUDA driver (ft_host_register: page-locked and mapped into
+/// the device's address space).  ft_render then takes its zero-copy path: the kernel stores every finished 4 x 8 pixel tile
+/// straight into this array (128-bit stores over PCIe), no staging buffer and no device->host copy.  Registration costs a few
+/// milliseconds once (bench.py prints `host_register_ms`), so keep one FrameBuffer per output size and render into it again.
+type FrameBuffer(size:ImageSize) =
+    let image = Array2D.zeroCreate<FColor> size.X size.Y
+    let pin = GCHandle.Alloc(image, GCHandleType.Pinned)
+    do Native.ft_host_register(pin.AddrOfPinnedObject(), int64 size.X * int64 size.Y * 12L) |> Native.check
+    member _.Size = size
+    member _.Image = image
+    member _.Address = pin.AddrOfPinnedObject()
+    interface IDisposable with
+        member _.Dispose() =
+            Native.ft_host_unregister(pin.AddrOfPinnedObject()) |> ignore
+            pin.Free()
+
 [<RequireQualifiedAccess>]
 module Image =
-    /// Image.render epsilon length imageSize camera (SdfScene.trace scene)   (Image.fs:26-35)
-    /// FColor[X,Y] is row-major with X the slow index and 12 bytes per element: exactly ft_render's out_rgb.
+    let private call (scene:CompiledScene) (camera:Camera) (size:ImageSize) (epsilon:float32) (length:float32) (address:nativeint) =
+        let mutable cam : Native.CameraDesc =
+            { position = camera.Position; forward = camera.Forward
+              upScaled = camera.UpScaled; rightScaled = camera.RightScaled }
+        Native.ft_render(scene.Handle, &cam, size.X, size.Y, epsilon, length, 0u, address, 0n, 0n) |> Native.check
+
+    /// The fast path (bench.py `e2e`): renders into a registered FrameBuffer and returns its FColor[X,Y].
+    let renderInto (frame:FrameBuffer) (epsilon:float32) (length:float32) (camera:Camera) (scene:CompiledScene) : FColor[,] =
+        call scene camera frame.Size epsilon length frame.Address
+        frame.Image
+
+    /// Image.render epsilon length imageSize camera (SdfScene.trace scene)   (Image.fs:26-35), the reference's own signature:
+    /// a FRESH FColor[X,Y] per call.  FColor[X,Y] is row-major with X the slow index and 12 bytes per element: exactly
+    /// ft_render's out_rgb.  A fresh array is pinned but not registered (registering 25 MB costs more than one 1080p frame),
+    /// so this call takes ft_render's staged path -- two column bands through device memory, bench.py `e2e_pageable`.
+    /// Callers that render more than one frame should hold a FrameBuffer and use renderInto.
     let render (epsilon:float32) (length:float32) (imageSize:ImageSize) (camera:Camera) (scene:CompiledScene) : FColor[,] =
         let image = Array2D.zeroCreate<FColor> imageSize.X imageSize.Y
         let pin = GCHandle.Alloc(image, GCHandleType.Pinned)
-        try
-            let mutable cam : Native.CameraDesc =
-                { position = camera.Position; forward = camera.Forward
-                  upScaled = camera.UpScaled; rightScaled = camera.RightScaled }
-            Native.ft_render(scene.Handle, &cam, imageSize.X, imageSize.Y, epsilon, length, 0u,
-                             pin.AddrOfPinnedObject(), 0n, 0n)
-            |> Native.check
+        try call scene camera imageSize epsilon length (pin.AddrOfPinnedObject())
         finally pin.Free()
         image

@@ -134,7 +134,7 @@ EXPORTS = [
     "ft_device_alloc", "ft_device_free", "ft_ipc_export", "ft_ipc_import", "ft_ipc_close", "ft_strip_layout", "ft_deinterleave_device",
     "ft_deinterleave_strips_device",
     "ft_trace_rays", "ft_distance", "ft_render_spectral", "ft_render_cloud", "ft_render_spectral_gather_device", "ft_render_cloud_gather_device",
-    "ft_image_max_device", "ft_tonemap_device", "ft_to_bitmap", "ft_save_bitmap",
+    "ft_image_max_device", "ft_tonemap_device", "ft_image_max_strips_device", "ft_tonemap_strips_device", "ft_to_bitmap", "ft_save_bitmap",
     "ft_host_register", "ft_host_unregister", "ft_host_alloc", "ft_host_free", "ft_host_get_device_pointer",
     "ft_measure_fp32_peak",
 ]
@@ -204,6 +204,8 @@ def load_library(path: str | None = None):
                                                     i32, i32, i32, P(vp), i32, vp, P(ft_render_stats)]),
         "ft_image_max_device": (C.c_int, [vp, i64, vp, vp]),
         "ft_tonemap_device": (C.c_int, [vp, i32, i32, f32, vp, f32, C.c_uint64, vp, i32, vp]),
+        "ft_image_max_strips_device": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
+        "ft_tonemap_strips_device": (C.c_int, [vp, i32, i32, i32, i32, i32, f32, vp, f32, C.c_uint64, vp, i32, vp]),
         "ft_to_bitmap": (C.c_int, [C.c_int, vp, i32, i32, f32, C.c_uint64, vp, i32]),
         "ft_save_bitmap": (C.c_int, [C.c_char_p, vp, i32, i32, i32]),
         "ft_host_register": (C.c_int, [vp, i64]),

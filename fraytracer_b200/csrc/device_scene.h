@@ -102,12 +102,12 @@ struct DevScene {
     int32_t chain_mat_valid;
     int32_t chain_mat_links;
     // Nearest-candidate sub-grid of U (subgrid_build.cu, DESIGN.md "sub-grid"): every cell of U's spatial lookup is cut into
-    // sub_res^3 sub-cells; sub_hdr[cell * sub_res^3 + (sx * sub_res + sy) * sub_res + sz] = (first << 8) | count addresses a
-    // short list in sub_idx[] of ABSOLUTE indices into entries[] -- those candidates of the cell's own list that can be the
+    // sub_res^3 sub-cells; sub_hdr[cell * sub_res^3 + (sx * sub_res + sy) * sub_res + sz] addresses a short list of ABSOLUTE
+    // indices into entries[] -- those candidates of the cell's own list that can be the
     // nearest one for some position inside the sub-cell (all others are provably farther than the nearest by a margin),
     // nearest first.  Positions inside the lookup's box evaluate only these (eval_chain); the result is certified equal to the
     // reference's sequential scan, otherwise the scan itself runs.  sub_valid == 0: no sub-grid (the scan always runs).
-    const uint32_t *sub_hdr;
+    const uint2 *sub_hdr;    // {(first << 8) | count, the nearest candidate}; sub_idx[first ...] holds candidates 1 .. count-1
     const uint32_t *sub_idx;
     int32_t sub_valid;
     int32_t sub_res;        // 1, 2, 4 or 8

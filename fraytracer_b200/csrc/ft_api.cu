@@ -819,12 +819,15 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
         else
             P.local_cols = n_local_strips * strip_width;
         P.xl_begin = first_local_strip * strip_width;
-        if (P.local_cols <= 0) return FT_OK;
+        if (P.local_cols <= 0) {
+            if (stats) std::memset(stats, 0, sizeof(*stats));
+            return FT_OK;
+        }
     }
     if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     unsigned long long *wc;
     CU(fresh_counter(scene, s, &wc));
-    cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render, scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, scene->d_stats, count, scene->sm_count, s);
+    cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render, scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, stats ? scene->d_stats : nullptr, count, scene->sm_count, s, false);
     if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -868,7 +871,7 @@ FT_API int ft_render_gather_device(ft_scene *scene, const ft_camera *camera, int
     if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     unsigned long long *wc;
     CU(fresh_counter(scene, s, &wc));
-    cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render_gather, scene->dev, *camera, P, d_dst, n_dst, wc, scene->d_stats, count, scene->sm_count, s);
+    cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render_gather, scene->dev, *camera, P, d_dst, n_dst, wc, stats ? scene->d_stats : nullptr, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "render-gather kernel launch");
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
@@ -974,7 +977,7 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
             RenderParams P = make_params(width, height, epsilon, length, width, 0, 1);
             unsigned long long *wc;
             CU(fresh_counter(scene, s, &wc));
-            cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, m_rgb, m_leaf, wc, scene->d_stats, count, scene->sm_count, s);
+            cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, m_rgb, m_leaf, wc, scene->d_stats, count, scene->sm_count, s, true);
             if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
             CU(cudaEventRecord(scene->ev[1], s));
             CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -1015,7 +1018,7 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
         int32_t *band_leaf = d_leaf ? d_leaf + (size_t)x0 * height : nullptr;
         unsigned long long *wc;
         CU(fresh_counter(scene, bs, &wc));
-        cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, band_rgb, band_leaf, wc, scene->d_stats, count, scene->sm_count, bs);
+        cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, band_rgb, band_leaf, wc, scene->d_stats, count, scene->sm_count, bs, false);
         if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
         launches++;
         CU(cudaEventRecord((launches & 1) ? scene->ev[1] : scene->ev[3], bs));  // end of the last kernel on each stream
@@ -1189,6 +1192,28 @@ FT_API int ft_tonemap_device(const float *d_rgb, int32_t width, int32_t height, 
     if (!d_rgb || !d_out_bgr || width <= 0 || height <= 0 || stride < 3 * width || !(gamma > 0.0f))
         return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
     cudaError_t e = launch_tonemap(d_rgb, width, height, gamma, d_max, max_value, seed, d_out_bgr, stride, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tonemap kernel launch");
+    return FT_OK;
+}
+
+FT_API int ft_image_max_strips_device(const float *d_rgb, int32_t width, int32_t height, int32_t strip_width, int32_t rank,
+                                      int32_t world, float *d_max, void *stream) {
+    if (!d_rgb || !d_max || width <= 0 || height <= 0 || strip_width <= 0 || world <= 0 || rank < 0 || rank >= world)
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    cudaError_t e = launch_image_max(d_rgb, (long long)width * height * 3, d_max, (cudaStream_t)stream, height * 3, strip_width,
+                                     rank, world);
+    if (e != cudaSuccess) return cuda_fail(e, "image max kernel launch");
+    return FT_OK;
+}
+
+FT_API int ft_tonemap_strips_device(const float *d_rgb, int32_t width, int32_t height, int32_t strip_width, int32_t rank,
+                                    int32_t world, float gamma, const float *d_max, float max_value, uint64_t seed,
+                                    uint8_t *d_out_bgr, int32_t stride, void *stream) {
+    if (!d_rgb || !d_out_bgr || width <= 0 || height <= 0 || stride < 3 * width || !(gamma > 0.0f) || strip_width <= 0 ||
+        world <= 0 || rank < 0 || rank >= world)
+        return fail(FT_ERR_INVALID_ARGUMENT, "invalid argument");
+    cudaError_t e = launch_tonemap(d_rgb, width, height, gamma, d_max, max_value, seed, d_out_bgr, stride, (cudaStream_t)stream,
+                                   strip_width, rank, world);
     if (e != cudaSuccess) return cuda_fail(e, "tonemap kernel launch");
     return FT_OK;
 }

@@ -57,7 +57,7 @@ struct StripTarget {
     namespace NS {                                                                                                    \
     cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb,         \
                               int *out_leaf, unsigned long long *work_counter, unsigned long long *stats, bool count, \
-                              int sm_count, cudaStream_t stream);                                                     \
+                              int sm_count, cudaStream_t stream, bool tile_store);                                    \
     cudaError_t launch_render_gather(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *const *dst,     \
                                      int n_dst, unsigned long long *work_counter, unsigned long long *stats, bool count,   \
                                      int sm_count, cudaStream_t stream);                                              \
@@ -77,7 +77,10 @@ cudaError_t launch_deinterleave(const float *gathered, int width, int height, in
 cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate);
 
 // post_kernels.cu
-cudaError_t launch_image_max(const float *rgb, long long n_floats, float *d_max, cudaStream_t stream);
+// strip_width > 0: only the columns of the strips `rank` owns (strip s -> rank s % world); 0: the whole frame
+cudaError_t launch_image_max(const float *rgb, long long n_floats, float *d_max, cudaStream_t stream, int column_floats = 0,
+                             int strip_width = 0, int rank = 0, int world = 1);
 cudaError_t launch_tonemap(const float *rgb, int X, int Y, float gamma, const float *d_max, float max_value,
-                           unsigned long long seed, unsigned char *out, int stride, cudaStream_t stream);
+                           unsigned long long seed, unsigned char *out, int stride, cudaStream_t stream, int strip_width = 0,
+                           int rank = 0, int world = 1);
 int write_bmp_file(const char *path, const unsigned char *bgr, int width, int height, int stride);

@@ -14,7 +14,10 @@ __global__ void __launch_bounds__(BLOCK) distance_kernel(const __grid_constant__
     const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= n) return;
     Acc acc{0ull, 0ull};
-    out[i] = eval_form<false>(S, S.root_word, V3{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]}, acc);
+    const V3 p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    uint32_t best = 0u;
+    // chain scenes go through the evaluator the render path uses (sub-grid included), so that tests see its values
+    out[i] = S.chain_valid ? eval_chain<false>(S, p, acc, best) : eval_form<false>(S, S.root_word, p, acc);
 }
 
 // persistent grid: resident CTAs per SM (occupancy API) x SM count, capped by the amount of work
@@ -38,10 +41,11 @@ static cudaError_t persistent_grid(K kernel, long long items, int sm_count, unsi
         machine_kernel<C, E, H, JOB><<<grid, MB, 0, stream>>>(S, job, work_counter, stats);                           \
     } while (0)
 
-cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb, int *out_leaf,
-                          unsigned long long *work_counter, unsigned long long *stats, bool count, int sm_count,
-                          cudaStream_t stream) {
-    RenderJob job;
+template <class JOB>
+static cudaError_t launch_render_job(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb, int *out_leaf,
+                                     unsigned long long *work_counter, unsigned long long *stats, bool count, int sm_count,
+                                     cudaStream_t stream) {
+    JOB job;
     job.cam = cam;
     job.P = P;
     job.out_rgb = out_rgb;
@@ -51,11 +55,19 @@ cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderP
     unsigned grid = 1;
     cudaError_t e;
     const bool chain = S.chain_valid != 0;
-    if (count && chain) FT_LAUNCH(true, true, true, RenderJob, job.n_items);
-    else if (count) FT_LAUNCH(true, true, false, RenderJob, job.n_items);
-    else if (chain) FT_LAUNCH(false, true, true, RenderJob, job.n_items);
-    else FT_LAUNCH(false, true, false, RenderJob, job.n_items);
+    if (count && chain) FT_LAUNCH(true, true, true, JOB, job.n_items);
+    else if (count) FT_LAUNCH(true, true, false, JOB, job.n_items);
+    else if (chain) FT_LAUNCH(false, true, true, JOB, job.n_items);
+    else FT_LAUNCH(false, true, false, JOB, job.n_items);
     return cudaGetLastError();
+}
+
+// tile_store: the destination is mapped host memory (ft_render's zero-copy path): whole tiles leave as 128-bit stores
+cudaError_t launch_render(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *out_rgb, int *out_leaf,
+                          unsigned long long *work_counter, unsigned long long *stats, bool count, int sm_count,
+                          cudaStream_t stream, bool tile_store) {
+    if (tile_store) return launch_render_job<RenderTileJob>(S, cam, P, out_rgb, out_leaf, work_counter, stats, count, sm_count, stream);
+    return launch_render_job<RenderJob>(S, cam, P, out_rgb, out_leaf, work_counter, stats, count, sm_count, stream);
 }
 
 cudaError_t launch_render_gather(const DevScene &S, const ft_camera &cam, const RenderParams &P, float *const *dst, int n_dst,

@@ -31,10 +31,15 @@ __device__ inline float atomic_max_float(float *addr, float v) {  // v >= 0 in p
     return __int_as_float(old);
 }
 
-__global__ void __launch_bounds__(256) image_max_kernel(const float *__restrict__ rgb, long long n, float *out) {
+// strip_width > 0: only the columns of the strips `rank` owns (strip s -> rank s % world) take part -- the rank's share of
+// Array2D.maxWith (Image.fs:40-43) when a frame is cut over several GPUs; the shares meet in an all-reduce(MAX)
+__global__ void __launch_bounds__(256) image_max_kernel(const float *__restrict__ rgb, long long n, float *out, int column_floats,
+                                                        int strip_width, int rank, int world) {
     float m = -__int_as_float(0x7f800000);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (strip_width > 0 && (int)((i / column_floats) / strip_width) % world != rank) continue;
         m = fmaxf(m, __ldg(rgb + i));
+    }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     __shared__ float s[8];
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
@@ -59,7 +64,8 @@ __device__ inline unsigned char to_byte(float c, float inv_gamma, float mx, uint
 // scanline (contiguous in the bitmap).
 __global__ void __launch_bounds__(256) tonemap_kernel(const float *__restrict__ rgb, int X, int Y, float inv_gamma,
                                                       const float *__restrict__ max_ptr, float max_value,
-                                                      uint32_t k0, uint32_t k1, unsigned char *__restrict__ out, int stride) {
+                                                      uint32_t k0, uint32_t k1, unsigned char *__restrict__ out, int stride,
+                                                      int strip_width, int rank, int world) {
     __shared__ unsigned char tile[32][32 * 3 + 4];
     const float raw_max = max_ptr ? *max_ptr : max_value;
     const float mx = fmaxf(0.01f, raw_max);  // |> MathF.max 0.01f
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const float *__restrict__ 
     for (int k = threadIdx.x; k < 32 * 32; k += 256) {
         const int tx = k >> 5, ty = k & 31;  // ty fastest: consecutive threads read consecutive y
         const int x = x0 + tx, y = y0 + ty;
-        if (x < X && y < Y) {
+        if (x < X && y < Y && (strip_width <= 0 || (x / strip_width) % world == rank)) {
             const long long idx = (long long)x * Y + y;
             uint32_t c[4] = {(uint32_t)idx, (uint32_t)((unsigned long long)idx >> 32), 0u, 0u};
             ft_philox4x32_10(c, k0, k1);
@@ -81,7 +87,7 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const float *__restrict__ 
     for (int k = threadIdx.x; k < 32 * 32; k += 256) {
         const int ty = k >> 5, tc = k & 31;  // tc fastest: consecutive threads write consecutive columns
         const int y = y0 + ty, x = x0 + (31 - tc);  // mirrored within the tile
-        if (x < X && y < Y) {
+        if (x < X && y < Y && (strip_width <= 0 || (x / strip_width) % world == rank)) {  // other ranks' columns stay untouched
             const int col = X - 1 - x;  // scanline r = y, column c = X-1-x
             unsigned char *p = out + (long long)y * stride + 3ll * col;
             p[0] = tile[ty][3 * (31 - tc) + 0];
@@ -93,22 +99,25 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const float *__restrict__ 
 
 }  // namespace
 
-cudaError_t launch_image_max(const float *rgb, long long n_floats, float *d_max, cudaStream_t stream) {
+cudaError_t launch_image_max(const float *rgb, long long n_floats, float *d_max, cudaStream_t stream, int column_floats,
+                             int strip_width, int rank, int world) {
     const float ninf = -__builtin_huge_valf();
     cudaError_t e = cudaMemcpyAsync(d_max, &ninf, sizeof(float), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess || n_floats <= 0) return e;
     long long blocks = (n_floats + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    image_max_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rgb, n_floats, d_max);
+    image_max_kernel<<<(unsigned)blocks, 256, 0, stream>>>(rgb, n_floats, d_max, column_floats > 0 ? column_floats : 1, strip_width, rank,
+                                                           world > 0 ? world : 1);
     return cudaGetLastError();
 }
 
 cudaError_t launch_tonemap(const float *rgb, int X, int Y, float gamma, const float *d_max, float max_value,
-                           unsigned long long seed, unsigned char *out, int stride, cudaStream_t stream) {
+                           unsigned long long seed, unsigned char *out, int stride, cudaStream_t stream, int strip_width, int rank,
+                           int world) {
     if (X <= 0 || Y <= 0) return cudaSuccess;
     dim3 grid((unsigned)((X + 31) / 32), (unsigned)((Y + 31) / 32));
     tonemap_kernel<<<grid, 256, 0, stream>>>(rgb, X, Y, 1.0f / gamma, d_max, max_value, (uint32_t)seed,
-                                             (uint32_t)(seed >> 32), out, stride);
+                                             (uint32_t)(seed >> 32), out, stride, strip_width, rank, world > 0 ? world : 1);
     return cudaGetLastError();
 }
 

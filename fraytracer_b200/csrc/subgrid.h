@@ -15,7 +15,8 @@ struct SubGridJob {
     long long max_subcells;  // budget: the resolution is halved until cells * res^3 fits
 };
 struct SubGrid {
-    uint32_t *hdr = nullptr, *idx = nullptr;  // device arrays (cudaFree by the owner); null when no sub-grid was built
+    uint2 *hdr = nullptr;  // device arrays (cudaFree by the owner); null when no sub-grid was built
+    uint32_t *idx = nullptr;
     int res = 0;
     long long n_subcells = 0, n_entries = 0, bytes = 0;
     float threshold = 0.f, build_ms = 0.f;

@@ -70,28 +70,28 @@ __global__ void __launch_bounds__(128) sub_count_kernel(const __grid_constant__ 
         n += !(prim_distance<false>(S, e.word(), e.bound(), c, acc) > lim);  // NaN distances are kept
     }
     dmin_out[t] = dmin;
-    count[t] = n > 255u ? 0u : n;  // too long to encode: no list, sub_lookup leaves such sub-cells to the scan
+    // what the index array holds: candidates 1 .. n-1 (the nearest one lives in the header); n > 255 is too long to encode:
+    // no list, sub_lookup leaves such sub-cells to the scan
+    count[t] = (n > 255u || n == 0u) ? 0u : n - 1u;
 }
 
 // pass 2: the list, nearest first (ties by list position)
 __global__ void __launch_bounds__(128) sub_fill_kernel(const __grid_constant__ DevScene S, const __grid_constant__ SubParams P,
                                                        const float *__restrict__ dmin_in, const uint32_t *__restrict__ count,
-                                                       const uint32_t *__restrict__ offset, uint32_t *__restrict__ hdr,
+                                                       const uint32_t *__restrict__ offset, uint2 *__restrict__ hdr,
                                                        uint32_t *__restrict__ idx_out) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.n_sub) return;
-    const uint32_t n = count[t], off = offset[t];
-    hdr[t] = (off << 8) | n;
-    if (n == 0u) return;
+    const uint32_t off = offset[t];
     uint32_t cell;
     const V3 c = sub_centre(P, t, cell);
     const uint32_t first = __float_as_uint(ld4(S.cells + P.cell_base + cell).w);
     Acc acc{0ull, 0ull};
     const float lim = dmin_in[t] + P.thr;
     float key[255];
-    uint32_t *out = idx_out + off;
+    uint32_t out[255];
     uint32_t m = 0;
-    for (uint32_t k = first; m < n; k++) {
+    for (uint32_t k = first; m < 255u; k++) {
         const Entry e = ld_entry(S, k);
         if (e.lb() == __int_as_float(0x7f800000)) break;
         const float d = prim_distance<false>(S, e.word(), e.bound(), c, acc);
@@ -107,6 +107,11 @@ __global__ void __launch_bounds__(128) sub_fill_kernel(const __grid_constant__ D
         out[j] = k;
         m++;
     }
+    // the count pass and this pass see the same distances, so m - 1 == count[t] whenever the list is encodable; a list the
+    // count pass refused (more than 255 candidates) stays empty
+    const bool ok = m > 0u && m - 1u == count[t];
+    hdr[t] = ok ? make_uint2((off << 8) | m, out[0]) : make_uint2(0u, 0u);
+    for (uint32_t j = 1; ok && j < m; j++) idx_out[off + j - 1u] = out[j];
 }
 
 }  // namespace ft_sub
@@ -124,7 +129,8 @@ __global__ void __launch_bounds__(128) sub_fill_kernel(const __grid_constant__ D
 cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out, std::string *err) {
     *out = SubGrid{};
     float *d_dmin = nullptr;
-    uint32_t *d_count = nullptr, *d_off = nullptr, *d_hdr = nullptr, *d_idx = nullptr;
+    uint32_t *d_count = nullptr, *d_off = nullptr, *d_idx = nullptr;
+    uint2 *d_hdr = nullptr;
     void *d_tmp = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&]() {
@@ -178,7 +184,7 @@ cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out
             cleanup();
             return cudaSuccess;  // no sub-grid: the scan always runs
         }
-        SG_CU(cudaMalloc(&d_hdr, sizeof(uint32_t) * (size_t)n_sub));
+        SG_CU(cudaMalloc(&d_hdr, sizeof(uint2) * (size_t)n_sub));
         SG_CU(cudaMalloc(&d_idx, sizeof(uint32_t) * (size_t)std::max(1u, total)));
         ft_sub::sub_fill_kernel<<<blocks, 128>>>(S, P, d_dmin, d_count, d_off, d_hdr, d_idx);
         SG_CU(cudaGetLastError());
@@ -188,8 +194,8 @@ cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out
         out->idx = d_idx;
         out->res = res;
         out->n_subcells = n_sub;
-        out->n_entries = total;
-        out->bytes = (long long)sizeof(uint32_t) * (n_sub + std::max(1u, total));
+        out->n_entries = (long long)total + n_sub;  // the nearest candidate of every sub-cell lives in its header
+        out->bytes = (long long)sizeof(uint2) * n_sub + (long long)sizeof(uint32_t) * std::max(1u, total);
         out->threshold = P.thr;
         cudaEventElapsedTime(&out->build_ms, e0, e1);
         cleanup();

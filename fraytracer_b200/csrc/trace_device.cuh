@@ -433,29 +433,34 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, V3 c, uint32
     const int R = S.sub_res;
     const int sx = (int)(fx * S.sub_res_f), sy = (int)(fy * S.sub_res_f), sz = (int)(fz * S.sub_res_f);
     const uint32_t cell_local = ci - __float_as_uint(S.chain_g1.w);
-    const uint32_t hdr = __ldg(S.sub_hdr + ((size_t)cell_local * (uint32_t)(R * R * R) + (uint32_t)((sx * R + sy) * R + sz)));
-    const uint32_t n = hdr & 255u;
+    // header: {(first << 8) | count, the nearest candidate}: the first record's load depends on one load only
+    const uint2 hdr = __ldg(S.sub_hdr + ((size_t)cell_local * (uint32_t)(R * R * R) + (uint32_t)((sx * R + sy) * R + sz)));
+    const uint32_t n = hdr.x & 255u;
     if (n == 0u) return false;  // no list for this sub-cell (too long to encode): the scan runs
     add_flops<COUNT>(acc, 9);
-    const uint32_t *lp = S.sub_idx + (hdr >> 8);
+    const uint32_t *lp = S.sub_idx + (hdr.x >> 8);  // candidates 1 .. n-1
     float M = __int_as_float(0x7f800000);
     uint32_t best = 0xffffffffu;
-    for (uint32_t k = 0; k < n; k++) {
-        const uint32_t idx = __ldg(lp + k);
+    uint32_t idx = hdr.y;
+    for (uint32_t k = 0;;) {
         const Entry e = ld_entry(S, idx);
+        const bool more = ++k < n;
         add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
-        if (certain_fail_up(M, e.bound(), e.b.w, p)) continue;
-        float d;
-        if (FT_WORD_KIND(e.word()) == FT_K_SPHERE) {
-            d = distance(xyz(e.bound()), p) - e.b.y;  // SdfForm.fs:127-129, the reference's operation order
-        } else {
-            d = prim_distance<COUNT>(S, e.word(), e.bound(), p, acc);
+        if (!certain_fail_up(M, e.bound(), e.b.w, p)) {
+            float d;
+            if (FT_WORD_KIND(e.word()) == FT_K_SPHERE) {
+                d = distance(xyz(e.bound()), p) - e.b.y;  // SdfForm.fs:127-129, the reference's operation order
+            } else {
+                d = prim_distance<COUNT>(S, e.word(), e.bound(), p, acc);
+            }
+            add_flops<COUNT>(acc, FLOPS_MINMAX);
+            if (d < M || (d == M && idx < best)) {
+                M = d;
+                best = idx;
+            }
         }
-        add_flops<COUNT>(acc, FLOPS_MINMAX);
-        if (d < M || (d == M && idx < best)) {
-            M = d;
-            best = idx;
-        }
+        if (!more) break;
+        idx = __ldg(lp + k - 1u);
     }
     if (best == 0xffffffffu) return false;  // nothing comparable (NaN positions): the scan decides
     // certificates on the arg-min

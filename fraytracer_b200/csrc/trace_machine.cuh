@@ -33,6 +33,12 @@ constexpr int MB = 128;             // threads per CTA
 #ifndef FT_LONG_BATCH
 #define FT_LONG_BATCH 1  // run the long class as soon as any lane has one (measured best with whole-tile lockstep)
 #endif
+#ifndef FT_TILE_STORE
+#define FT_TILE_STORE 1  // whole tiles leave as 128-bit stores (RenderJob / GatherJob::store_tile)
+#endif
+#ifndef FT_REFILL_MIN
+#define FT_REFILL_MIN 32  // idle lanes that trigger a refill (see the refill block of machine_kernel)
+#endif
 constexpr int FT_CHUNK = 32;        // work items per global-counter grab (one tile of 4x8 pixels)
 
 enum : int {
@@ -50,7 +56,8 @@ enum : int {
 // ---- work sources -----------------------------------------------------------------------------------------
 // Image.render: item i -> pixel, tiles of 4 (x) by 8 (y) pixels, tiles ordered along y first so that a chunk
 // of 8 tiles is a 4 x 64 pixel block of the x-major FColor[X,Y] output.
-struct RenderJob {
+template <bool TILE>
+struct RenderJobT {
     ft_camera cam;
     RenderParams P;
     float *out_rgb;
@@ -105,7 +112,34 @@ struct RenderJob {
         out_rgb[3ll * slot + 2] = b;
         if (out_leaf) out_leaf[slot] = leaf;
     }
+    // Whole-tile store (FT_TILE_STORE): `sh` holds the tile's 32 pixels in tile order (lane = column * 8 + row, 3 floats each),
+    // i.e. the four 96-byte column runs of the x-major FColor[X,Y] back to back; `valid` marks the lanes that hold a pixel.
+    // A complete, 16-byte-aligned tile leaves as 24 128-bit stores -- full 32-byte sectors for mapped host memory and peer
+    // framebuffers (PCIe / NVLink write efficiency) -- anything else pixel by pixel.
+    static constexpr bool kTileStore = TILE;  // launch_render picks it for destinations behind PCIe (mapped host memory)
+    __device__ __forceinline__ int *out_leaf_ptr() const { return out_leaf; }
+    __device__ __forceinline__ void store_tile(long long base_item, const float *sh, unsigned valid, int lane) const {
+        const long long tile = base_item >> 5;
+        const int tiles_y = (P.height + FT_TILE_H - 1) / FT_TILE_H;
+        const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
+        const int xc0 = tx * FT_TILE_W, y0 = ty * FT_TILE_H;
+        if (valid == 0xffffffffu && (P.height & 3) == 0 && ((uintptr_t)out_rgb & 15) == 0) {
+            if (lane < 24) {
+                const int col = lane / 6, part = lane - col * 6;
+                const float4 v = *reinterpret_cast<const float4 *>(sh + col * 24 + part * 4);
+                *reinterpret_cast<float4 *>(out_rgb + 3ll * ((long long)(xc0 + col) * P.height + y0) + part * 4) = v;
+            }
+        } else if ((valid >> lane) & 1u) {
+            const long long slot = (long long)(xc0 + lane / FT_TILE_H) * P.height + (y0 + lane % FT_TILE_H);
+            out_rgb[3 * slot + 0] = sh[3 * lane + 0];
+            out_rgb[3 * slot + 1] = sh[3 * lane + 1];
+            out_rgb[3 * slot + 2] = sh[3 * lane + 2];
+        }
+    }
 };
+
+typedef RenderJobT<false> RenderJob;      // device-memory destination: plain per-pixel stores (2-3 % faster on the device)
+typedef RenderJobT<true> RenderTileJob;   // mapped host memory: whole tiles as 128-bit stores
 
 // Image.render of this rank's column strips, fused with the framebuffer gather: every finished
 // pixel is stored at its final x-major position in the framebuffer of EVERY destination -- the rank's own and its
@@ -158,6 +192,39 @@ struct GatherJob {
             out[2] = b;
         }
     }
+    // see RenderJob::store_tile; the tile's four columns are consecutive image columns when the strip width is a multiple of 4
+    static constexpr bool kTileStore = true;
+    __device__ __forceinline__ int *out_leaf_ptr() const { return nullptr; }
+    __device__ __forceinline__ void store_tile(long long base_item, const float *sh, unsigned valid, int lane) const {
+        const long long tile = base_item >> 5;
+        const int tiles_y = (P.height + FT_TILE_H - 1) / FT_TILE_H;
+        const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
+        const int xl0 = tx * FT_TILE_W, y0 = ty * FT_TILE_H;
+        const int strip = xl0 / P.strip_width;
+        const int x0 = (strip * P.world + P.rank) * P.strip_width + (xl0 - strip * P.strip_width);  // image column of the tile
+        if (valid == 0xffffffffu && (P.height & 3) == 0 && (P.strip_width & 3) == 0) {
+            const int col = lane / 6, part = lane - col * 6;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < 24) v = *reinterpret_cast<const float4 *>(sh + col * 24 + part * 4);
+            const long long at = 3ll * ((long long)(x0 + col) * P.height + y0) + part * 4;
+            for (int k = 0; k < n_dst; k++)
+                if (lane < 24 && ((uintptr_t)dst[k] & 15) == 0) *reinterpret_cast<float4 *>(dst[k] + at) = v;
+                else if (lane < 24) {
+                    dst[k][at + 0] = v.x; dst[k][at + 1] = v.y; dst[k][at + 2] = v.z; dst[k][at + 3] = v.w;
+                }
+        } else if ((valid >> lane) & 1u) {
+            const int xl = xl0 + lane / FT_TILE_H;
+            const int st2 = xl / P.strip_width;
+            const long long x = (long long)(st2 * P.world + P.rank) * P.strip_width + (xl - st2 * P.strip_width);
+            const long long slot = x * P.height + (y0 + lane % FT_TILE_H);
+            for (int k = 0; k < n_dst; k++) {
+                float *out = dst[k] + 3 * slot;
+                out[0] = sh[3 * lane + 0];
+                out[1] = sh[3 * lane + 1];
+                out[2] = sh[3 * lane + 2];
+            }
+        }
+    }
 };
 
 // batched SdfScene.trace: 32-byte ft_ray records read as two LDG.128
@@ -196,6 +263,9 @@ struct RaysJob {
         if (out_steps) out_steps[slot] = steps;
         if (out_shadow) out_shadow[slot] = shadow;
     }
+    static constexpr bool kTileStore = false;
+    __device__ __forceinline__ int *out_leaf_ptr() const { return nullptr; }
+    __device__ __forceinline__ void store_tile(long long, const float *, unsigned, int) const {}
 };
 
 // ESCAPE: resolve rays by the escape proof (identical colours / leaf / shadow mask; the step counters then
@@ -218,8 +288,18 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
 #define FT_EPS (Job::kUniformEps ? job.uniform_eps() : eps_lane)
     int steps = 0, primary_steps = 0, light = 0, leaf_obj = 0;
     unsigned shadow_mask = 0;
+    // the warp's current chunk (uniform)
+    long long chunk_next = 0;
+    int chunk_left = 0;
+    bool exhausted = false;
     // per-lane totals for the stats flush
     // event counters live in shared memory (one row per warp, RED.shared on the rare transition paths)
+    // FT_TILE_STORE: finished pixels wait in the warp's shared-memory row until the whole tile leaves at once (store_tile)
+    constexpr bool TILE_STORE = FT_TILE_STORE && Job::kTileStore && FT_REFILL_MIN >= 32;
+    __shared__ __align__(16) float sh_tile[TILE_STORE ? MB / 32 : 1][TILE_STORE ? 96 : 4];
+    float *const wtile = sh_tile[TILE_STORE ? (threadIdx.x >> 5) : 0];
+    long long tile_base = -1;  // the chunk whose pixels are staged (uniform)
+    bool has_pix = false;
     __shared__ unsigned sh_stats[MB / 32][4];
     unsigned *const wstats = sh_stats[threadIdx.x >> 5];
     if (lane < 4) wstats[lane] = 0u;
@@ -228,20 +308,53 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
 
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
-        // Whole tiles in lockstep (measured 1.5-2.9x faster than per-lane refill: adjacent pixels share cells, candidate lists
-        // and trip counts): the warp takes a new 32-item chunk only when all its lanes are idle, so no chunk cursor has to
-        // survive between iterations.  One atomic per chunk.
-        if (__all_sync(FULL, phase == PH_FETCH)) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)FT_CHUNK);
-            base = __shfl_sync(FULL, base, 0);
-            if ((long long)base >= total) break;
-            const long long mine = (long long)base + lane;
-            if (mine < total && job.load(mine, d0, o, d, len, eps_lane, slot, steps)) {
-                add_flops<COUNT>(acc, FLOPS_PRIMARY_RAY);
-                phase = PH_PRIMARY;
+        // The warp draws 32-item chunks (one 4 x 8 pixel tile) from one global counter -- one atomic per chunk -- and deals the
+        // chunk's items to idle lanes.  FT_REFILL_MIN idle lanes trigger a refill: 32 = whole tiles in lockstep (a new tile only
+        // when every lane is idle), smaller values let finished lanes start on the next tile's pixels while their neighbours
+        // are still marching (a warp then holds pixels of two or three neighbouring tiles).
+        {
+            unsigned idle = __ballot_sync(FULL, phase == PH_FETCH);
+            if (idle == FULL || (__popc(idle) >= FT_REFILL_MIN && !(exhausted && chunk_left == 0))) {
+                if (TILE_STORE && idle == FULL && tile_base >= 0) {  // the previous tile is complete: it leaves as a whole
+                    __syncwarp();
+                    job.store_tile(tile_base, wtile, __ballot_sync(FULL, has_pix), lane);
+                    __syncwarp();
+                    tile_base = -1;
+                    has_pix = false;
+                }
+                while (idle) {
+                    if (chunk_left == 0) {
+                        if (exhausted) break;
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)FT_CHUNK);
+                        base = __shfl_sync(FULL, base, 0);
+                        if ((long long)base >= total) {
+                            exhausted = true;
+                            break;
+                        }
+                        chunk_next = (long long)base;
+                        chunk_left = FT_CHUNK;
+                        if (TILE_STORE) tile_base = (long long)base;
+                    }
+                    const int want = __popc(idle), take = want < chunk_left ? want : chunk_left;
+                    const int r = __popc(idle & ((1u << lane) - 1u));
+                    if (phase == PH_FETCH && r < take) {
+                        const long long mine = chunk_next + r;
+                        if (mine < total && job.load(mine, d0, o, d, len, eps_lane, slot, steps)) {
+                            add_flops<COUNT>(acc, FLOPS_PRIMARY_RAY);
+                            phase = PH_PRIMARY;
+                        }
+                    }
+                    chunk_next += take;
+                    chunk_left -= take;
+                    idle = __ballot_sync(FULL, phase == PH_FETCH);  // padding items leave their lane idle: it draws again ...
+                    if (FT_REFILL_MIN >= 32 && idle != FULL) break;  // ... but whole-tile lockstep never mixes two tiles in a warp
+                }
+                if (idle == FULL) {
+                    if (exhausted) break;  // no work left anywhere
+                    continue;
+                }
             }
-            if (__all_sync(FULL, phase == PH_FETCH)) continue;  // a chunk of padding items only
         }
         // ------------------------------------------------------------------ march pre-check (SdfForm.fs:94)
         // a ray whose Length is exhausted (or that hit the watchdog) ends as a miss without another evaluation
@@ -397,7 +510,15 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                 }
             }
             if (finish) {
-                job.store(slot, r, g, b, leaf, primary_steps, shadow_mask);
+                if (TILE_STORE) {
+                    wtile[3 * lane + 0] = r;
+                    wtile[3 * lane + 1] = g;
+                    wtile[3 * lane + 2] = b;
+                    has_pix = true;
+                    if (job.out_leaf_ptr()) job.out_leaf_ptr()[slot] = leaf;
+                } else {
+                    job.store(slot, r, g, b, leaf, primary_steps, shadow_mask);
+                }
                 phase = PH_FETCH;
             }
         }
@@ -416,7 +537,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
             ev += __shfl_xor_sync(FULL, ev, k);
         }
     }
-    if (lane == 0) {
+    if (lane == 0 && stats) {  // stats == nullptr: an asynchronous launch whose caller asked for no counters
         const unsigned w = (blockIdx.x * (MB / 32) + (threadIdx.x >> 5)) & (FT_STAT_SLOTS - 1);
         unsigned long long *s = stats + w * FT_STAT_STRIDE;
         if (hits) atomicAdd(s + FT_STAT_HITS, (unsigned long long)hits);

@@ -48,6 +48,12 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float *out, int iters, f
 }
 
 cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate) {
+    // the caller's current device is restored on every exit (the host thread may be torch's)
+    struct Restore {
+        int prev = -1;
+        Restore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+        ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+    } restore;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
     cudaDeviceProp prop;
@@ -56,9 +62,12 @@ cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estim
     float *d = nullptr;
     e = cudaMalloc(&d, 256);
     if (e != cudaSuccess) return e;
-    cudaEvent_t a, b;
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
+    cudaEvent_t a = nullptr, b = nullptr;
+    if ((e = cudaEventCreate(&a)) != cudaSuccess || (e = cudaEventCreate(&b)) != cudaSuccess) {
+        if (a) cudaEventDestroy(a);
+        cudaFree(d);
+        return e;
+    }
     const int blocks = prop.multiProcessorCount * 8, iters = 4096;
     float best = 0.f;
     for (int rep = 0; rep < 6; rep++) {

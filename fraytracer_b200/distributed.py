@@ -232,6 +232,32 @@ class DistributedRenderer:
         self.torch.cuda.current_stream().synchronize()
         return host
 
+    # ---- Image.toColors + Image.toBitmap over the ranks (Image.fs:37-72)
+    def to_bitmap(self, frame, gamma: float, seed: int):
+        """`frame`: the full FColor[X,Y] device tensor every rank holds after `render`.  Every rank takes the maximum over the
+        columns of ITS strips (Array2D.maxWith, Image.fs:40-43), the maxima meet in an all-reduce(MAX), every rank tonemaps
+        its own strips into a zeroed bitmap and -- each byte being written by exactly one rank -- an all-reduce(MAX) over
+        the bitmaps assembles it.  Returns (uint8 [Y, X, 3] device tensor of top-down B,G,R scanlines in the reference's
+        pixel order, identical on every rank; the raw maximum as a 1-element float32 device tensor)."""
+        torch = self.torch
+        X, Y = self.size.X, self.size.Y
+        lib = self.tracer.lib
+        stream = torch.cuda.current_stream().cuda_stream
+        st = C.c_void_p(stream) if stream else None
+        dev = frame.device
+        mx = torch.empty(1, dtype=torch.float32, device=dev)
+        bitmap = torch.zeros((Y, X, 3), dtype=torch.uint8, device=dev)
+        A.check(lib.ft_image_max_strips_device(C.c_void_p(frame.data_ptr()), X, Y, self.strip_width, self.rank, self.world,
+                                               C.c_void_p(mx.data_ptr()), st))
+        if self.world > 1:
+            self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX, group=self.group)
+        A.check(lib.ft_tonemap_strips_device(C.c_void_p(frame.data_ptr()), X, Y, self.strip_width, self.rank, self.world,
+                                             C.c_float(gamma), C.c_void_p(mx.data_ptr()), C.c_float(0.0), C.c_uint64(seed),
+                                             C.c_void_p(bitmap.data_ptr()), 3 * X, st))
+        if self.world > 1:
+            self.dist.all_reduce(bitmap, op=self.dist.ReduceOp.MAX, group=self.group)
+        return bitmap, mx
+
     def close(self):
         """release the IPC mappings and the shared framebuffers (after a barrier: no peer may still be writing)"""
         if getattr(self, "_host", None) is not None:
@@ -253,7 +279,13 @@ class DistributedRenderer:
                 self.tracer.lib.ft_device_free(self.tracer.device, p)
             self._owned, self._imported, self.frames = [], [], []
 
-    def render(self, camera, epsilon: float, length: float, flags: int = 0):
+    def render(self, camera, epsilon: float, length: float, flags: int = 0, copy: bool = False):
+        """One frame on all ranks; returns the full FColor[X,Y] as a device tensor on every rank.
+
+        Lifetime of the returned tensor: with gather="p2p" it is a view of one of the rank's two IPC framebuffers (frame
+        parity), which the peers overwrite two `render` calls later -- read it on the current stream before the second next
+        call, or pass copy=True to get a private clone.  With gather="nccl" (and with one rank) it is `self.final`, owned by
+        this renderer and overwritten by the next call."""
         torch = self.torch
         stream = torch.cuda.current_stream().cuda_stream
         X, Y = self.size.X, self.size.Y
@@ -264,7 +296,7 @@ class DistributedRenderer:
                                              strip_width=self.strip_width, rank=self.rank, world=self.world)
             self.dist.all_reduce(self._done, group=self.group)  # every writer's kernel has finished: the frame is complete
             self.final = self.frames[parity]
-            return self.final
+            return self.final.clone() if copy else self.final
         if self.world == 1:
             self.tracer.render_device(camera, self.size, epsilon, length, self.final.data_ptr(), stream=stream,
                                       flags=flags, strip_width=self.strip_width, rank=0, world=1)

@@ -82,9 +82,14 @@ def default_lights():  # Program.fs:79-82
     ]
 
 
+# Program.fs:16-22 -- every workload uses the reference's camera; kept as plain numbers so that the oracle can build the same
+# camera through its own Lens.create / Camera.lookAt
+CAMERA_SPEC = dict(Position=(0.0, 0.0, -10.0), LookAt=(0.0, 0.0, 0.0), Up=(0.0, 1.0, 0.0), FieldOfView=60.0)
+
+
 def default_camera() -> Camera:  # Program.fs:16-22
-    return Camera.lookAt(Position=(0.0, 0.0, -10.0), LookAt=(0.0, 0.0, 0.0), Up=(0.0, 1.0, 0.0),
-                         Lens=Lens.create(60.0))
+    return Camera.lookAt(Position=CAMERA_SPEC["Position"], LookAt=CAMERA_SPEC["LookAt"], Up=CAMERA_SPEC["Up"],
+                         Lens=Lens.create(CAMERA_SPEC["FieldOfView"]))
 
 
 @dataclass

@@ -424,6 +424,17 @@ FT_API int ft_render_cloud_gather_device(ft_scene *scene, const ft_camera *camer
                                          int32_t world, float *const *d_dst, int32_t n_dst, void *stream,
                                          ft_render_stats *stats);
 
+/* The same two steps for a frame cut over several GPUs: every rank reduces and tonemaps only
+ * the columns of the strips it owns (strip s -> rank s % world) of the full-size FColor[X,Y] it holds; the ranks'
+ * maxima meet in an all-reduce(MAX) (Array2D.maxWith, Image.fs:40-43), and since every byte of the bitmap is written
+ * by exactly one rank, an all-reduce(MAX) over the zero-initialised bitmaps assembles it
+ * (fraytracer_b200/distributed.py DistributedRenderer.to_bitmap).  world = 1 equals the whole-frame calls.         */
+FT_API int ft_image_max_strips_device(const float *d_rgb, int32_t width, int32_t height, int32_t strip_width,
+                                      int32_t rank, int32_t world, float *d_max, void *stream);
+FT_API int ft_tonemap_strips_device(const float *d_rgb, int32_t width, int32_t height, int32_t strip_width,
+                                    int32_t rank, int32_t world, float gamma, const float *d_max, float max_value,
+                                    uint64_t seed, uint8_t *d_out_bgr, int32_t stride, void *stream);
+
 /* ---- post-process: Image.toColors / toBitmap / saveBitmap (Image.fs:37-90) -- */
 /* max over the n_floats values of an FColor image (Array2D.Parallel.maxWith FColor.getMaxColor, Image.fs:40-42);
  * d_max is one DEVICE float.  With several GPUs, all-reduce(max) it before ft_tonemap_device.               */

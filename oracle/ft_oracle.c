@@ -37,6 +37,19 @@
 
 #define FTO_API __attribute__((visibility("default")))
 
+/* FTO_ASSUME: build-time switches for the three assumptions about code that lives OUTSIDE /root/reference
+ * and that nothing reference-held pins.  0 (the default, what every parity claim in this repository means) = the .NET 6
+ * in-box System.Numerics and Array.Sort.  tests/test_assumption_sensitivity.py builds one library per switch and reports how
+ * many pixels of the reference scenes each assumption moves, so that a maintainer with .NET knows what to check first.
+ *   bit 0  Vector3 / float32 and Vector3.Normalize multiply by the reciprocal (System.Numerics.Vectors 4.5.0 / .NET Core 2.x:
+ *          `float invDiv = 1.0f / value2`) instead of dividing per component (.NET Core 3.0+)
+ *   bit 1  Vector3.Dot reduces as x*x' + (y*y' + z*z') instead of (x*x' + y*y') + z*z' (dpps)
+ *   bit 2  Array.sortInPlaceBy keeps equal LowerBounds in their original order (a stable sort) instead of the introsort's  */
+#ifndef FTO_ASSUME
+#define FTO_ASSUME 0
+#endif
+FTO_API int fto_assumptions(void) { return FTO_ASSUME; }
+
 /* ------------------------------------------------------------------------ */
 /* System.Numerics restatement                                               */
 /* ------------------------------------------------------------------------ */
@@ -48,9 +61,17 @@ static inline v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline v3 vmul(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline v3 vdivv(v3 a, v3 b) { return V(a.x / b.x, a.y / b.y, a.z / b.z); }
 static inline v3 vscale(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+#if FTO_ASSUME & 1
+static inline v3 vdiv(v3 a, float s) { float inv = 1.0f / s; return V(a.x * inv, a.y * inv, a.z * inv); }
+#else
 static inline v3 vdiv(v3 a, float s) { return V(a.x / s, a.y / s, a.z / s); }
+#endif
 static inline v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
+#if FTO_ASSUME & 2
+static inline float vdot(v3 a, v3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+#else
 static inline float vdot(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+#endif
 static inline float vlen2(v3 a) { return vdot(a, a); }
 static inline float vlen(v3 a) { return sqrtf(vdot(a, a)); }
 static inline float vdist(v3 a, v3 b) { return vlen(vsub(a, b)); }
@@ -229,6 +250,10 @@ static void gi_intro_sort(gitem *a, int n, int depth_limit) {
 }
 static void dotnet_sort_by_lower_bound(gitem *a, int n) {
     if (n < 2) return;
+#if FTO_ASSUME & 4
+    gi_insertion_sort(a, n); /* stable: equal keys keep their order (strict < moves) */
+    return;
+#endif
     int left = 0;
     for (int i = 0; i < n; i++)
         if (isnan(a[i].lb)) { gi_swap(a, left, i); left++; }

@@ -35,15 +35,25 @@ def build(force: bool = False):
     return LIB_PATH
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def assumption_library(bits: int) -> str:
+    """path of the oracle built with FTO_ASSUME=bits (ft_oracle.c: the unpinned assumptions about System.Numerics / Array.Sort);
+    built on demand"""
+    path = os.path.join(HERE, f"libft_oracle_assume{int(bits)}.so")
+    src = os.path.join(HERE, "ft_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "-s", os.path.basename(path)])
+    return path
+
+
+def lib(path: str | None = None):
+    key = path or LIB_PATH
+    if key not in _libs:
+        if path is None and not os.path.exists(LIB_PATH):
             build()
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(key)
         vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
         P = C.POINTER
         L.fto_random_create.restype = vp
@@ -81,8 +91,9 @@ def lib():
                                           C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.fto_to_bitmap.restype = f32
         L.fto_to_bitmap.argtypes = [vp, C.c_int, C.c_int, f32, C.c_uint64, vp, C.c_int]
-        _lib = L
-    return _lib
+        L.fto_assumptions.restype = C.c_int
+        _libs[key] = L
+    return _libs[key]
 
 
 def _ptr(a):
@@ -124,34 +135,35 @@ def camera_look_at(position, look_at, up, nps) -> A.ft_camera:
 class OracleScene:
     """CPU restatement of a scene, built from the same flat description the product takes."""
 
-    def __init__(self, description):
-        """description: fraytracer_b200.SceneDescription"""
+    def __init__(self, description, library: str | None = None):
+        """description: fraytracer_b200.SceneDescription; library: another build of the oracle (assumption_library)"""
+        self._L = lib(library)
         self.description = description
         self.h = C.c_void_p()
         err = C.create_string_buffer(256)
-        st = lib().fto_scene_create(C.byref(description.desc), C.byref(self.h), err, 256)
+        st = self._L.fto_scene_create(C.byref(description.desc), C.byref(self.h), err, 256)
         if st != 0:
             raise A.FrayTracerError(st, err.value.decode())
 
     def __del__(self):
         if getattr(self, "h", None) and self.h.value:
-            lib().fto_scene_destroy(self.h)
+            self._L.fto_scene_destroy(self.h)
             self.h = C.c_void_p()
 
     def set_step_cap(self, cap):
-        lib().fto_scene_set_step_cap(self.h, int(cap))
+        self._L.fto_scene_set_step_cap(self.h, int(cap))
 
     def grids(self):
         res = []
-        for g in range(lib().fto_grid_count(self.h)):
+        for g in range(self._L.fto_grid_count(self.h)):
             gi = A.ft_grid_info()
-            lib().fto_grid_info(self.h, g, C.byref(gi))
+            self._L.fto_grid_info(self.h, g, C.byref(gi))
             nc = gi.count[0] * gi.count[1] * gi.count[2]
             centers = np.empty((nc, 3), np.float32)
             begin = np.empty(nc + 1, np.int64)
             lb = np.empty(gi.n_entries, np.float32)
             item = np.empty(gi.n_entries, np.int32)
-            lib().fto_grid_read(self.h, g, _ptr(centers), _ptr(begin), _ptr(lb), _ptr(item))
+            self._L.fto_grid_read(self.h, g, _ptr(centers), _ptr(begin), _ptr(lb), _ptr(item))
             res.append(dict(count=tuple(gi.count), aabb_min=np.array(gi.aabb_min, np.float32),
                             cell_size=np.array(gi.cell_size, np.float32),
                             cell_size_inv=np.array(gi.cell_size_inv, np.float32),
@@ -168,7 +180,7 @@ class OracleScene:
         steps = np.zeros((X, Y), np.int32)
         shadow = np.zeros((X, Y), np.uint32)
         ctr = fto_counters()
-        st = lib().fto_render(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), x_begin, x_end,
+        st = self._L.fto_render(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), x_begin, x_end,
                               x_stride, threads, _ptr(rgb), _ptr(leaf), _ptr(steps), _ptr(shadow),
                               C.byref(ctr) if counters else None)
         assert st == 0
@@ -183,7 +195,7 @@ class OracleScene:
         (only the columns x_begin, x_begin + x_stride, ... < x_end of the full-size array are written)"""
         cam = camera.to_c() if hasattr(camera, "to_c") else camera
         rgb = np.zeros((X, Y, 3), np.float32)
-        st = lib().fto_render_spectral(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), n_wavelengths,
+        st = self._L.fto_render_spectral(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), n_wavelengths,
                                        max_bounces, C.c_uint64(seed), x_begin, X if x_end is None else x_end, x_stride,
                                        threads or os.cpu_count() or 1, _ptr(rgb))
         assert st == 0, st
@@ -197,7 +209,7 @@ class OracleScene:
         cp = cloud.to_c()
         rgb = np.zeros((X, Y, 3), np.float32)
         ctr = np.zeros(3, np.int64)
-        st = lib().fto_render_cloud(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), C.byref(cp), spp,
+        st = self._L.fto_render_cloud(self.h, C.byref(cam), X, Y, C.c_float(eps), C.c_float(length), C.byref(cp), spp,
                                     C.c_uint64(seed), x_begin, X if x_end is None else x_end, x_stride,
                                     threads or os.cpu_count() or 1, _ptr(rgb), _ptr(ctr))
         assert st == 0, st
@@ -212,7 +224,7 @@ class OracleScene:
         steps = np.empty(n, np.int32)
         shadow = np.empty(n, np.uint32)
         ctr = fto_counters()
-        st = lib().fto_trace_rays(self.h, n, _ptr(rays), threads, _ptr(rgb), _ptr(leaf), _ptr(steps),
+        st = self._L.fto_trace_rays(self.h, n, _ptr(rays), threads, _ptr(rgb), _ptr(leaf), _ptr(steps),
                                   _ptr(shadow), C.byref(ctr) if counters else None)
         assert st == 0
         out = dict(rgb=rgb, leaf=leaf, steps=steps, shadow=shadow)
@@ -223,7 +235,7 @@ class OracleScene:
     def distance(self, points, threads=None):
         points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
         out = np.empty(points.shape[0], np.float32)
-        st = lib().fto_distance(self.h, points.shape[0], _ptr(points), threads or os.cpu_count() or 1,
+        st = self._L.fto_distance(self.h, points.shape[0], _ptr(points), threads or os.cpu_count() or 1,
                                 _ptr(out), None)
         assert st == 0
         return out
@@ -231,19 +243,19 @@ class OracleScene:
     def form_distance(self, form_id, points):
         points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
         out = np.empty(points.shape[0], np.float32)
-        st = lib().fto_form_distance(self.h, form_id, points.shape[0], _ptr(points), _ptr(out))
+        st = self._L.fto_form_distance(self.h, form_id, points.shape[0], _ptr(points), _ptr(out))
         assert st == 0, st
         return out
 
     def form_boundary(self, form_id):
         out = np.empty(4, np.float32)
-        st = lib().fto_form_boundary(self.h, form_id, _ptr(out))
+        st = self._L.fto_form_boundary(self.h, form_id, _ptr(out))
         assert st == 0, st
         return out
 
     def root_boundary(self):
         out = np.empty(4, np.float32)
-        lib().fto_root_boundary(self.h, _ptr(out))
+        self._L.fto_root_boundary(self.h, _ptr(out))
         return out
 
 

@@ -273,10 +273,11 @@ def test_chain_program_equals_generic_interpreter(monkeypatch):
         assert np.array_equal(bits(a), bits(b)) and np.array_equal(la, lb)
 
 
-@pytest.mark.parametrize("make,stride", [(scenes.default_scene, 25), (scenes.spheres_capsules_scene, 48)])
+@pytest.mark.parametrize("make,stride", [(scenes.default_scene, 25), (scenes.spheres_capsules_scene, 48),
+                                         (scenes.mixed_scene, 256)])
 def test_full_size_frames_against_oracle_columns(make, stride):
-    """BASELINE.json's full frame sizes (config 1: 1000x1000, config 2: 1920x1080): every `stride`-th column of the
-    GPU frame must equal the oracle bit for bit (the oracle finishes these columns in seconds)."""
+    """BASELINE.json's full frame sizes (config 1: 1000x1000, config 2: 1920x1080, config 5: 7680x4320): every
+    `stride`-th column of the GPU frame must equal the oracle bit for bit (the oracle finishes these columns in seconds)."""
     w = make()
     X, Y = w.size.X, w.size.Y
     tracer = ft.SceneTracer(w.scene, device=0)
@@ -427,3 +428,42 @@ def test_extension_strip_rendering_equals_whole_frame():
                 assert np.array_equal(bits(d.cpu().numpy()), bits(ref)), (kind, world, sw)
             assert rays == st["primary_rays"] + st["shadow_rays"]
         tracer.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make", [lambda: scenes.default_scene(n_tori=300, size=160),
+                                  lambda: scenes.spheres_capsules_scene(width=240, height=135),
+                                  lambda: scenes.mixed_scene(width=256, height=144)])
+def test_subgrid_certified_path_equals_sequential_scan(make, monkeypatch):
+    """The nearest-candidate sub-grid (DESIGN.md "sub-grid") against the reference's sequential candidate scan
+    (SdfForm.fs:27-33) on the same device: (a) sub-grid off, (b) sub-grid on, (c) sub-grid on with every certificate
+    distrusted, so that every evaluation runs the sub-grid path AND the scan -- frames, leaf ids, per-ray step counts and
+    Distance values must be identical bit for bit; (b) must also equal the oracle."""
+    w = make()
+    X, Y = w.size.X, w.size.Y
+    monkeypatch.setenv("FT_NO_SUBGRID", "1")
+    plain = ft.SceneTracer(w.scene, device=0)
+    monkeypatch.delenv("FT_NO_SUBGRID")
+    assert plain.subgrid_info()["resolution"] == 0
+    sub = ft.SceneTracer(w.scene, device=0)
+    info = sub.subgrid_info()
+    assert info["resolution"] in (1, 2, 4, 8) and info["n_entries"] >= info["n_subcells"] > 0
+    rng = np.random.default_rng(5)
+    pts = (rng.random((20000, 3), dtype=np.float32) - 0.5) * 12.0  # inside and outside the lookup's box
+    rays = np.zeros((4096, 8), np.float32)
+    rays[:, 0:3] = (rng.random((4096, 3), dtype=np.float32) - 0.5) * 14.0
+    d = -rays[:, 0:3] + (rng.random((4096, 3), dtype=np.float32) - 0.5) * 4.0
+    rays[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 6], rays[:, 7] = 30.0, 0.01
+    ref = O.OracleScene(sub.description).render(w.camera, X, Y, w.epsilon, w.length)
+    results = []
+    for tracer, debug in ((plain, 0), (sub, 0), (sub, 1)):
+        tracer.set_debug(debug)
+        rgb, leaf, _ = tracer.render(w.camera, w.size, w.epsilon, w.length, want_leaf=True)
+        tr, _ = tracer.trace_rays(rays)
+        results.append((bits(rgb), leaf, tr["steps"], bits(tr["rgb"]), tr["leaf"], bits(tracer.distance(pts))))
+    for r in results[1:]:
+        for a, b in zip(results[0], r):
+            assert np.array_equal(a, b)
+    assert np.array_equal(results[1][0], bits(ref["rgb"])) and np.array_equal(results[1][1], ref["leaf"])
+    assert np.array_equal(results[1][5], bits(O.OracleScene(sub.description).distance(pts)))

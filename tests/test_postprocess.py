@@ -92,3 +92,60 @@ def test_gpu_image_max_and_device_tonemap_with_given_max():
                                   C.c_void_p(out.data_ptr()), 3 * 70, None))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), O.to_bitmap(img, 1.0, 11)[0])
+
+
+@pytest.mark.gpu
+def test_strip_owned_max_and_tonemap_assemble_the_whole_bitmap():
+    """Image.toColors over several GPUs (Image.fs:37-50): the per-rank maxima over the rank's own strips meet in a max, and the
+    per-rank bitmaps -- each byte written by exactly one rank -- meet in a bytewise max (what DistributedRenderer.to_bitmap
+    does with two all-reduce(MAX)); the result equals the whole-frame bitmap and the oracle's (gamma 1: exactly)."""
+    import ctypes as C
+
+    import torch
+
+    from fraytracer_b200 import _abi as A
+
+    lib = ft.load_library()
+    rng = np.random.default_rng(8)
+    X, Y, sw = 83, 47, 8  # ragged: the last strip is 3 columns wide
+    img = rng.uniform(0, 3, size=(X, Y, 3)).astype(np.float32)
+    img[61, 5, 2] = 7.25  # the maximum lives in a strip of rank 61 // 8 % world
+    d = torch.from_numpy(img).cuda()
+    for world in (1, 2, 3):
+        maxima, bitmaps = [], []
+        for rank in range(world):
+            mx = torch.zeros(1, dtype=torch.float32, device="cuda")
+            A.check(lib.ft_image_max_strips_device(C.c_void_p(d.data_ptr()), X, Y, sw, rank, world, C.c_void_p(mx.data_ptr()), None))
+            maxima.append(mx)
+        owner = (61 // sw) % world
+        assert float(maxima[owner].item()) == 7.25 and all(float(m.item()) < 7.25 for r, m in enumerate(maxima) if r != owner)
+        gmax = torch.stack(maxima).max(dim=0).values  # all-reduce(MAX)
+        for rank in range(world):
+            out = torch.zeros((Y, X, 3), dtype=torch.uint8, device="cuda")
+            A.check(lib.ft_tonemap_strips_device(C.c_void_p(d.data_ptr()), X, Y, sw, rank, world, C.c_float(1.0),
+                                                 C.c_void_p(gmax.data_ptr()), C.c_float(0.0), C.c_uint64(11),
+                                                 C.c_void_p(out.data_ptr()), 3 * X, None))
+            bitmaps.append(out)
+        torch.cuda.synchronize()
+        # every byte position is written by at most one rank
+        written = torch.stack([(b != 0) for b in bitmaps]).sum(dim=0)
+        assert int(written.max().item()) <= 1
+        whole = torch.stack(bitmaps).max(dim=0).values.cpu().numpy()  # all-reduce(MAX) over the bitmaps
+        assert np.array_equal(whole, O.to_bitmap(img, 1.0, 11)[0])
+
+
+@pytest.mark.gpu
+def test_distributed_renderer_to_bitmap_single_rank():
+    import torch
+
+    from fraytracer_b200.distributed import DistributedRenderer
+
+    w = scenes.default_scene(n_tori=200, size=120)
+    tracer = ft.SceneTracer(w.scene, device=0)
+    r = DistributedRenderer(tracer, w.size)
+    frame = r.render(w.camera, w.epsilon, w.length)
+    bitmap, mx = r.to_bitmap(frame, 1.0, 3)
+    torch.cuda.synchronize()
+    img = frame.cpu().numpy()
+    want, want_max = O.to_bitmap(img, 1.0, 3)
+    assert np.array_equal(bitmap.cpu().numpy(), want) and float(mx.item()) == want_max
