@@ -104,7 +104,7 @@ class ft_grid_info(C.Structure):
 
 
 class ft_subgrid_info(C.Structure):
-    _fields_ = [("resolution", C.c_int32), ("reserved", C.c_int32), ("n_subcells", C.c_int64), ("n_entries", C.c_int64),
+    _fields_ = [("resolution", C.c_int32), ("halo", C.c_int32), ("n_subcells", C.c_int64), ("n_entries", C.c_int64),
                 ("device_bytes", C.c_int64), ("threshold", C.c_float), ("build_ms", C.c_float)]
 
 

@@ -101,18 +101,24 @@ struct DevScene {
     // obj_links[chain_mat_links + child position] is the leaf object.
     int32_t chain_mat_valid;
     int32_t chain_mat_links;
-    // Nearest-candidate sub-grid of U (subgrid_build.cu, DESIGN.md "sub-grid"): every cell of U's spatial lookup is cut into
-    // sub_res^3 sub-cells; sub_hdr[cell * sub_res^3 + (sx * sub_res + sy) * sub_res + sz] addresses a short list of ABSOLUTE
-    // indices into entries[] -- those candidates of the cell's own list that can be the
-    // nearest one for some position inside the sub-cell (all others are provably farther than the nearest by a margin),
-    // nearest first.  Positions inside the lookup's box evaluate only these (eval_chain); the result is certified equal to the
-    // reference's sequential scan, otherwise the scan itself runs.  sub_valid == 0: no sub-grid (the scan always runs).
-    const uint2 *sub_hdr;    // {(first << 8) | count, the nearest candidate}; sub_idx[first ...] holds candidates 1 .. count-1
+    // Nearest-candidate sub-grid of U (subgrid_build.cu, DESIGN.md "sub-grid"): a FINE grid of sub_scale sub-cells per cell and
+    // axis that also covers a halo of sub_halo cells around U's box.  With c = (p - aabbMin) * cellSizeInv (the reference's own
+    // cell coordinate, SdfBoundary.fs:276), the fine index along an axis is  g = floor(c * sub_scale) + sub_off  (the product is
+    // exact: sub_scale is a power of two), valid for sub_lo <= c < sub_hi; the reference's cell is clamp(floor(c)) =
+    // clamp((g - sub_off) >> sub_shift), so a fine cell maps to ONE reference cell, halo included (border cells).
+    // sub_hdr[(gx * sub_ny + gy) * sub_nz + gz] = {(first << 8) | count, nearest candidate}; sub_idx[first ...] holds candidates
+    // 1 .. count-1: ABSOLUTE indices into entries[] -- those candidates of the reference cell's own list that can be the nearest
+    // one for some position inside the fine cell (all others are provably farther than the nearest by a margin), nearest first.
+    // Positions inside the covered region evaluate only these (eval_chain); the result is certified equal to the reference's
+    // sequential scan, otherwise the scan itself runs.  sub_valid == 0: no sub-grid (the scan always runs).
+    const uint2 *sub_hdr;
     const uint32_t *sub_idx;
     int32_t sub_valid;
-    int32_t sub_res;        // 1, 2, 4 or 8
-    float sub_res_f;        // (float)sub_res
-    float sub_count_f[3];   // (float)countX, countY, countZ of U's lookup: 0 <= c < count is "inside the box"
+    int32_t sub_shift;      // log2(sub-cells per cell and axis): 0 .. 3
+    int32_t sub_off;        // sub_halo << sub_shift
+    int32_t sub_ny, sub_nz; // fine cells along y and z
+    float sub_scale;        // (float)(1 << sub_shift)
+    float sub_lo[3], sub_hi[3];  // -halo and count + halo per axis, as floats
     int32_t sub_debug;      // bit 0: distrust every certificate (every evaluation also runs the sequential scan; tests)
                             // bit 1: COUNT kernels compare the certified result with the scan and count mismatches
 };

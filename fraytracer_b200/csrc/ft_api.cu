@@ -617,6 +617,8 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
             job.cell_base = cell_base;
             job.max_res = 8;
             job.max_subcells = 1ll << 22;
+            job.halo = 1;
+            if (const char *hh = getenv("FT_SUBGRID_HALO")) job.halo = std::max(0, std::min(8, atoi(hh)));  // experiments
             if (const char *r = getenv("FT_SUBGRID_RES")) job.max_res = std::max(1, std::min(8, atoi(r)));  // experiments
             std::string sub_err;
             if ((e = build_subgrid(s->dev, job, &s->sub, &sub_err)) != cudaSuccess) {
@@ -626,9 +628,15 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
             if (s->sub.hdr) {
                 s->dev.sub_hdr = s->sub.hdr;
                 s->dev.sub_idx = s->sub.idx;
-                s->dev.sub_res = s->sub.res;
-                s->dev.sub_res_f = (float)s->sub.res;
-                for (int k = 0; k < 3; k++) s->dev.sub_count_f[k] = (float)g.count[k];
+                s->dev.sub_shift = s->sub.shift;
+                s->dev.sub_off = s->sub.halo << s->sub.shift;
+                s->dev.sub_ny = s->sub.ny;
+                s->dev.sub_nz = s->sub.nz;
+                s->dev.sub_scale = (float)s->sub.res;
+                for (int k = 0; k < 3; k++) {
+                    s->dev.sub_lo[k] = -(float)s->sub.halo;
+                    s->dev.sub_hi[k] = (float)(g.count[k] + s->sub.halo);
+                }
                 s->dev.sub_valid = 1;
                 s->device_bytes += s->sub.bytes;
             }
@@ -685,6 +693,7 @@ FT_API int ft_scene_subgrid_info(const ft_scene *scene, ft_subgrid_info *out) {
     if (!scene || !out) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
     std::memset(out, 0, sizeof(*out));
     out->resolution = scene->sub.hdr ? scene->sub.res : 0;
+    out->halo = scene->sub.hdr ? scene->sub.halo : 0;
     out->n_subcells = scene->sub.n_subcells;
     out->n_entries = scene->sub.n_entries;
     out->device_bytes = scene->sub.bytes;

@@ -12,12 +12,13 @@ struct SubGridJob {
     int count[3];
     uint32_t cell_base;      // its first cell in cells[]
     int max_res;             // 8, 4, 2 or 1 sub-cells per axis at most
+    int halo;                // cells of halo around the lookup's box that the fine grid covers as well
     long long max_subcells;  // budget: the resolution is halved until cells * res^3 fits
 };
 struct SubGrid {
     uint2 *hdr = nullptr;  // device arrays (cudaFree by the owner); null when no sub-grid was built
     uint32_t *idx = nullptr;
-    int res = 0;
+    int res = 0, shift = 0, halo = 0, ny = 0, nz = 0;
     long long n_subcells = 0, n_entries = 0, bytes = 0;
     float threshold = 0.f, build_ms = 0.f;
 };

@@ -28,22 +28,26 @@ namespace ft_sub {
 struct SubParams {
     float amin[3], cell[3];  // U's aabbMin and cellSize
     int cx, cy, cz;          // cell counts
-    int S;                   // sub-cells per axis
+    int S, shift;            // sub-cells per cell and axis (1 << shift)
+    int halo;                // cells of halo around the box
+    int nx, ny, nz;          // fine cells per axis: (count + 2 halo) S
     uint32_t cell_base;      // first cell of U in cells[]
     float thr;               // 2 hd + tol
-    unsigned n_sub;          // cx cy cz S^3
+    unsigned n_sub;          // nx ny nz
 };
 
+// fine cell t = (gx ny + gy) nz + gz: its centre and the reference cell whose list it draws from -- clamp(floor(c)) per axis,
+// the border cell for the halo (SdfBoundary.fs:276-282)
 __device__ __forceinline__ V3 sub_centre(const SubParams &P, unsigned t, uint32_t &cell) {
-    const unsigned S3 = (unsigned)(P.S * P.S * P.S);
-    cell = t / S3;
-    const unsigned r = t - cell * S3;
-    const int sz = (int)(r % P.S), sy = (int)((r / P.S) % P.S), sx = (int)(r / (P.S * P.S));
-    const int iz = (int)(cell % P.cz), iy = (int)((cell / P.cz) % P.cy), ix = (int)(cell / (P.cz * P.cy));
+    const int gz = (int)(t % P.nz), gy = (int)((t / P.nz) % P.ny), gx = (int)(t / (P.nz * P.ny));
+    const int off = P.halo << P.shift;
+    const int fx = gx - off, fy = gy - off, fz = gz - off;  // fine coordinates relative to aabbMin, negative in the halo
+    const int ix = min(max(fx >> P.shift, 0), P.cx - 1), iy = min(max(fy >> P.shift, 0), P.cy - 1),
+              iz = min(max(fz >> P.shift, 0), P.cz - 1);
+    cell = (uint32_t)((ix * P.cy + iy) * P.cz + iz);
     const float inv = 1.0f / (float)P.S;
-    return V3{P.amin[0] + ((float)ix + ((float)sx + 0.5f) * inv) * P.cell[0],
-              P.amin[1] + ((float)iy + ((float)sy + 0.5f) * inv) * P.cell[1],
-              P.amin[2] + ((float)iz + ((float)sz + 0.5f) * inv) * P.cell[2]};
+    return V3{P.amin[0] + (((float)fx + 0.5f) * inv) * P.cell[0], P.amin[1] + (((float)fy + 0.5f) * inv) * P.cell[1],
+              P.amin[2] + (((float)fz + 0.5f) * inv) * P.cell[2]};
 }
 
 // pass 1: nearest candidate distance at the sub-cell centre and the number of candidates within the threshold
@@ -138,7 +142,8 @@ cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
-    const long long n_cells = (long long)job.count[0] * job.count[1] * job.count[2];
+    const int halo = job.halo < 0 ? 0 : job.halo;
+    const long long n_cells = (long long)(job.count[0] + 2 * halo) * (job.count[1] + 2 * halo) * (job.count[2] + 2 * halo);
     int res = job.max_res;
     while (res > 1 && n_cells * res * res * res > job.max_subcells) res >>= 1;
     SG_CU(cudaEventCreate(&e0));
@@ -149,7 +154,7 @@ cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out
         // factor within 2^-23, cellSizeInv * cellSize within 2^-22 of 1): 1e-6 of the lookup's reach per axis is ample
         double hd2 = 0.0, scale = 1.0;
         for (int k = 0; k < 3; k++) {
-            const double reach = std::fabs((double)job.amin[k]) + (double)job.count[k] * job.cell[k];
+            const double reach = std::fabs((double)job.amin[k]) + (double)(job.count[k] + halo) * job.cell[k];
             const double half = 0.5 / res * job.cell[k] * (1.0 + 1e-5) + 1e-6 * reach;
             hd2 += half * half;
             scale = std::max(scale, 2.0 * reach);
@@ -159,6 +164,11 @@ cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out
         for (int k = 0; k < 3; k++) { P.amin[k] = job.amin[k]; P.cell[k] = job.cell[k]; }
         P.cx = job.count[0]; P.cy = job.count[1]; P.cz = job.count[2];
         P.S = res;
+        P.shift = res == 8 ? 3 : res == 4 ? 2 : res == 2 ? 1 : 0;
+        P.halo = halo;
+        P.nx = (job.count[0] + 2 * halo) * res;
+        P.ny = (job.count[1] + 2 * halo) * res;
+        P.nz = (job.count[2] + 2 * halo) * res;
         P.cell_base = job.cell_base;
         P.thr = (float)(2.0 * std::sqrt(hd2) + tol);
         const long long n_sub = n_cells * res * res * res;
@@ -193,6 +203,10 @@ cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out
         out->hdr = d_hdr;
         out->idx = d_idx;
         out->res = res;
+        out->shift = P.shift;
+        out->halo = halo;
+        out->ny = P.ny;
+        out->nz = P.nz;
         out->n_subcells = n_sub;
         out->n_entries = (long long)total + n_sub;  // the nearest candidate of every sub-cell lives in its header
         out->bytes = (long long)sizeof(uint2) * n_sub + (long long)sizeof(uint32_t) * std::max(1u, total);

@@ -425,16 +425,12 @@ __device__ __forceinline__ bool certain_fail_up(float M, float4 b0, float rup, V
     return sf > __fmaf_rn(u, u, 1e-30f);
 }
 
+// `g` = the fine-cell coordinates of p (see DevScene): the caller has checked that p lies in the covered region
 template <bool COUNT>
-__device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, V3 c, uint32_t ci, int ix, int iy, int iz, float &m_out,
-                                           uint32_t &best_out, Acc &acc) {
-    // sub-cell of p inside its cell: fractional part of the reference's own cell coordinate (exact: Sterbenz), times a power of two
-    const float fx = c.x - (float)ix, fy = c.y - (float)iy, fz = c.z - (float)iz;
-    const int R = S.sub_res;
-    const int sx = (int)(fx * S.sub_res_f), sy = (int)(fy * S.sub_res_f), sz = (int)(fz * S.sub_res_f);
-    const uint32_t cell_local = ci - __float_as_uint(S.chain_g1.w);
+__device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int gy, int gz, float &m_out, uint32_t &best_out,
+                                           Acc &acc) {
     // header: {(first << 8) | count, the nearest candidate}: the first record's load depends on one load only
-    const uint2 hdr = __ldg(S.sub_hdr + ((size_t)cell_local * (uint32_t)(R * R * R) + (uint32_t)((sx * R + sy) * R + sz)));
+    const uint2 hdr = __ldg(S.sub_hdr + (uint32_t)((gx * S.sub_ny + gy) * S.sub_nz + gz));
     const uint32_t n = hdr.x & 255u;
     if (n == 0u) return false;  // no list for this sub-cell (too long to encode): the scan runs
     add_flops<COUNT>(acc, 9);
@@ -465,11 +461,16 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, V3 c, uint32
     if (best == 0xffffffffu) return false;  // nothing comparable (NaN positions): the scan decides
     // certificates on the arg-min
     const Entry eb = ld_entry(S, best);
-    const float4 cell = ld4(S.cells + ci);
     add_flops<COUNT>(acc, 12);
     const float x = eb.lb() - M;
     bool ok = true;
     if (x > 0.0f) {  // (1)  M >= fl(lb - dtc): certainly true when |p - centre|^2 > x^2 (1 + 2^-10); else compare exactly
+        // the reference's cell of this fine cell: clamp(floor(c)) per axis (SdfBoundary.fs:276-282)
+        const int mx = __float_as_int(S.chain_g3.x), my = __float_as_int(S.chain_g3.y), mz = __float_as_int(S.chain_g3.z);
+        const int ix = min(max((gx - S.sub_off) >> S.sub_shift, 0), mx), iy = min(max((gy - S.sub_off) >> S.sub_shift, 0), my),
+                  iz = min(max((gz - S.sub_off) >> S.sub_shift, 0), mz);
+        const float4 cell = ld4(S.cells + (__float_as_uint(S.chain_g1.w) +
+                                           (uint32_t)(ix * __float_as_int(S.chain_g3.w) + iy * (mz + 1) + iz)));
         const V3 dc = p - xyz(cell);
         const float dtc2 = __fmaf_rn(dc.z, dc.z, __fmaf_rn(dc.y, dc.y, dc.x * dc.x));
         if (!(dtc2 > (x * x) * 1.0009765625f)) ok = M >= eb.lb() - distance(p, xyz(cell));
@@ -498,14 +499,13 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, u
         // SdfBoundary.fs:276-282 with U's header from the constant bank (see grid_cell_from)
         const float4 g1 = S.chain_g1, g2 = S.chain_g2, g3 = S.chain_g3;
         const V3 c = (p - xyz(g1)) * xyz(g2);
-        const int mx = __float_as_int(g3.x), my = __float_as_int(g3.y), mz = __float_as_int(g3.z);
-        const int ix = cell_index(c.x, mx), iy = cell_index(c.y, my), iz = cell_index(c.z, mz);
-        const uint32_t ci = __float_as_uint(g1.w) + (uint32_t)(ix * __float_as_int(g3.w) + iy * (mz + 1) + iz);
-        if (S.sub_valid && c.x >= 0.0f && c.y >= 0.0f && c.z >= 0.0f && c.x < S.sub_count_f[0] && c.y < S.sub_count_f[1] &&
-            c.z < S.sub_count_f[2]) {
+        if (S.sub_valid && c.x >= S.sub_lo[0] && c.y >= S.sub_lo[1] && c.z >= S.sub_lo[2] && c.x < S.sub_hi[0] &&
+            c.y < S.sub_hi[1] && c.z < S.sub_hi[2]) {
             uint32_t best = 0u;
             float ms = 0.f;
-            certified = sub_lookup<COUNT>(S, p, c, ci, ix, iy, iz, ms, best, acc);
+            certified = sub_lookup<COUNT>(S, p, __float2int_rd(c.x * S.sub_scale) + S.sub_off,
+                                          __float2int_rd(c.y * S.sub_scale) + S.sub_off,
+                                          __float2int_rd(c.z * S.sub_scale) + S.sub_off, ms, best, acc);
             if (certified) {
                 m = ms;
 #if FT_CHAIN_MAT
@@ -514,6 +514,9 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, u
             }
         }
         if (!certified) {
+            const int mx = __float_as_int(g3.x), my = __float_as_int(g3.y), mz = __float_as_int(g3.z);
+            const int ix = cell_index(c.x, mx), iy = cell_index(c.y, my), iz = cell_index(c.z, mz);
+            const uint32_t ci = __float_as_uint(g1.w) + (uint32_t)(ix * __float_as_int(g3.w) + iy * (mz + 1) + iz);
             const float4 cell = ld4(S.cells + ci);
             dtc = distance(p, xyz(cell));  // SdfForm.fs:25
             i = __float_as_uint(cell.w);

@@ -196,7 +196,7 @@ typedef struct ft_scene_info {
  * equal to the reference's sequential candidate scan (SdfForm.fs:22-34)        */
 typedef struct ft_subgrid_info {
     int32_t resolution;      /* sub-cells per cell and axis (8, 4, 2, 1); 0 = none */
-    int32_t reserved;
+    int32_t halo;            /* cells around the lookup's box the sub-grid covers too */
     int64_t n_subcells;
     int64_t n_entries;       /* candidate references over all sub-cells        */
     int64_t device_bytes;
