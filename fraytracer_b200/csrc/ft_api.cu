@@ -77,6 +77,33 @@ cudaError_t upload(const std::vector<T> &v, const T **out, int64_t *bytes) {
 
 }  // namespace
 
+// Scheduling hint of one launch shape (frame size, strip partition, band): the per-tile costs the last launch of that
+// shape measured and the tile order (most expensive first) derived from them.  Purely a scheduling matter: pixels do not
+// depend on the order tiles are drawn in (tests render with and without hints).  Launches of one shape are serialised on the
+// device through `ready`, so that the order a kernel reads is never rewritten under it.
+struct TileHint {
+    int key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned n_tiles = 0;
+    unsigned short *d_cost = nullptr, *d_snap = nullptr, *d_keys = nullptr;
+    unsigned *d_order = nullptr, *d_iota = nullptr;
+    void *d_temp = nullptr;
+    size_t temp_bytes = 0;
+    cudaEvent_t ready = nullptr;
+    bool valid = false;  // d_order holds a permutation
+    unsigned long long stamp = 0;
+    void release() {
+        if (d_cost) cudaFree(d_cost);
+        if (d_snap) cudaFree(d_snap);
+        if (d_order) cudaFree(d_order);
+        if (d_keys) cudaFree(d_keys);
+        if (d_iota) cudaFree(d_iota);
+        if (d_temp) cudaFree(d_temp);
+        if (ready) cudaEventDestroy(ready);
+        *this = TileHint();
+    }
+};
+constexpr int kTileHints = 16;
+
 struct ft_scene {
     int device = 0;
     int sm_count = 0;
@@ -100,6 +127,10 @@ struct ft_scene {
     size_t scratch2_bytes = 0;
     unsigned *d_spec_counts = nullptr, *h_spec_counts = nullptr;
     SubGrid sub;  // nearest-candidate sub-grid of a chain scene's spatial lookup (subgrid_build.cu)
+    TileHint hints[kTileHints];
+    unsigned long long hint_clock = 0;
+    bool hints_enabled = true;
+    bool hint_interleave = true;  // destinations behind PCIe: expensive and cheap tiles alternate (RenderParams::order_mode)
     std::mutex mu;
 
     cudaError_t reserve(size_t bytes) {
@@ -125,6 +156,7 @@ struct ft_scene {
                               dev.objects, dev.obj_links, dev.materials, dev.lights};
         for (const void *p : ptrs)
             if (p) cudaFree(const_cast<void *>(p));
+        for (auto &h : hints) h.release();
         if (sub.hdr) cudaFree(sub.hdr);
         if (sub.idx) cudaFree(sub.idx);
         if (d_stats) cudaFree(d_stats);
@@ -205,6 +237,9 @@ RenderParams make_params(int width, int height, float eps, float length, int str
     P.world = world;
     P.x_offset = 0;
     P.xl_begin = 0;
+    P.order = nullptr;
+    P.cost = nullptr;
+    P.order_mode = 0;
     const int strips = (width + strip_width - 1) / strip_width;
     const int spr = (strips + world - 1) / world;
     P.local_cols = world == 1 ? width : spr * strip_width;
@@ -214,6 +249,61 @@ RenderParams make_params(int width, int height, float eps, float length, int str
     return P;
 }
 
+
+// The hint slot of a launch shape (least recently used slot is recycled); null when hints are off or allocation fails.
+// Attaches the order (if one exists) and the cost buffer to P and makes `s` wait for the slot's previous user.
+TileHint *hint_attach(ft_scene *scene, RenderParams &P, int tag, cudaStream_t s, bool behind_pcie = false) {
+    if (!scene->hints_enabled) return nullptr;
+    const long long tiles = (long long)((P.local_cols + 3) / 4) * ((P.height + 7) / 8);
+    if (tiles <= 0 || tiles > (1ll << 26)) return nullptr;
+    const int key[8] = {P.width, P.height, P.local_cols, P.world > 1 ? P.strip_width : 0, P.rank, P.world, P.x_offset * 2 + tag, P.xl_begin};
+    TileHint *slot = nullptr, *lru = &scene->hints[0];
+    for (auto &h : scene->hints) {
+        if (h.n_tiles && std::memcmp(h.key, key, sizeof(key)) == 0) slot = &h;
+        if (h.stamp < lru->stamp) lru = &h;
+    }
+    if (!slot) {
+        slot = lru;
+        if (slot->ready) cudaEventSynchronize(slot->ready);  // its last user has finished
+        slot->release();
+        std::memcpy(slot->key, key, sizeof(key));
+        slot->n_tiles = (unsigned)tiles;
+        if (cudaMalloc(&slot->d_cost, sizeof(unsigned short) * (size_t)tiles) != cudaSuccess ||
+            cudaMalloc(&slot->d_snap, sizeof(unsigned short) * (size_t)tiles) != cudaSuccess ||
+            cudaMalloc(&slot->d_order, sizeof(unsigned) * (size_t)tiles) != cudaSuccess ||
+            cudaMalloc(&slot->d_keys, sizeof(unsigned short) * (size_t)tiles) != cudaSuccess ||
+            cudaMalloc(&slot->d_iota, sizeof(unsigned) * (size_t)tiles) != cudaSuccess ||
+            (slot->temp_bytes = tile_order_temp_bytes((unsigned)tiles)) == 0 ||
+            cudaMalloc(&slot->d_temp, slot->temp_bytes) != cudaSuccess ||
+            launch_tile_iota(slot->d_iota, (unsigned)tiles, s) != cudaSuccess ||
+            cudaEventCreateWithFlags(&slot->ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaMemsetAsync(slot->d_cost, 0, sizeof(unsigned short) * (size_t)tiles, s) != cudaSuccess) {
+            cudaGetLastError();
+            slot->release();
+            return nullptr;
+        }
+    } else if (cudaStreamWaitEvent(s, slot->ready, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    slot->stamp = ++scene->hint_clock;
+    P.order = slot->valid ? slot->d_order : nullptr;
+    P.cost = slot->d_cost;
+    P.order_mode = (behind_pcie && scene->hint_interleave) ? 1 : 0;
+    return slot;
+}
+
+// after the render kernel has been enqueued on `s`: derive the next launch's order from the costs it records
+void hint_finish(TileHint *h, cudaStream_t s) {
+    if (!h) return;
+    if (launch_tile_order(h->d_cost, h->d_snap, h->d_keys, h->d_iota, h->n_tiles, h->d_order, h->d_temp, h->temp_bytes, s) == cudaSuccess &&
+        cudaEventRecord(h->ready, s) == cudaSuccess) {
+        h->valid = true;
+    } else {
+        cudaGetLastError();
+        h->valid = false;
+    }
+}
 
 // pixels of the frame the strips of `T` cover (padding columns of the last strip excluded)
 int64_t owned_pixels(const StripTarget &T, int width, int height) {
@@ -644,6 +734,8 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
         }
     }
     s->dev.sub_debug = 0;
+    s->hints_enabled = getenv("FT_NO_TILE_HINT") == nullptr;
+    s->hint_interleave = getenv("FT_NO_HINT_INTERLEAVE") == nullptr;  // experiments only
     if (const char *d = getenv("FT_SUB_DEBUG")) s->dev.sub_debug = atoi(d);  // tests: 1 = distrust every certificate
     if (getenv("FT_NO_ESCAPE")) s->dev.esc_valid = 0;  // experiments only
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
@@ -705,7 +797,8 @@ FT_API int ft_scene_subgrid_info(const ft_scene *scene, ft_subgrid_info *out) {
 FT_API int ft_scene_set_debug(ft_scene *scene, int32_t sub_debug) {
     if (!scene) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(scene->mu);
-    scene->dev.sub_debug = sub_debug;
+    scene->dev.sub_debug = sub_debug & 3;
+    scene->hints_enabled = (sub_debug & 4) == 0 && getenv("FT_NO_TILE_HINT") == nullptr;  // bit 2: natural tile order, no hints
     return FT_OK;
 }
 
@@ -836,8 +929,10 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
     if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     unsigned long long *wc;
     CU(fresh_counter(scene, s, &wc));
+    TileHint *hint = hint_attach(scene, P, 0, s);
     cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render, scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, stats ? scene->d_stats : nullptr, count, scene->sm_count, s, false);
     if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
+    hint_finish(hint, s);
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -880,8 +975,16 @@ FT_API int ft_render_gather_device(ft_scene *scene, const ft_camera *camera, int
     if (stats) CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     unsigned long long *wc;
     CU(fresh_counter(scene, s, &wc));
+    bool to_host = false;  // a destination in mapped host memory (render_to_host): its stores cross PCIe
+    for (int k = 0; k < n_dst; k++) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, d_dst[k]) == cudaSuccess) to_host = to_host || pa.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    TileHint *hint = hint_attach(scene, P, to_host ? 1 : 0, s, to_host);
     cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render_gather, scene->dev, *camera, P, d_dst, n_dst, wc, stats ? scene->d_stats : nullptr, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "render-gather kernel launch");
+    hint_finish(hint, s);
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -986,9 +1089,11 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
             RenderParams P = make_params(width, height, epsilon, length, width, 0, 1);
             unsigned long long *wc;
             CU(fresh_counter(scene, s, &wc));
+            TileHint *hint = hint_attach(scene, P, 1, s, true);
             cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, m_rgb, m_leaf, wc, scene->d_stats, count, scene->sm_count, s, true);
             if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
             CU(cudaEventRecord(scene->ev[1], s));
+            hint_finish(hint, s);
             CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
             CU(cudaEventRecord(scene->ev[2], s));
             CU(cudaStreamSynchronize(s));  // kernel completion makes its system-scope stores visible to the host
@@ -1027,10 +1132,12 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
         int32_t *band_leaf = d_leaf ? d_leaf + (size_t)x0 * height : nullptr;
         unsigned long long *wc;
         CU(fresh_counter(scene, bs, &wc));
+        TileHint *hint = hint_attach(scene, P, 0, bs);
         cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, band_rgb, band_leaf, wc, scene->d_stats, count, scene->sm_count, bs, false);
         if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
         launches++;
         CU(cudaEventRecord((launches & 1) ? scene->ev[1] : scene->ev[3], bs));  // end of the last kernel on each stream
+        hint_finish(hint, bs);
         CU(cudaMemcpyAsync(out_rgb + (size_t)x0 * height * 3, band_rgb, (size_t)cols * height * 3 * sizeof(float),
                            cudaMemcpyDeviceToHost, bs));
         if (out_leaf)

@@ -25,6 +25,14 @@ struct RenderParams {
     int x_offset;        // image column of compact column 0 (band rendering)
     int xl_begin;        // first compact column (in the rank's strip space) this launch renders; out_rgb starts there
     float epsilon, length, max_size;
+    // Scheduling hints (ft_api.cu TileHint; never used in arithmetic): `order` = the launch's tiles, most expensive first, as
+    // measured by the previous launch of the same shape on this scene (null: natural order); `cost` receives every tile's
+    // iteration count for the next launch (null: not recorded).
+    const unsigned *order;
+    unsigned short *cost;
+    int order_mode;      // 0: order[] as it is (most expensive first); 1: expensive and cheap tiles alternate (order[0], order[n-1],
+                         // order[1], order[n-2] ...) -- for destinations behind PCIe, where the cheap tiles' stores must not all
+                         // arrive at the end of the launch
 };
 
 // Which pixels a rank renders and where they go (multi-GPU): column strips dealt round-robin
@@ -75,6 +83,11 @@ FT_DECLARE_LAUNCHERS(ft_fast)
 cudaError_t launch_deinterleave(const float *gathered, int width, int height, int strip_width, int world, int channels,
                                 int first_local_strip, int n_local_strips, float *out, cudaStream_t stream);
 cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate);
+// tiles sorted by descending cost (stable radix sort of a private snapshot of `cost`): order[] is a permutation of 0..n-1
+size_t tile_order_temp_bytes(unsigned n);
+cudaError_t launch_tile_iota(unsigned *v, unsigned n, cudaStream_t stream);
+cudaError_t launch_tile_order(const unsigned short *cost, unsigned short *snapshot, unsigned short *sorted_keys, const unsigned *iota,
+                              unsigned n, unsigned *order, void *temp, size_t temp_bytes, cudaStream_t stream);
 
 // post_kernels.cu
 // strip_width > 0: only the columns of the strips `rank` owns (strip s -> rank s % world); 0: the whole frame

@@ -53,6 +53,15 @@ enum : int {
     PH_PROBE = 7,     // Distance at the common origin of all primary rays (render jobs), once per warp
 };
 
+// Scheduling hint (RenderParams::order): the n-th chunk drawn from the work counter is tile order[n] of the previous launch's
+// cost ranking, or -- order_mode 1 -- the ranking read from both ends alternately.
+__device__ __forceinline__ long long hinted_chunk(const RenderParams &P, long long base, long long n_items) {
+    if (!P.order) return base;
+    long long t = base >> 5;
+    if (P.order_mode == 1) t = (t & 1) ? (n_items >> 5) - 1 - (t >> 1) : (t >> 1);
+    return (long long)__ldg(P.order + t) << 5;
+}
+
 // ---- work sources -----------------------------------------------------------------------------------------
 // Image.render: item i -> pixel, tiles of 4 (x) by 8 (y) pixels, tiles ordered along y first so that a chunk
 // of 8 tiles is a 4 x 64 pixel block of the x-major FColor[X,Y] output.
@@ -116,6 +125,11 @@ struct RenderJobT {
     // i.e. the four 96-byte column runs of the x-major FColor[X,Y] back to back; `valid` marks the lanes that hold a pixel.
     // A complete, 16-byte-aligned tile leaves as 24 128-bit stores -- full 32-byte sectors for mapped host memory and peer
     // framebuffers (PCIe / NVLink write efficiency) -- anything else pixel by pixel.
+    static constexpr bool kTileCost = true;
+    __device__ __forceinline__ long long map_chunk(long long base) const { return hinted_chunk(P, base, n_items); }
+    __device__ __forceinline__ void note_cost(long long base, unsigned iters) const {
+        if (P.cost) P.cost[base >> 5] = (unsigned short)(iters < 65535u ? iters : 65535u);
+    }
     static constexpr bool kTileStore = TILE;  // launch_render picks it for destinations behind PCIe (mapped host memory)
     __device__ __forceinline__ int *out_leaf_ptr() const { return out_leaf; }
     __device__ __forceinline__ void store_tile(long long base_item, const float *sh, unsigned valid, int lane) const {
@@ -192,6 +206,11 @@ struct GatherJob {
             out[2] = b;
         }
     }
+    static constexpr bool kTileCost = true;
+    __device__ __forceinline__ long long map_chunk(long long base) const { return hinted_chunk(P, base, n_items); }
+    __device__ __forceinline__ void note_cost(long long base, unsigned iters) const {
+        if (P.cost) P.cost[base >> 5] = (unsigned short)(iters < 65535u ? iters : 65535u);
+    }
     // see RenderJob::store_tile; the tile's four columns are consecutive image columns when the strip width is a multiple of 4
     static constexpr bool kTileStore = true;
     __device__ __forceinline__ int *out_leaf_ptr() const { return nullptr; }
@@ -264,6 +283,9 @@ struct RaysJob {
         if (out_shadow) out_shadow[slot] = shadow;
     }
     static constexpr bool kTileStore = false;
+    static constexpr bool kTileCost = false;
+    __device__ __forceinline__ long long map_chunk(long long base) const { return base; }
+    __device__ __forceinline__ void note_cost(long long, unsigned) const {}
     __device__ __forceinline__ int *out_leaf_ptr() const { return nullptr; }
     __device__ __forceinline__ void store_tile(long long, const float *, unsigned, int) const {}
 };
@@ -298,7 +320,8 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     constexpr bool TILE_STORE = FT_TILE_STORE && Job::kTileStore && FT_REFILL_MIN >= 32;
     __shared__ __align__(16) float sh_tile[TILE_STORE ? MB / 32 : 1][TILE_STORE ? 96 : 4];
     float *const wtile = sh_tile[TILE_STORE ? (threadIdx.x >> 5) : 0];
-    long long tile_base = -1;  // the chunk whose pixels are staged (uniform)
+    long long tile_base = -1;  // the chunk in flight (uniform): staged pixels, cost record
+    unsigned iters = 0u;       // loop iterations spent on it
     bool has_pix = false;
     __shared__ unsigned sh_stats[MB / 32][4];
     unsigned *const wstats = sh_stats[threadIdx.x >> 5];
@@ -315,12 +338,15 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         {
             unsigned idle = __ballot_sync(FULL, phase == PH_FETCH);
             if (idle == FULL || (__popc(idle) >= FT_REFILL_MIN && !(exhausted && chunk_left == 0))) {
-                if (TILE_STORE && idle == FULL && tile_base >= 0) {  // the previous tile is complete: it leaves as a whole
-                    __syncwarp();
-                    job.store_tile(tile_base, wtile, __ballot_sync(FULL, has_pix), lane);
-                    __syncwarp();
+                if ((TILE_STORE || Job::kTileCost) && idle == FULL && tile_base >= 0) {  // the previous tile is complete
+                    if (TILE_STORE) {  // it leaves as a whole
+                        __syncwarp();
+                        job.store_tile(tile_base, wtile, __ballot_sync(FULL, has_pix), lane);
+                        __syncwarp();
+                        has_pix = false;
+                    }
+                    if (Job::kTileCost && lane == 0) job.note_cost(tile_base, iters);
                     tile_base = -1;
-                    has_pix = false;
                 }
                 while (idle) {
                     if (chunk_left == 0) {
@@ -332,9 +358,11 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                             exhausted = true;
                             break;
                         }
-                        chunk_next = (long long)base;
+                        // scheduling hint: the n-th chunk drawn is the n-th most expensive tile of the previous launch
+                        chunk_next = job.map_chunk((long long)base);
                         chunk_left = FT_CHUNK;
-                        if (TILE_STORE) tile_base = (long long)base;
+                        if (TILE_STORE || Job::kTileCost) tile_base = chunk_next;
+                        iters = 0u;
                     }
                     const int want = __popc(idle), take = want < chunk_left ? want : chunk_left;
                     const int r = __popc(idle & ((1u << lane) - 1u));
@@ -356,6 +384,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                 }
             }
         }
+        iters++;
         // ------------------------------------------------------------------ march pre-check (SdfForm.fs:94)
         // a ray whose Length is exhausted (or that hit the watchdog) ends as a miss without another evaluation
         int event = 0;  // 1 primary miss, 2 primary hit, 3 shadow finished (miss), 4 shadow finished (hit), 5 normal done

@@ -467,3 +467,41 @@ def test_subgrid_certified_path_equals_sequential_scan(make, monkeypatch):
             assert np.array_equal(a, b)
     assert np.array_equal(results[1][0], bits(ref["rgb"])) and np.array_equal(results[1][1], ref["leaf"])
     assert np.array_equal(results[1][5], bits(O.OracleScene(sub.description).distance(pts)))
+
+
+@pytest.mark.gpu
+def test_tile_order_hints_change_nothing_but_the_schedule():
+    """ft_api.cu TileHint: from the second frame of a shape on, tiles are drawn most-expensive-first as measured by the previous
+    frame.  Pixels are independent of the order tiles are drawn in: every path (staged ft_render, zero-copy ft_render, device
+    strips, fused gather) must return the first frame's bits again and again, and the frame rendered with hints disabled."""
+    import ctypes as C
+
+    import torch
+
+    w = scenes.spheres_capsules_scene(width=333, height=251)  # ragged: partial tiles at both edges
+    X, Y = w.size.X, w.size.Y
+    tracer = ft.SceneTracer(w.scene, device=0)
+    ref = O.OracleScene(tracer.description).render(w.camera, X, Y, w.epsilon, w.length)
+    host = C.c_void_p()
+    A.check(tracer.lib.ft_host_alloc(C.byref(host), X * Y * 12))
+    mapped = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(X, Y, 3))
+    dev = torch.empty((X, Y, 3), dtype=torch.float32, device="cuda:0")
+    dst = [torch.zeros((X, Y, 3), dtype=torch.float32, device="cuda:0") for _ in range(2)]
+    for frame in range(4):  # frame 0 runs unhinted and measures, frames 1.. are ordered by the previous frame's costs
+        tracer.set_debug(4 if frame == 3 else 0)  # the last frame: hints disabled again
+        rgb, leaf, _ = tracer.render(w.camera, w.size, w.epsilon, w.length, want_leaf=True)  # pageable: two staged bands
+        assert np.array_equal(bits(rgb), bits(ref["rgb"])) and np.array_equal(leaf, ref["leaf"]), frame
+        mapped.fill(-1.0)
+        tracer.render(w.camera, w.size, w.epsilon, w.length, out=mapped)  # zero-copy, whole-tile stores
+        assert np.array_equal(bits(mapped), bits(ref["rgb"])), frame
+        dev.fill_(-1.0)
+        tracer.render_device(w.camera, w.size, w.epsilon, w.length, dev.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        for d in dst:
+            d.fill_(-1.0)
+        tracer.render_gather_device(w.camera, w.size, w.epsilon, w.length, [d.data_ptr() for d in dst],
+                                    stream=torch.cuda.current_stream().cuda_stream, strip_width=8)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(dev.cpu().numpy()), bits(ref["rgb"])), frame
+        for d in dst:
+            assert np.array_equal(bits(d.cpu().numpy()), bits(ref["rgb"])), frame
+    A.check(tracer.lib.ft_host_free(host))
