@@ -77,28 +77,29 @@ cudaError_t upload(const std::vector<T> &v, const T **out, int64_t *bytes) {
 
 }  // namespace
 
-// Scheduling hint of one launch shape (frame size, strip partition, band): the per-tile costs the last launch of that
-// shape measured and the tile order (most expensive first) derived from them.  Purely a scheduling matter: pixels do not
-// depend on the order tiles are drawn in (tests render with and without hints).  Launches of one shape are serialised on the
-// device through `ready`, so that the order a kernel reads is never rewritten under it.
+// Scheduling hint of one launch shape (frame size, strip partition, band, kind of destination): the per-tile costs its launches
+// record and the tile orders derived from them (tile_rank.cu).  Purely a scheduling matter: pixels do not depend on the order
+// tiles are drawn in (tests render with and without hints).  Frame N of a shape draws its tiles in the order ranked from
+// frame N - 2's costs: the ranking of frame N - 1 runs on the scene's side stream while frame N is being rendered, so that
+// back-to-back launches never wait for a sort.
 struct TileHint {
     int key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned n_tiles = 0;
-    unsigned short *d_cost = nullptr, *d_snap = nullptr, *d_keys = nullptr;
-    unsigned *d_order = nullptr, *d_iota = nullptr;
-    void *d_temp = nullptr;
-    size_t temp_bytes = 0;
-    cudaEvent_t ready = nullptr;
-    bool valid = false;  // d_order holds a permutation
-    unsigned long long stamp = 0;
+    unsigned short *d_cost = nullptr;
+    TileRank *rank = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr};  // order[parity] has been written
+    cudaEvent_t snapped = nullptr;              // the last frame's costs have been copied out of d_cost
+    bool valid[2] = {false, false};
+    unsigned long long frames = 0, stamp = 0;
+    int mode = 0;  // FT_RANK_*
     void release() {
+        for (cudaEvent_t e : {ready[0], ready[1], snapped})
+            if (e) {
+                cudaEventSynchronize(e);
+                cudaEventDestroy(e);
+            }
         if (d_cost) cudaFree(d_cost);
-        if (d_snap) cudaFree(d_snap);
-        if (d_order) cudaFree(d_order);
-        if (d_keys) cudaFree(d_keys);
-        if (d_iota) cudaFree(d_iota);
-        if (d_temp) cudaFree(d_temp);
-        if (ready) cudaEventDestroy(ready);
+        tile_rank_destroy(rank);
         *this = TileHint();
     }
 };
@@ -128,9 +129,12 @@ struct ft_scene {
     unsigned *d_spec_counts = nullptr, *h_spec_counts = nullptr;
     SubGrid sub;  // nearest-candidate sub-grid of a chain scene's spatial lookup (subgrid_build.cu)
     TileHint hints[kTileHints];
+    cudaStream_t hint_stream = nullptr;  // the tile rankings are computed here, beside the caller's stream
     unsigned long long hint_clock = 0;
     bool hints_enabled = true;
-    bool hint_interleave = true;  // destinations behind PCIe: expensive and cheap tiles alternate (RenderParams::order_mode)
+    // destinations behind PCIe (mapped host memory): FT_RANK_TIMED by default (tile_rank.cu); 0 = plain LPT, 1 = LPT read from
+    // both ends alternately (RenderParams::order_mode) -- experiments
+    int hint_pcie_mode = FT_RANK_TIMED, hint_pcie_shift = 0, hint_split_pct = 150;
     std::mutex mu;
 
     cudaError_t reserve(size_t bytes) {
@@ -156,7 +160,9 @@ struct ft_scene {
                               dev.objects, dev.obj_links, dev.materials, dev.lights};
         for (const void *p : ptrs)
             if (p) cudaFree(const_cast<void *>(p));
+        if (hint_stream) cudaStreamSynchronize(hint_stream);
         for (auto &h : hints) h.release();
+        if (hint_stream) cudaStreamDestroy(hint_stream);
         if (sub.hdr) cudaFree(sub.hdr);
         if (sub.idx) cudaFree(sub.idx);
         if (d_stats) cudaFree(d_stats);
@@ -240,6 +246,7 @@ RenderParams make_params(int width, int height, float eps, float length, int str
     P.order = nullptr;
     P.cost = nullptr;
     P.order_mode = 0;
+    P.order_shift = 0;
     const int strips = (width + strip_width - 1) / strip_width;
     const int spr = (strips + world - 1) / world;
     P.local_cols = world == 1 ? width : spr * strip_width;
@@ -251,7 +258,7 @@ RenderParams make_params(int width, int height, float eps, float length, int str
 
 
 // The hint slot of a launch shape (least recently used slot is recycled); null when hints are off or allocation fails.
-// Attaches the order (if one exists) and the cost buffer to P and makes `s` wait for the slot's previous user.
+// Attaches the order (if one exists yet) and the cost buffer to P and orders `s` after the slot's earlier users.
 TileHint *hint_attach(ft_scene *scene, RenderParams &P, int tag, cudaStream_t s, bool behind_pcie = false) {
     if (!scene->hints_enabled) return nullptr;
     const long long tiles = (long long)((P.local_cols + 3) / 4) * ((P.height + 7) / 8);
@@ -264,44 +271,50 @@ TileHint *hint_attach(ft_scene *scene, RenderParams &P, int tag, cudaStream_t s,
     }
     if (!slot) {
         slot = lru;
-        if (slot->ready) cudaEventSynchronize(slot->ready);  // its last user has finished
-        slot->release();
+        slot->release();  // waits for its last users
         std::memcpy(slot->key, key, sizeof(key));
         slot->n_tiles = (unsigned)tiles;
+        slot->mode = behind_pcie ? scene->hint_pcie_mode : FT_RANK_LPT;
         if (cudaMalloc(&slot->d_cost, sizeof(unsigned short) * (size_t)tiles) != cudaSuccess ||
-            cudaMalloc(&slot->d_snap, sizeof(unsigned short) * (size_t)tiles) != cudaSuccess ||
-            cudaMalloc(&slot->d_order, sizeof(unsigned) * (size_t)tiles) != cudaSuccess ||
-            cudaMalloc(&slot->d_keys, sizeof(unsigned short) * (size_t)tiles) != cudaSuccess ||
-            cudaMalloc(&slot->d_iota, sizeof(unsigned) * (size_t)tiles) != cudaSuccess ||
-            (slot->temp_bytes = tile_order_temp_bytes((unsigned)tiles)) == 0 ||
-            cudaMalloc(&slot->d_temp, slot->temp_bytes) != cudaSuccess ||
-            launch_tile_iota(slot->d_iota, (unsigned)tiles, s) != cudaSuccess ||
-            cudaEventCreateWithFlags(&slot->ready, cudaEventDisableTiming) != cudaSuccess ||
+            tile_rank_create((unsigned)tiles, behind_pcie ? scene->hint_pcie_shift : 0, s, &slot->rank) != cudaSuccess ||
+            cudaEventCreateWithFlags(&slot->ready[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&slot->ready[1], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&slot->snapped, cudaEventDisableTiming) != cudaSuccess ||
             cudaMemsetAsync(slot->d_cost, 0, sizeof(unsigned short) * (size_t)tiles, s) != cudaSuccess) {
             cudaGetLastError();
             slot->release();
             return nullptr;
         }
-    } else if (cudaStreamWaitEvent(s, slot->ready, 0) != cudaSuccess) {
+    }
+    const int parity = (int)(slot->frames & 1ull);
+    // the kernel overwrites d_cost (the previous frame's costs must have been copied out) and reads order[parity]
+    if ((slot->frames > 0 && cudaStreamWaitEvent(s, slot->snapped, 0) != cudaSuccess) ||
+        (slot->valid[parity] && cudaStreamWaitEvent(s, slot->ready[parity], 0) != cudaSuccess)) {
         cudaGetLastError();
         return nullptr;
     }
     slot->stamp = ++scene->hint_clock;
-    P.order = slot->valid ? slot->d_order : nullptr;
+    P.order = slot->valid[parity] ? tile_rank_order(slot->rank, parity) : nullptr;
     P.cost = slot->d_cost;
-    P.order_mode = (behind_pcie && scene->hint_interleave) ? 1 : 0;
+    P.order_mode = slot->mode == 1 ? 1 : 0;
+    P.order_shift = tile_rank_shift(slot->rank);
     return slot;
 }
 
-// after the render kernel has been enqueued on `s`: derive the next launch's order from the costs it records
-void hint_finish(TileHint *h, cudaStream_t s) {
+// after the render kernel has been enqueued on `s`: keep its costs and rank them on the scene's side stream
+void hint_finish(ft_scene *scene, TileHint *h, cudaStream_t s) {
     if (!h) return;
-    if (launch_tile_order(h->d_cost, h->d_snap, h->d_keys, h->d_iota, h->n_tiles, h->d_order, h->d_temp, h->temp_bytes, s) == cudaSuccess &&
-        cudaEventRecord(h->ready, s) == cudaSuccess) {
-        h->valid = true;
+    const int parity = (int)(h->frames & 1ull);
+    h->frames++;
+    cudaStream_t side = scene->hint_stream ? scene->hint_stream : s;
+    if (tile_rank_snapshot(h->rank, h->d_cost, parity, s) == cudaSuccess && cudaEventRecord(h->snapped, s) == cudaSuccess &&
+        (side == s || cudaStreamWaitEvent(side, h->snapped, 0) == cudaSuccess) &&
+        tile_rank_run(h->rank, parity, h->mode == FT_RANK_TIMED ? FT_RANK_TIMED : FT_RANK_LPT, scene->hint_split_pct, side) == cudaSuccess &&
+        cudaEventRecord(h->ready[parity], side) == cudaSuccess) {
+        h->valid[parity] = true;
     } else {
         cudaGetLastError();
-        h->valid = false;
+        h->valid[parity] = false;
     }
 }
 
@@ -735,10 +748,13 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
     }
     s->dev.sub_debug = 0;
     s->hints_enabled = getenv("FT_NO_TILE_HINT") == nullptr;
-    s->hint_interleave = getenv("FT_NO_HINT_INTERLEAVE") == nullptr;  // experiments only
+    if (const char *d = getenv("FT_HINT_PCIE_MODE")) s->hint_pcie_mode = std::min(std::max(atoi(d), 0), 2);  // experiments only
+    if (const char *d = getenv("FT_HINT_PCIE_SHIFT")) s->hint_pcie_shift = std::min(std::max(atoi(d), 0), 4);
+    if (const char *d = getenv("FT_HINT_SPLIT")) s->hint_split_pct = std::min(std::max(atoi(d), 1), 1000);
     if (const char *d = getenv("FT_SUB_DEBUG")) s->dev.sub_debug = atoi(d);  // tests: 1 = distrust every certificate
     if (getenv("FT_NO_ESCAPE")) s->dev.esc_valid = 0;  // experiments only
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&s->hint_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto &ev : s->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -932,7 +948,7 @@ FT_API int ft_render_strips_device(ft_scene *scene, const ft_camera *camera, int
     TileHint *hint = hint_attach(scene, P, 0, s);
     cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render, scene->dev, *camera, P, d_out_rgb, d_out_leaf, wc, stats ? scene->d_stats : nullptr, count, scene->sm_count, s, false);
     if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
-    hint_finish(hint, s);
+    hint_finish(scene, hint, s);
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -984,7 +1000,7 @@ FT_API int ft_render_gather_device(ft_scene *scene, const ft_camera *camera, int
     TileHint *hint = hint_attach(scene, P, to_host ? 1 : 0, s, to_host);
     cudaError_t e = FT_DISPATCH((flags & FT_FLAG_FAST_MATH), launch_render_gather, scene->dev, *camera, P, d_dst, n_dst, wc, stats ? scene->d_stats : nullptr, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "render-gather kernel launch");
-    hint_finish(hint, s);
+    hint_finish(scene, hint, s);
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
         CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -1093,7 +1109,7 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
             cudaError_t e = FT_DISPATCH(fast, launch_render, scene->dev, *camera, P, m_rgb, m_leaf, wc, scene->d_stats, count, scene->sm_count, s, true);
             if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
             CU(cudaEventRecord(scene->ev[1], s));
-            hint_finish(hint, s);
+            hint_finish(scene, hint, s);
             CU(cudaMemcpyAsync(scene->h_stats, scene->d_stats, kStatWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
             CU(cudaEventRecord(scene->ev[2], s));
             CU(cudaStreamSynchronize(s));  // kernel completion makes its system-scope stores visible to the host
@@ -1137,7 +1153,7 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
         if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
         launches++;
         CU(cudaEventRecord((launches & 1) ? scene->ev[1] : scene->ev[3], bs));  // end of the last kernel on each stream
-        hint_finish(hint, bs);
+        hint_finish(scene, hint, bs);
         CU(cudaMemcpyAsync(out_rgb + (size_t)x0 * height * 3, band_rgb, (size_t)cols * height * 3 * sizeof(float),
                            cudaMemcpyDeviceToHost, bs));
         if (out_leaf)

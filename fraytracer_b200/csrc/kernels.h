@@ -30,9 +30,13 @@ struct RenderParams {
     // iteration count for the next launch (null: not recorded).
     const unsigned *order;
     unsigned short *cost;
-    int order_mode;      // 0: order[] as it is (most expensive first); 1: expensive and cheap tiles alternate (order[0], order[n-1],
+    int order_mode;      // 0: order[] as it is (most expensive first); 1: expensive and cheap units alternate (order[0], order[n-1],
                          // order[1], order[n-2] ...) -- for destinations behind PCIe, where the cheap tiles' stores must not all
                          // arrive at the end of the launch
+    int order_shift;     // order[] ranks units of (1 << order_shift) consecutive tiles (vertical neighbours: tile ids run along y).
+                         // 0 for device destinations; 2 behind PCIe, where neighbouring 96-byte column runs must be written at about
+                         // the same time to leave the GPU as full lines (measured, tools/micro/pcie_store.cu: 4x8 tiles in
+                         // scattered order 29 GB/s, in natural order 47 GB/s, 4x32 units in scattered order 46-48 GB/s)
 };
 
 // Which pixels a rank renders and where they go (multi-GPU): column strips dealt round-robin
@@ -83,11 +87,18 @@ FT_DECLARE_LAUNCHERS(ft_fast)
 cudaError_t launch_deinterleave(const float *gathered, int width, int height, int strip_width, int world, int channels,
                                 int first_local_strip, int n_local_strips, float *out, cudaStream_t stream);
 cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estimate);
-// tiles sorted by descending cost (stable radix sort of a private snapshot of `cost`): order[] is a permutation of 0..n-1
-size_t tile_order_temp_bytes(unsigned n);
-cudaError_t launch_tile_iota(unsigned *v, unsigned n, cudaStream_t stream);
-cudaError_t launch_tile_order(const unsigned short *cost, unsigned short *snapshot, unsigned short *sorted_keys, const unsigned *iota,
-                              unsigned n, unsigned *order, void *temp, size_t temp_bytes, cudaStream_t stream);
+
+// tile_rank.cu: the order in which the next frames' tiles are drawn, from the per-tile costs a frame recorded
+struct TileRank;
+enum { FT_RANK_LPT = 0, FT_RANK_TIMED = 2 };
+cudaError_t tile_rank_create(unsigned n_tiles, int shift, cudaStream_t stream, TileRank **out);
+void tile_rank_destroy(TileRank *r);
+// on the render stream, right after the kernel that wrote cost[]: keep the frame's unit costs (frames alternate in parity)
+cudaError_t tile_rank_snapshot(TileRank *r, const unsigned short *cost, int parity, cudaStream_t stream);
+// on any stream ordered after the snapshot: order[parity] = the units in drawing order
+cudaError_t tile_rank_run(TileRank *r, int parity, int mode, int split_pct, cudaStream_t stream);
+const unsigned *tile_rank_order(const TileRank *r, int parity);
+int tile_rank_shift(const TileRank *r);
 
 // post_kernels.cu
 // strip_width > 0: only the columns of the strips `rank` owns (strip s -> rank s % world); 0: the whole frame

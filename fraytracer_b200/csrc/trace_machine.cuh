@@ -53,13 +53,25 @@ enum : int {
     PH_PROBE = 7,     // Distance at the common origin of all primary rays (render jobs), once per warp
 };
 
-// Scheduling hint (RenderParams::order): the n-th chunk drawn from the work counter is tile order[n] of the previous launch's
-// cost ranking, or -- order_mode 1 -- the ranking read from both ends alternately.
+// Scheduling hint (RenderParams::order): the n-th chunk drawn from the work counter belongs to unit order[n >> shift] of the
+// previous launch's cost ranking (a unit = 1 << shift vertically adjacent tiles), or -- order_mode 1 -- of the ranking read from
+// both ends alternately.  The last unit may be partial: its missing tiles map beyond n_items and are skipped by the caller.
 __device__ __forceinline__ long long hinted_chunk(const RenderParams &P, long long base, long long n_items) {
     if (!P.order) return base;
-    long long t = base >> 5;
-    if (P.order_mode == 1) t = (t & 1) ? (n_items >> 5) - 1 - (t >> 1) : (t >> 1);
-    return (long long)__ldg(P.order + t) << 5;
+    const long long t = base >> 5;
+    const int sh = P.order_shift;
+    long long u = t >> sh;
+    if (P.order_mode == 1) {
+        const long long n_units = ((n_items >> 5) + (1ll << sh) - 1) >> sh;
+        u = (u & 1) ? n_units - 1 - (u >> 1) : (u >> 1);
+    }
+    return (((long long)__ldg(P.order + u) << sh) + (t & ((1ll << sh) - 1))) << 5;
+}
+// chunks to draw: whole units when a ranking is attached
+__device__ __forceinline__ long long hinted_total(const RenderParams &P, long long n_items) {
+    if (!P.order) return n_items;
+    const int sh = P.order_shift;
+    return ((((n_items >> 5) + (1ll << sh) - 1) >> sh) << sh) << 5;
 }
 
 // ---- work sources -----------------------------------------------------------------------------------------
@@ -127,8 +139,9 @@ struct RenderJobT {
     // framebuffers (PCIe / NVLink write efficiency) -- anything else pixel by pixel.
     static constexpr bool kTileCost = true;
     __device__ __forceinline__ long long map_chunk(long long base) const { return hinted_chunk(P, base, n_items); }
+    __device__ __forceinline__ long long draw_total() const { return hinted_total(P, n_items); }
     __device__ __forceinline__ void note_cost(long long base, unsigned iters) const {
-        if (P.cost) P.cost[base >> 5] = (unsigned short)(iters < 65535u ? iters : 65535u);
+        if (P.cost && base < n_items) P.cost[base >> 5] = (unsigned short)(iters < 65535u ? iters : 65535u);
     }
     static constexpr bool kTileStore = TILE;  // launch_render picks it for destinations behind PCIe (mapped host memory)
     __device__ __forceinline__ int *out_leaf_ptr() const { return out_leaf; }
@@ -208,8 +221,9 @@ struct GatherJob {
     }
     static constexpr bool kTileCost = true;
     __device__ __forceinline__ long long map_chunk(long long base) const { return hinted_chunk(P, base, n_items); }
+    __device__ __forceinline__ long long draw_total() const { return hinted_total(P, n_items); }
     __device__ __forceinline__ void note_cost(long long base, unsigned iters) const {
-        if (P.cost) P.cost[base >> 5] = (unsigned short)(iters < 65535u ? iters : 65535u);
+        if (P.cost && base < n_items) P.cost[base >> 5] = (unsigned short)(iters < 65535u ? iters : 65535u);
     }
     // see RenderJob::store_tile; the tile's four columns are consecutive image columns when the strip width is a multiple of 4
     static constexpr bool kTileStore = true;
@@ -285,6 +299,7 @@ struct RaysJob {
     static constexpr bool kTileStore = false;
     static constexpr bool kTileCost = false;
     __device__ __forceinline__ long long map_chunk(long long base) const { return base; }
+    __device__ __forceinline__ long long draw_total() const { return n; }
     __device__ __forceinline__ void note_cost(long long, unsigned) const {}
     __device__ __forceinline__ int *out_leaf_ptr() const { return nullptr; }
     __device__ __forceinline__ void store_tile(long long, const float *, unsigned, int) const {}
@@ -299,7 +314,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                                                      unsigned long long *__restrict__ stats) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const long long total = job.total();
+    const long long total = job.total(), draw_total = job.draw_total();
 
     // lane state
     int phase = Job::kProbe ? PH_PROBE : PH_FETCH;
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                         unsigned long long base = 0;
                         if (lane == 0) base = atomicAdd(work_counter, (unsigned long long)FT_CHUNK);
                         base = __shfl_sync(FULL, base, 0);
-                        if ((long long)base >= total) {
+                        if ((long long)base >= draw_total) {
                             exhausted = true;
                             break;
                         }

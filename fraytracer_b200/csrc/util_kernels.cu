@@ -1,6 +1,4 @@
 // util_kernels.cu -- strip de-interleave after the multi-GPU all-gather, and the FP32 peak probe.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "kernels.h"
 
 // gathered: [world][n_local_strips][strip_width][height][channels], holding local strips
@@ -92,36 +90,4 @@ cudaError_t measure_fp32_peak(int device, float *tflops_fma, float *sm_mhz_estim
     // 128 FP32 lanes per SM, 2 flops per FFMA
     if (sm_mhz_estimate) *sm_mhz_estimate = (float)(best * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6);
     return cudaSuccess;
-}
-
-
-// ---- tile order for the next frame (ft_api.cu TileHint): longest-processing-time-first.  A persistent grid hands out tiles
-// from one counter; a tile is a serial chain of up to hundreds of Distance evaluations, so the launch ends when the last
-// long tile does -- started late, it leaves every other SM idle (ncu: sm__cycles_active.avg 82 % of elapsed).  Costs measured
-// by one frame order the next one: a stable descending radix sort (CUB) of (cost, tile) over a private snapshot of the costs.
-__global__ void __launch_bounds__(256) tile_iota_kernel(unsigned *__restrict__ v, unsigned n) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = i;
-}
-
-size_t tile_order_temp_bytes(unsigned n) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const unsigned short *)nullptr, (unsigned short *)nullptr,
-                                              (const unsigned *)nullptr, (unsigned *)nullptr, (int)n, 0, 16);
-    return bytes;
-}
-
-cudaError_t launch_tile_iota(unsigned *v, unsigned n, cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    tile_iota_kernel<<<(n + 255) / 256, 256, 0, stream>>>(v, n);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_tile_order(const unsigned short *cost, unsigned short *snapshot, unsigned short *sorted_keys, const unsigned *iota,
-                              unsigned n, unsigned *order, void *temp, size_t temp_bytes, cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaMemcpyAsync(snapshot, cost, sizeof(unsigned short) * (size_t)n, cudaMemcpyDeviceToDevice, stream);
-    if (e != cudaSuccess) return e;
-    return cub::DeviceRadixSort::SortPairsDescending(temp, temp_bytes, (const unsigned short *)snapshot, sorted_keys, iota, order, (int)n,
-                                                     0, 16, stream);
 }

@@ -471,9 +471,10 @@ def test_subgrid_certified_path_equals_sequential_scan(make, monkeypatch):
 
 @pytest.mark.gpu
 def test_tile_order_hints_change_nothing_but_the_schedule():
-    """ft_api.cu TileHint: from the second frame of a shape on, tiles are drawn most-expensive-first as measured by the previous
-    frame.  Pixels are independent of the order tiles are drawn in: every path (staged ft_render, zero-copy ft_render, device
-    strips, fused gather) must return the first frame's bits again and again, and the frame rendered with hints disabled."""
+    """ft_api.cu TileHint / tile_rank.cu: from the third frame of a shape on, tiles are drawn in an order ranked from the costs
+    an earlier frame recorded (most expensive first; a timed merge of expensive and cheap tiles for host destinations).  Pixels are
+    independent of the order tiles are drawn in: every path (staged ft_render, zero-copy ft_render, device strips, fused gather)
+    must return the first frame's bits again and again, and the frame rendered with hints disabled."""
     import ctypes as C
 
     import torch
@@ -487,8 +488,8 @@ def test_tile_order_hints_change_nothing_but_the_schedule():
     mapped = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(X, Y, 3))
     dev = torch.empty((X, Y, 3), dtype=torch.float32, device="cuda:0")
     dst = [torch.zeros((X, Y, 3), dtype=torch.float32, device="cuda:0") for _ in range(2)]
-    for frame in range(4):  # frame 0 runs unhinted and measures, frames 1.. are ordered by the previous frame's costs
-        tracer.set_debug(4 if frame == 3 else 0)  # the last frame: hints disabled again
+    for frame in range(6):  # frames 0 and 1 run unhinted and measure, frames 2.. are ordered by the costs of frame N - 2
+        tracer.set_debug(4 if frame == 5 else 0)  # the last frame: hints disabled again
         rgb, leaf, _ = tracer.render(w.camera, w.size, w.epsilon, w.length, want_leaf=True)  # pageable: two staged bands
         assert np.array_equal(bits(rgb), bits(ref["rgb"])) and np.array_equal(leaf, ref["leaf"]), frame
         mapped.fill(-1.0)
