@@ -21,4 +21,5 @@ struct CloudParams {
     unsigned long long *stats;
 };
 
-cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, int sm_count, cudaStream_t stream);  // trace + resolve
+// trace + resolve; count: the instrumented variant (algorithmic flops into the stats block)
+cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, bool count, int sm_count, cudaStream_t stream);

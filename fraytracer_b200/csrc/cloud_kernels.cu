@@ -124,7 +124,13 @@ __global__ void __launch_bounds__(CB) cloud_resolve_kernel(const __grid_constant
     P.T.store((unsigned long long)x * P.height + y, t.x / inv, t.y / inv, t.z / inv);
 }
 
-template <bool CHAIN>
+// algorithmic operation counts of the extension's own steps (the evaluator counts its own, trace_device.cuh)
+constexpr int FLOPS_TRACK_STEP = 11;  // t, p = o + d t, the two comparisons
+constexpr int FLOPS_DENSITY = 95;     // cloud_density: Noise.gradient in float64 (82) + the float32 shaping (13)
+constexpr int FLOPS_SAMPLE_RAY = 29;  // jittered camera ray (Camera.uniformPixelToRay + 4)
+
+// COUNT: instrumented variant (algorithmic flops into the stats block; bench.py's roofline numerator)
+template <bool CHAIN, bool COUNT>
 __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_constant__ DevScene S, const __grid_constant__ CloudParams P) {
     __shared__ NoiseTab tab;
     for (int i = threadIdx.x; i < 256; i += CB) tab.perm[i] = P.perm[i];
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
     Acc acc{0ull, 0ull};
     uint32_t best_dummy = 0u, hit_best = 0u;  // eval_chain's arg-min note: kept at a hit, it names the material's leaf (FT_CHAIN_MAT)
     // Distance at the common origin of all camera rays, once per warp
-    const float d0 = CHAIN ? eval_chain<false>(S, cam, acc, best_dummy) : eval_form<false>(S, S.root_word, cam, acc);
+    const float d0 = CHAIN ? eval_chain<COUNT>(S, cam, acc, best_dummy) : eval_form<COUNT>(S, S.root_word, cam, acc);
 
     int phase = C_FETCH;
     bool have_tile = false, active = false, cloud_mode = false;
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             }
             seg = 0;
             phase = C_MARCH;
+            add_flops<COUNT>(acc, FLOPS_SAMPLE_RAY);
         }
         // ------------------------------------------------------------------ pre-checks
         // event: 1 march miss, 2 march hit, 3 shadow unoccluded, 4 shadow occluded, 5 normal done, 6 sample ends on the
@@ -234,9 +241,10 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
         // ------------------------------------------------------------------ the one distance evaluation
         if (phase > C_FETCH && event == 0) {
             uint32_t best_lo = 0u;
-            const float dist = CHAIN ? eval_chain<false>(S, p, acc, best_lo) : eval_form<false>(S, S.root_word, p, acc);
+            const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
             if (phase <= C_SHADOW) {
                 steps++;
+                add_flops<COUNT>(acc, FLOPS_MOVE + 1);
                 if (dist < eps) {
                     event = phase == C_MARCH ? 2 : 4;
                     if (phase == C_MARCH) hit_best = best_lo;  // the hit evaluation's arg-min candidate
@@ -255,9 +263,11 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                 phase = C_N3;
             } else if (phase == C_N3) {
                 n = normalize(n - V3{dist, dist, dist});
+                add_flops<COUNT>(acc, FLOPS_NORMAL);
                 event = 5;
             } else {  // tracking step inside the medium
                 n_track++;
+                add_flops<COUNT>(acc, FLOPS_TRACK_STEP);
                 if (dist >= eps) {
                     if (phase == C_TRACK) {  // left the medium: the camera ray goes on as an ordinary ray
                         seg++;
@@ -292,6 +302,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                         float u1;
                         cloud_rnd(P, pixel, (uint32_t)s, k, stream + (phase == C_LTRACK ? 1u + (uint32_t)light : 0u), ucur, u1);
                     }
+                    add_flops<COUNT>(acc, FLOPS_DENSITY);
                     if (ucur < cloud_density(tab, P, p, dist) * P.step) {
                         if (phase == C_TRACK) {  // real collision: single scattering at p
                             n_scattered++;
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                 phase = C_N0;
             } else if (event == 5) {
                 const int leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, ho, hit_best)
-                                                                                  : material_leaf<false>(S, ho, acc);
+                                                                                  : material_leaf<COUNT>(S, ho, acc);
                 mat = __ldg(S.objects + leaf_obj).z;
                 if (__float_as_uint(ld4(S.materials + mat).w) == (uint32_t)FT_MATERIAL_CLOUD) {
                     stream = 1u + seg * nstreams;
@@ -340,6 +351,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                 next_light = true;
             } else {  // a light is decided: 3 / 7 it contributes, 4 / 8 it does not
                 if (event == 3 || event == 7) lc = cloud_mode ? lc + cint : lc + cint * lcos;
+                add_flops<COUNT>(acc, 6);
                 light++;
                 next_light = true;
             }
@@ -348,6 +360,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                 for (; light < S.n_lights; light++) {
                     const float4 lv = ld4(S.lights + 2 * light), lrgb = ld4(S.lights + 2 * light + 1);
                     const bool directional = __float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL;
+                    add_flops<COUNT>(acc, directional ? FLOPS_LIGHT : FLOPS_LIGHT + FLOPS_POINT_LIGHT);
                     if (cloud_mode) {  // isotropic scattering: every light, visibility by tracking
                         cint = xyz(lrgb);
                         maxdist = __int_as_float(0x7f800000);
@@ -393,10 +406,12 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                     const V3 albedo = xyz(ld4(S.materials + mat));
                     const float pi_inv = 1.0f / 3.14159274f;
                     L = cloud_mode ? albedo * (lc * (pi_inv * 0.25f)) : albedo * (lc * pi_inv);
+                    add_flops<COUNT>(acc, FLOPS_FINAL);
                 }
             }
             if (finish) {
                 sum = sum + L;
+                add_flops<COUNT>(acc, 3);
                 s++;
                 phase = C_FETCH;
             }
@@ -417,23 +432,36 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
         if (scattered) atomicAdd(st + FT_STAT_PATHS, (unsigned long long)scattered);
         if (n_track) atomicAdd(st + FT_STAT_STEPS, n_track);
     }
+    if (COUNT) {
+        unsigned long long fl = acc.flops;
+        for (int sh = 16; sh > 0; sh >>= 1) fl += __shfl_xor_sync(FULL, fl, sh);
+        if (lane == 0) atomicAdd(P.stats + ((blockIdx.x * (CB / 32) + (threadIdx.x >> 5)) & (FT_STAT_SLOTS - 1)) * FT_STAT_STRIDE + FT_STAT_FLOPS, fl);
+    }
 }
 
 }  // namespace ft_cloud
 
-cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, int sm_count, cudaStream_t stream) {
+template <bool CHAIN, bool COUNT>
+static cudaError_t cloud_launch_variant(const DevScene &S, const CloudParams &P, int sm_count, cudaStream_t stream) {
     using namespace ft_cloud;
-    if (P.n_tiles <= 0) return cudaSuccess;
     int per_sm = 0;
-    cudaError_t e = S.chain_valid ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cloud_kernel<true>, CB, 0)
-                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cloud_kernel<false>, CB, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cloud_kernel<CHAIN, COUNT>, CB, 0);
     if (e != cudaSuccess) return e;
     long long grid = (long long)(per_sm < 1 ? 1 : per_sm) * sm_count;
     const long long need = (P.n_tiles * FT_CLOUD_SAMPLE_GROUPS + CB / 32 - 1) / (CB / 32);
     if (grid > need) grid = need;
-    if (S.chain_valid) cloud_kernel<true><<<(unsigned)grid, CB, 0, stream>>>(S, P);
-    else cloud_kernel<false><<<(unsigned)grid, CB, 0, stream>>>(S, P);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    cloud_kernel<CHAIN, COUNT><<<(unsigned)grid, CB, 0, stream>>>(S, P);
+    return cudaGetLastError();
+}
+
+// count: the instrumented variant (algorithmic flops into the stats block)
+cudaError_t cloud_launch(const DevScene &S, const CloudParams &P, bool count, int sm_count, cudaStream_t stream) {
+    using namespace ft_cloud;
+    if (P.n_tiles <= 0) return cudaSuccess;
+    cudaError_t e;
+    if (S.chain_valid) e = count ? cloud_launch_variant<true, true>(S, P, sm_count, stream) : cloud_launch_variant<true, false>(S, P, sm_count, stream);
+    else e = count ? cloud_launch_variant<false, true>(S, P, sm_count, stream) : cloud_launch_variant<false, false>(S, P, sm_count, stream);
+    if (e != cudaSuccess) return e;
     cloud_resolve_kernel<<<(unsigned)((P.n_tiles * 32 + CB - 1) / CB), CB, 0, stream>>>(P);
     return cudaGetLastError();
 }

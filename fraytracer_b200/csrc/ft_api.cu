@@ -132,6 +132,7 @@ struct ft_scene {
     cudaStream_t hint_stream = nullptr;  // the tile rankings are computed here, beside the caller's stream
     unsigned long long hint_clock = 0;
     bool hints_enabled = true;
+    bool ext_count = false;  // ft_scene_set_debug bit 3
     // destinations behind PCIe (mapped host memory): FT_RANK_TIMED by default (tile_rank.cu); 0 = plain LPT, 1 = LPT read from
     // both ends alternately (RenderParams::order_mode) -- experiments
     int hint_pcie_mode = FT_RANK_TIMED, hint_pcie_shift = 0, hint_split_pct = 150;
@@ -403,8 +404,8 @@ int spectral_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32
     const size_t rgb_bytes = out_rgb ? (npix * 3 * sizeof(float) + 255) & ~(size_t)255 : 0;
     CU(scene->reserve(rgb_bytes + npix_local * 3 * sizeof(float4)));  // (image +) worst-case hit queue of this rank's strips
     if (!scene->d_spec_counts) {
-        CU(cudaMalloc(&scene->d_spec_counts, 512 * sizeof(unsigned)));
-        CU(cudaMallocHost(&scene->h_spec_counts, 512 * sizeof(unsigned)));
+        CU(cudaMalloc(&scene->d_spec_counts, 1024 * sizeof(unsigned)));
+        CU(cudaMallocHost(&scene->h_spec_counts, 1024 * sizeof(unsigned)));
     }
     SpectralParams P{};
     P.cam = *camera;
@@ -424,17 +425,18 @@ int spectral_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32
     }
     P.T = T;
     P.hit_q = (float4 *)((char *)scene->d_scratch + rgb_bytes);
-    unsigned *counts = scene->d_spec_counts;  // [0] glass hits, [1 + w] live paths entering wave w
+    unsigned *counts = scene->d_spec_counts;  // [0] glass hits, [2 w], [2 w + 1] live paths of either class entering wave w
     P.hit_count = counts;
     P.stats = scene->d_stats;
     CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
-    CU(cudaMemsetAsync(counts, 0, 512 * sizeof(unsigned), s));
+    CU(cudaMemsetAsync(counts, 0, 1024 * sizeof(unsigned), s));
     CU(cudaEventRecord(scene->ev[0], s));
     int launches = 0;
     // ---- wave 0: primary rays
     P.wave = 0;
     CU(fresh_counter(scene, s, &P.work_counter));
-    cudaError_t e = spectral_launch_primary(scene->dev, P, scene->sm_count, s);
+    const bool count = scene->ext_count;
+    cudaError_t e = spectral_launch_primary(scene->dev, P, count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "spectral primary kernel launch");
     launches++;
     CU(cudaMemcpyAsync(scene->h_spec_counts, counts, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
@@ -450,21 +452,22 @@ int spectral_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32
         float4 *qa = (float4 *)((char *)scene->d_scratch2 + slot_bytes), *qb = (float4 *)((char *)qa + q_bytes);
         // ---- the material stage of wave 0
         P.out_q = qa;
+        P.out_count = counts + 2;
+        P.q_cap = (unsigned)n_paths0;
+        P.split = getenv("FT_SPEC_NO_SPLIT") == nullptr;  // experiments only
         e = spectral_launch_spawn(scene->dev, P, n_hits, s);
         if (e != cudaSuccess) return cuda_fail(e, "spectral spawn kernel launch");
         launches++;
         if (max_bounces > 0) {
-            scene->h_spec_counts[1] = (unsigned)n_paths0;  // pinned
-            CU(cudaMemcpyAsync(counts + 1, scene->h_spec_counts + 1, sizeof(unsigned), cudaMemcpyHostToDevice, s));
             // ---- waves 1 .. max_bounces (a wave whose queue is empty exits at once)
             for (int w = 1; w <= max_bounces; w++) {
                 P.wave = w;
                 P.in_q = (w & 1) ? qa : qb;
                 P.out_q = (w & 1) ? qb : qa;
-                P.in_count = counts + w;
-                P.out_count = counts + w + 1;
+                P.in_count = counts + 2 * w;
+                P.out_count = counts + 2 * w + 2;
                 CU(fresh_counter(scene, s, &P.work_counter));
-                e = spectral_launch_wave(scene->dev, P, (long long)n_paths0, scene->sm_count, s);
+                e = spectral_launch_wave(scene->dev, P, (long long)n_paths0, count, scene->sm_count, s);
                 if (e != cudaSuccess) return cuda_fail(e, "spectral wave kernel launch");
                 launches++;
             }
@@ -486,6 +489,8 @@ int spectral_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32
         stats->primary_rays = owned_pixels(T, width, height);
         stats->shadow_rays += (int64_t)paths;  // every secondary ray: shadow rays + continuation segments
         stats->reserved = (int32_t)n_hits;     // pixels whose primary ray hit glass
+        if (count)  // the material stage (60 per path, FLOPS_GLASS) and the per-pixel wavelength sums (9 per wavelength + 3)
+            stats->eval_flops += (int64_t)n_paths0 * (max_bounces > 0 ? 60 : 0) + (int64_t)n_hits * (9 * n_wavelengths + 3);
         stats->launches = launches;
         cudaEventElapsedTime(&stats->kernel_ms, scene->ev[0], scene->ev[1]);
         cudaEventElapsedTime(&stats->total_ms, scene->ev[0], scene->ev[2]);
@@ -552,7 +557,7 @@ int cloud_core(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t 
     CU(cudaMemsetAsync(scene->d_stats, 0, kStatWords * sizeof(unsigned long long), s));
     CU(fresh_counter(scene, s, &P.work_counter));
     CU(cudaEventRecord(scene->ev[0], s));
-    cudaError_t e = cloud_launch(scene->dev, P, scene->sm_count, s);
+    cudaError_t e = cloud_launch(scene->dev, P, scene->ext_count, scene->sm_count, s);
     if (e != cudaSuccess) return cuda_fail(e, "cloud kernel launch");
     CU(cudaEventRecord(scene->ev[1], s));
     if (out_rgb) CU(cudaMemcpyAsync(out_rgb, T.dst[0], npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -815,6 +820,7 @@ FT_API int ft_scene_set_debug(ft_scene *scene, int32_t sub_debug) {
     std::lock_guard<std::mutex> lock(scene->mu);
     scene->dev.sub_debug = sub_debug & 3;
     scene->hints_enabled = (sub_debug & 4) == 0 && getenv("FT_NO_TILE_HINT") == nullptr;  // bit 2: natural tile order, no hints
+    scene->ext_count = (sub_debug & 8) != 0;  // bit 3: the extension entry points run their instrumented kernels (eval_flops, march_steps)
     return FT_OK;
 }
 

@@ -17,16 +17,25 @@ struct SpectralParams {
     StripTarget T;      // the rank's strips and the destination framebuffers
     float4 *hit_q;      // glass hits of wave 0: {origin, Length} {direction, bits(pixel)} {normal, bits(material)}
     unsigned *hit_count;
+    // Path queues are filled from both ends: continuation segments expected to run INSIDE glass (transmitted into it, or
+    // reflected internally) are appended from index 0 upwards, segments in free space from index q_cap - 1 downwards.  The two
+    // classes differ by an order of magnitude in length (a few steps to the far side of a glass body against a march through
+    // the scene plus shading with its shadow rays); a 32-path chunk never mixes them, so lockstep lanes finish together.
+    // count[0] / count[1] = paths of either class.  split == 0: one class (everything from index 0; experiments).
     const float4 *in_q;  // live paths: {origin, dir.x} {dir.y, dir.z, Length, bits(pixel)} {bits(slot), bits(k), -, -}
     const unsigned *in_count;
     float4 *out_q;
     unsigned *out_count;
+    unsigned q_cap;
+    int split;
     float *slots;  // radiance of path (glass hit h, wavelength k) at h * nl + k
     unsigned long long *work_counter;
     unsigned long long *stats;
 };
 
-cudaError_t spectral_launch_primary(const DevScene &S, const SpectralParams &P, int sm_count, cudaStream_t stream);
+// count: the instrumented variant (algorithmic flops and march steps into the stats block)
+cudaError_t spectral_launch_primary(const DevScene &S, const SpectralParams &P, bool count, int sm_count, cudaStream_t stream);
 cudaError_t spectral_launch_spawn(const DevScene &S, const SpectralParams &P, unsigned n_hits, cudaStream_t stream);
-cudaError_t spectral_launch_wave(const DevScene &S, const SpectralParams &P, long long max_items, int sm_count, cudaStream_t stream);
+cudaError_t spectral_launch_wave(const DevScene &S, const SpectralParams &P, long long max_items, bool count, int sm_count,
+                                 cudaStream_t stream);
 cudaError_t spectral_launch_resolve(const SpectralParams &P, unsigned n_hits, cudaStream_t stream);

@@ -32,10 +32,10 @@
 namespace ft_spectral {
 
 constexpr int SB = 128;  // threads per CTA
+constexpr unsigned FULL = 0xffffffffu;
 #ifndef FT_SPEC_MINB
 #define FT_SPEC_MINB 8  // <= 64 registers.  Measured (config 3, 4K): 4 CTAs/SM 139.8 ms, 6: 114.9, 8: 108.1, 10: 115.6
 #endif
-constexpr unsigned FULL = 0xffffffffu;
 
 enum : int {
     SP_FETCH = 0,
@@ -91,6 +91,7 @@ __device__ __forceinline__ void write_pixel_from_bands(const StripTarget &T, lon
 struct Continuation {
     V3 o, d;
     float len;
+    bool into_glass;  // the medium the continuation is expected to run in (the march itself decides from the sign of Distance)
 };
 __device__ __forceinline__ Continuation glass_interact(V3 ab, float nu, uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel,
                                                        uint32_t k, uint32_t bounce, V3 ho, V3 hd, float hlen, float eps,
@@ -118,11 +119,32 @@ __device__ __forceinline__ Continuation glass_interact(V3 ab, float nu, uint32_t
     ft_philox4x32_10(c, seed_lo, seed_hi);
     const float u = __uint2float_rn(c[0]) * 2.3283064365386963e-10f;  // == (float)(c0 * 2^-32 in double)
     Continuation r;
-    if (u < reflectance) r.d = normalize(hd - N * (2.0f * cosi));  // Light.fs:57
-    else r.d = normalize(hd * n1n2 + N * (n1n2cosi - cost));         // Light.fs:58
+    const bool reflect = u < reflectance;
+    if (reflect) r.d = normalize(hd - N * (2.0f * cosi));     // Light.fs:57
+    else r.d = normalize(hd * n1n2 + N * (n1n2cosi - cost));  // Light.fs:58
+    r.into_glass = reflect ? inside != 0 : inside == 0;
     r.o = ho + r.d * (2.0f * eps);
     r.len = hlen - 2.0f * eps;
     return r;
+}
+
+// queue append of the lanes with `push` set: ballot + popc ranks, one atomic per warp and class; returns the lane's index
+__device__ __forceinline__ unsigned queue_slot(const SpectralParams &P, bool push, bool into_glass, int lane) {
+    const bool front = into_glass || !P.split;
+    const unsigned pa = __ballot_sync(FULL, push && front), pb = __ballot_sync(FULL, push && !front);
+    unsigned base_a = 0, base_b = 0;
+    if (pa) {
+        const int leader = __ffs(pa) - 1;
+        if (lane == leader) base_a = atomicAdd(P.out_count, (unsigned)__popc(pa));
+        base_a = __shfl_sync(FULL, base_a, leader);
+    }
+    if (pb) {
+        const int leader = __ffs(pb) - 1;
+        if (lane == leader) base_b = atomicAdd(P.out_count + 1, (unsigned)__popc(pb));
+        base_b = __shfl_sync(FULL, base_b, leader);
+    }
+    const unsigned below = (1u << lane) - 1u;
+    return front ? base_a + (unsigned)__popc(pa & below) : P.q_cap - 1u - (base_b + (unsigned)__popc(pb & below));
 }
 
 __device__ __forceinline__ void store_path(float4 *q, unsigned idx, const Continuation &c, uint32_t pixel, uint32_t slot, uint32_t k) {
@@ -134,11 +156,20 @@ __device__ __forceinline__ void store_path(float4 *q, unsigned idx, const Contin
 // ---- wave kernels ----------------------------------------------------------------------------------------
 // One distance-evaluation call site; every lane runs a small state machine (march -> 4 normal probes -> light
 // loop with shadow marches), whole 32-item chunks in lockstep like the hot path's ray machine.
-template <bool CHAIN, bool PRIMARY>
+// algorithmic float32 operations of the extension's own steps (the evaluator counts its own, trace_device.cuh)
+constexpr int FLOPS_SPEC = 8;            // spec(rgb, band): 3 mul, 4 add, 1 div
+constexpr int FLOPS_GLASS = 60;          // Cauchy index, Light.fresnel, reflect / transmit direction, new origin
+constexpr int FLOPS_BAND_SUM = 9;        // per wavelength of the pixel sum: 3 mul, 6 add
+
+// COUNT: instrumented variant (algorithmic flops and march steps into the stats block; bench.py's roofline numerator)
+template <bool CHAIN, bool PRIMARY, bool COUNT>
 __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ SpectralParams P) {
     const int lane = threadIdx.x & 31;
     const float eps = P.epsilon;
-    const long long total = PRIMARY ? P.n_items : (long long)__ldg(P.in_count);
+    // path waves: the front class occupies whole chunks [0, front_pad), the back class follows
+    const unsigned n_front = PRIMARY ? 0u : __ldg(P.in_count), n_back = PRIMARY ? 0u : __ldg(P.in_count + 1);
+    const long long front_pad = ((long long)n_front + 31) & ~31ll;
+    const long long total = PRIMARY ? P.n_items : front_pad + (long long)n_back;
     constexpr int NB = PRIMARY ? 6 : 1;
 
     Acc acc{0ull, 0ull};
@@ -146,7 +177,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
     float d0 = 0.f;
     if (PRIMARY) {  // Distance at the common origin of all primary rays, once per warp
         const V3 c = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
-        d0 = CHAIN ? eval_chain<false>(S, c, acc, best_dummy) : eval_form<false>(S, S.root_word, c, acc);
+        d0 = CHAIN ? eval_chain<COUNT>(S, c, acc, best_dummy) : eval_form<COUNT>(S, S.root_word, c, acc);
     }
 
     int phase = SP_FETCH;
@@ -168,7 +199,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
             base = __shfl_sync(FULL, base, 0);
             if ((long long)base >= total) break;
             const long long i = (long long)base + lane;
-            if (i < total) {
+            if (i < total && (PRIMARY || i >= front_pad || i < (long long)n_front)) {
                 if (PRIMARY) {  // 4 (x) by 8 (y) pixel tiles, like Image.render's machine
                     const int tiles_y = (P.height + 7) / 8;
                     const bool by_tile = P.T.strip_width == 0;  // tiles dealt round-robin over the ranks instead of column strips
@@ -191,9 +222,11 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                         armed = true;
                         inside = 0;
                         phase = SP_MARCH;
+                        add_flops<COUNT>(acc, FLOPS_PRIMARY_RAY);
                     }
                 } else {
-                    const float4 a = __ldg(P.in_q + 3 * i), b = __ldg(P.in_q + 3 * i + 1), c = __ldg(P.in_q + 3 * i + 2);
+                    const long long qi = i < front_pad ? i : (long long)P.q_cap - 1 - (i - front_pad);
+                    const float4 a = __ldg(P.in_q + 3 * qi), b = __ldg(P.in_q + 3 * qi + 1), c = __ldg(P.in_q + 3 * qi + 2);
                     o = V3{a.x, a.y, a.z};
                     d = V3{a.w, b.x, b.y};
                     len = b.z;
@@ -234,7 +267,11 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
         }
         if (phase > SP_FETCH && event == 0) {
             uint32_t best_lo = 0u;
-            const float dist = CHAIN ? eval_chain<false>(S, p, acc, best_lo) : eval_form<false>(S, S.root_word, p, acc);
+            const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
+            if (COUNT && phase <= SP_SHADOW) {
+                acc.steps++;
+                add_flops<COUNT>(acc, FLOPS_MOVE + 2);
+            }
             if (phase == SP_MARCH) {
                 if (!armed) sign = dist < 0.0f ? -1.0f : 1.0f;  // the medium: inside glass the march runs on -Distance
                 const float sd = sign * dist;
@@ -274,12 +311,13 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 phase = SP_N3;
             } else {
                 n = normalize(n - V3{dist, dist, dist});
+                add_flops<COUNT>(acc, FLOPS_NORMAL);
                 event = 5;
             }
         }
         // ------------------------------------------------------------------ transitions
         bool push = false;
-        Continuation cont{V3{0, 0, 0}, V3{0, 0, 0}, 0.f};
+        Continuation cont{V3{0, 0, 0}, V3{0, 0, 0}, 0.f, false};
         if (event != 0) {
             bool next_light = false;
             if (event == 1) {  // miss: spec(BackgroundColor, nu)
@@ -289,8 +327,10 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
 #pragma unroll
                     for (int b = 0; b < 6; b++) Lb[b] = spec(bg, b);
                     write_pixel_from_bands(P.T, pixel, P.nl, Lb);
+                    add_flops<COUNT>(acc, 6 * FLOPS_SPEC + FLOPS_BAND_SUM * P.nl + 3);
                 } else {
                     P.slots[slot] = spec(bg, band);
+                    add_flops<COUNT>(acc, FLOPS_SPEC);
                 }
                 phase = SP_FETCH;
             } else if (event == 2) {  // hit: keep the un-moved hit ray, probe the normal
@@ -303,7 +343,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 phase = SP_N0;
             } else if (event == 5) {  // normal done: Material arg-min at the un-moved hit origin (SdfObject.fs:75-77)
                 const int leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, ho, hit_best)
-                                                                                  : material_leaf<false>(S, ho, acc);
+                                                                                  : material_leaf<COUNT>(S, ho, acc);
                 mat = __ldg(S.objects + leaf_obj).z;
                 const float4 m = ld4(S.materials + mat);
                 if (__float_as_uint(m.w) == (uint32_t)FT_MATERIAL_GLASS) {
@@ -314,6 +354,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                     } else {
                         cont = glass_interact(xyz(m), wavelength_nu((int)kk, P.nl), P.seed_lo, P.seed_hi, pixel, kk,
                                               (uint32_t)P.wave, ho, hd, hlen, eps, n, inside);
+                        add_flops<COUNT>(acc, FLOPS_GLASS);
                         push = true;
                     }
                     phase = SP_FETCH;
@@ -328,6 +369,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 if (event == 3) {
 #pragma unroll
                     for (int b = 0; b < NB; b++) lcb[b] = lcb[b] + spec(cint, PRIMARY ? b : band) * lcos;
+                    add_flops<COUNT>(acc, NB * (FLOPS_SPEC + 2));
                 }
                 light++;
                 next_light = true;
@@ -339,6 +381,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                     const bool directional = __float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL;
                     const V3 ldir = directional ? xyz(lv) : normalize(xyz(lv) - q);
                     lcos = dot(n, ldir);
+                    add_flops<COUNT>(acc, FLOPS_LIGHT);
                     if (lcos > 0.0f) {
                         o = q;
                         if (directional) {
@@ -351,6 +394,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                             len = sqrtf(d2);
                             d = diff / d2;
                             cint = xyz(lrgb) / d2;
+                            add_flops<COUNT>(acc, FLOPS_POINT_LIGHT);
                         }
                         if (inside) {  // inside glass no shadow ray is cast: the light contributes
 #pragma unroll
@@ -372,30 +416,33 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
 #pragma unroll
                         for (int b = 0; b < 6; b++) Lb[b] = spec(albedo, b) * (lcb[b < NB ? b : 0] * pi_inv);
                         write_pixel_from_bands(P.T, pixel, P.nl, Lb);
+                        add_flops<COUNT>(acc, 6 * (FLOPS_SPEC + 2) + FLOPS_BAND_SUM * P.nl + 3);
                     } else {
                         P.slots[slot] = spec(albedo, band) * (lcb[0] * pi_inv);
+                        add_flops<COUNT>(acc, FLOPS_SPEC + 2);
                     }
                     phase = SP_FETCH;
                 }
             }
         }
         // ------------------------------------------------------------------ queue append: ballot + popc ranks, one atomic per warp
-        const unsigned pm = __ballot_sync(FULL, push);
-        if (pm) {
-            const int leader = __ffs(pm) - 1;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd(PRIMARY ? P.hit_count : P.out_count, (unsigned)__popc(pm));
-            base = __shfl_sync(FULL, base, leader);
-            if (push) {
-                const unsigned idx = base + (unsigned)__popc(pm & ((1u << lane) - 1u));
-                if (PRIMARY) {
+        if (PRIMARY) {
+            const unsigned pm = __ballot_sync(FULL, push);
+            if (pm) {
+                const int leader = __ffs(pm) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(P.hit_count, (unsigned)__popc(pm));
+                base = __shfl_sync(FULL, base, leader);
+                if (push) {
+                    const unsigned idx = base + (unsigned)__popc(pm & ((1u << lane) - 1u));
                     P.hit_q[3ull * idx + 0] = float4{ho.x, ho.y, ho.z, hlen};
                     P.hit_q[3ull * idx + 1] = float4{hd.x, hd.y, hd.z, __uint_as_float(pixel)};
                     P.hit_q[3ull * idx + 2] = float4{n.x, n.y, n.z, __int_as_float(mat)};
-                } else {
-                    store_path(P.out_q, idx, cont, pixel, slot, kk);
                 }
             }
+        } else if (__any_sync(FULL, push)) {
+            const unsigned idx = queue_slot(P, push, cont.into_glass, lane);
+            if (push) store_path(P.out_q, idx, cont, pixel, slot, kk);
         }
     }
 
@@ -411,23 +458,42 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
         if (escaped) atomicAdd(s + FT_STAT_ESCAPED, (unsigned long long)escaped);
         if (paths) atomicAdd(s + FT_STAT_PATHS, (unsigned long long)paths);
     }
+    if (COUNT) {
+        unsigned long long fl = acc.flops, st = acc.steps;
+        for (int k = 16; k > 0; k >>= 1) {
+            fl += __shfl_xor_sync(FULL, fl, k);
+            st += __shfl_xor_sync(FULL, st, k);
+        }
+        if (lane == 0) {
+            const unsigned w = (blockIdx.x * (SB / 32) + (threadIdx.x >> 5)) & (FT_STAT_SLOTS - 1);
+            atomicAdd(P.stats + w * FT_STAT_STRIDE + FT_STAT_FLOPS, fl);
+            atomicAdd(P.stats + w * FT_STAT_STRIDE + FT_STAT_STEPS, st);
+        }
+    }
 }
 
-// ---- the material stage of wave 0: one thread per (glass hit, wavelength)
+// ---- the material stage of wave 0: one thread per (glass hit, wavelength); the continuations enter wave 1's queue by class
 __global__ void __launch_bounds__(SB) spectral_spawn_kernel(const __grid_constant__ DevScene S, const __grid_constant__ SpectralParams P,
                                                             unsigned n_hits) {
     const unsigned long long t = (unsigned long long)blockIdx.x * SB + threadIdx.x;
-    if (t >= (unsigned long long)n_hits * (unsigned)P.nl) return;
-    const unsigned h = (unsigned)(t / (unsigned)P.nl), k = (unsigned)(t - (unsigned long long)h * (unsigned)P.nl);
+    const bool live = t < (unsigned long long)n_hits * (unsigned)P.nl;
     if (P.max_bounces < 1) {  // no interaction allowed: the path carries nothing
-        P.slots[t] = 0.0f;
+        if (live) P.slots[t] = 0.0f;
         return;
     }
-    const float4 a = __ldg(P.hit_q + 3ull * h), b = __ldg(P.hit_q + 3ull * h + 1), c = __ldg(P.hit_q + 3ull * h + 2);
-    const float4 m = ld4(S.materials + __float_as_int(c.w));
-    const Continuation cont = glass_interact(xyz(m), wavelength_nu((int)k, P.nl), P.seed_lo, P.seed_hi, __float_as_uint(b.w), k, 0u,
-                                             V3{a.x, a.y, a.z}, V3{b.x, b.y, b.z}, a.w, P.epsilon, V3{c.x, c.y, c.z}, 0);
-    store_path(P.out_q, (unsigned)t, cont, __float_as_uint(b.w), (unsigned)t, k);
+    Continuation cont{V3{0, 0, 0}, V3{0, 0, 0}, 0.f, false};
+    uint32_t pixel = 0u, k = 0u;
+    if (live) {
+        const unsigned h = (unsigned)(t / (unsigned)P.nl);
+        k = (unsigned)(t - (unsigned long long)h * (unsigned)P.nl);
+        const float4 a = __ldg(P.hit_q + 3ull * h), b = __ldg(P.hit_q + 3ull * h + 1), c = __ldg(P.hit_q + 3ull * h + 2);
+        const float4 m = ld4(S.materials + __float_as_int(c.w));
+        pixel = __float_as_uint(b.w);
+        cont = glass_interact(xyz(m), wavelength_nu((int)k, P.nl), P.seed_lo, P.seed_hi, pixel, k, 0u, V3{a.x, a.y, a.z},
+                              V3{b.x, b.y, b.z}, a.w, P.epsilon, V3{c.x, c.y, c.z}, 0);
+    }
+    const unsigned idx = queue_slot(P, live, cont.into_glass, (int)(threadIdx.x & 31));
+    if (live) store_path(P.out_q, idx, cont, pixel, (unsigned)t, k);
 }
 
 // ---- per glass pixel: RGB = sum_k w(nu_k) L_k / sum_k w(nu_k) in k order
@@ -460,18 +526,30 @@ static cudaError_t wave_grid(K kernel, long long items, int sm_count, unsigned *
 
 }  // namespace ft_spectral
 
-cudaError_t spectral_launch_primary(const DevScene &S, const SpectralParams &P, int sm_count, cudaStream_t stream) {
+#define FT_SPEC_LAUNCH(CHAIN, PRIM, COUNT, ITEMS)                                                                       \
+    do {                                                                                                              \
+        if ((e = wave_grid(spectral_trace_kernel<CHAIN, PRIM, COUNT>, ITEMS, sm_count, &grid)) != cudaSuccess) return e; \
+        spectral_trace_kernel<CHAIN, PRIM, COUNT><<<grid, SB, 0, stream>>>(S, P);                                      \
+    } while (0)
+template <bool PRIM>
+static cudaError_t spectral_launch_trace(const DevScene &S, const SpectralParams &P, long long items, bool count, int sm_count,
+                                         cudaStream_t stream) {
     using namespace ft_spectral;
     unsigned grid = 1;
     cudaError_t e;
     if (S.chain_valid) {
-        if ((e = wave_grid(spectral_trace_kernel<true, true>, P.n_items, sm_count, &grid)) != cudaSuccess) return e;
-        spectral_trace_kernel<true, true><<<grid, SB, 0, stream>>>(S, P);
+        if (count) FT_SPEC_LAUNCH(true, PRIM, true, items);
+        else FT_SPEC_LAUNCH(true, PRIM, false, items);
     } else {
-        if ((e = wave_grid(spectral_trace_kernel<false, true>, P.n_items, sm_count, &grid)) != cudaSuccess) return e;
-        spectral_trace_kernel<false, true><<<grid, SB, 0, stream>>>(S, P);
+        if (count) FT_SPEC_LAUNCH(false, PRIM, true, items);
+        else FT_SPEC_LAUNCH(false, PRIM, false, items);
     }
     return cudaGetLastError();
+}
+#undef FT_SPEC_LAUNCH
+
+cudaError_t spectral_launch_primary(const DevScene &S, const SpectralParams &P, bool count, int sm_count, cudaStream_t stream) {
+    return spectral_launch_trace<true>(S, P, P.n_items, count, sm_count, stream);
 }
 
 cudaError_t spectral_launch_spawn(const DevScene &S, const SpectralParams &P, unsigned n_hits, cudaStream_t stream) {
@@ -483,19 +561,10 @@ cudaError_t spectral_launch_spawn(const DevScene &S, const SpectralParams &P, un
 }
 
 // max_items: an upper bound of the live paths of this wave (the true count is read from P.in_count on the device)
-cudaError_t spectral_launch_wave(const DevScene &S, const SpectralParams &P, long long max_items, int sm_count, cudaStream_t stream) {
-    using namespace ft_spectral;
+cudaError_t spectral_launch_wave(const DevScene &S, const SpectralParams &P, long long max_items, bool count, int sm_count,
+                                 cudaStream_t stream) {
     if (max_items <= 0) return cudaSuccess;
-    unsigned grid = 1;
-    cudaError_t e;
-    if (S.chain_valid) {
-        if ((e = wave_grid(spectral_trace_kernel<true, false>, max_items, sm_count, &grid)) != cudaSuccess) return e;
-        spectral_trace_kernel<true, false><<<grid, SB, 0, stream>>>(S, P);
-    } else {
-        if ((e = wave_grid(spectral_trace_kernel<false, false>, max_items, sm_count, &grid)) != cudaSuccess) return e;
-        spectral_trace_kernel<false, false><<<grid, SB, 0, stream>>>(S, P);
-    }
-    return cudaGetLastError();
+    return spectral_launch_trace<false>(S, P, max_items, count, sm_count, stream);
 }
 
 cudaError_t spectral_launch_resolve(const SpectralParams &P, unsigned n_hits, cudaStream_t stream) {
