@@ -266,6 +266,31 @@ def bench_extension(args):
         kern_ms += st["kernel_ms"]
     clocks = sampler.stop(t_begin, time.time())
     rays = st["primary_rays"] + st["shadow_rays"]
+    # ---- FP32 roofline of the call's kernels: algorithmic operations of one frame (instrumented kernels, same inputs;
+    # constants in spectral_kernels.cu / cloud_kernels.cu / trace_device.cuh) / the event-timed device time of a frame
+    tracer.set_debug(8)
+    stc = call()
+    tracer.set_debug(0)
+    tf, mhz = C.c_float(), C.c_float()
+    A.check(lib.ft_measure_fp32_peak(0, C.byref(tf), C.byref(mhz)))
+    achieved = stc["eval_flops"] / (kern_ms / args.steps * 1e-3) / 1e12
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
+                "frac": achieved / tf.value if tf.value else None, "traffic": tj.get(w.name),
+                "kernel": ("spectral_trace_kernel (wave 0 + path waves) + spawn + resolve" if spectral
+                           else "cloud_kernel + cloud_resolve_kernel"),
+                "kernel_ms": kern_ms / args.steps, "flops_per_launch": stc["eval_flops"],
+                "issue_bound_ncu": tj.get(w.name + "_ncu"),
+                "flops_per_ray": stc["eval_flops"] / max(1, rays),
+                "steps": stc["march_steps"],
+                "steps_meaning": ("Distance evaluations inside march loops" if spectral else
+                                  "fixed-step tracking steps through the medium (each: one Distance evaluation, one float64 "
+                                  "lattice-noise density, one Philox draw)"),
+                "peak_source": "measured live: dependent-free FFMA stream on all SMs, FMA = 2 flops; strict mode issues no FMA"
+                               + ("" if spectral else "; the float64 lattice noise (82 of the 95 operations of a density "
+                                                      "evaluation) is counted at one flop per operation against the FP32 peak"),
+                "mode": "strict (bit-exact against this repository's CPU restatement, -fmad=false)"}
     cpu = None
     if not args.no_cpu:
         orc = O.OracleScene(tracer.description)
@@ -294,7 +319,7 @@ def bench_extension(args):
         "clocks": clocks,
         "e2e": {"value": rays * args.steps / wall / 1e6, "unit": UNIT, "h2d_bytes_per_step": C.sizeof(A.ft_camera) + 32,
                 "d2h_bytes_per_step": X * Y * 12, "ms_per_step": 1e3 * wall / args.steps},
-        "gpu_launches": args.steps * st["launches"], "roofline": None, "cpu_baseline": cpu,
+        "gpu_launches": args.steps * st["launches"], "roofline": roofline, "cpu_baseline": cpu,
     }))
 
 

@@ -29,6 +29,10 @@
 namespace ft_cloud {
 
 constexpr int CB = 128;
+#ifndef FT_CLOUD_REFILL_MIN
+#define FT_CLOUD_REFILL_MIN 16  // lanes that must want their next sample before any of them starts it (1: at once).  Measured on B200
+                                // (config 4, one box): 1: 263.6 ms, 4: 240.3, 8: 229.4, 16: 220.3
+#endif
 #ifndef FT_CLOUD_MINB
 #define FT_CLOUD_MINB 4  // <= 128 registers.  Measured (config 4, 16 spp): 2 or 3 CTAs/SM 94 ms, 4: 81.4, 6: 84.9, 8: 87.5
 #endif
@@ -86,12 +90,38 @@ __device__ __forceinline__ float cloud_density(const NoiseTab &n, const CloudPar
     const float edge = clamp01f(-D / P.fade);
     return (P.density * shape) * edge;
 }
-__device__ __forceinline__ void cloud_rnd(const CloudParams &P, uint32_t pixel, uint32_t sample, uint32_t step, uint32_t stream,
+// Random numbers: block b of stream `stream` of (pixel, sample) = Philox4x32-10({pixel, sample, b, stream}; seed).
+// Stream 0 / block 0: the sub-pixel jitter (words 0, 1).  A tracking stream: block 0 word 0 = the collision draw of step 0,
+// word 1 = the offset xi0 of the first step; the collision draw of step k >= 1 is word (k + 1) & 3 of block (k + 1) >> 2 -- one
+// Philox evaluation serves four tracking steps (it was a fifth of a tracking step's instructions when every step drew its own).
+__device__ __forceinline__ float cloud_u(uint32_t w) { return __uint2float_rn(w) * 2.3283064365386963e-10f; }  // == (float)(w * 2^-32 in double)
+__device__ __noinline__ uint4 cloud_block(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel, uint32_t sample, uint32_t block,
+                                          uint32_t stream) {  // one out-of-line copy: four call sites in a kernel that is
+    uint32_t c[4] = {pixel, sample, block, stream};            // bound by instruction fetch
+    ft_philox4x32_10(c, seed_lo, seed_hi);
+    return make_uint4(c[0], c[1], c[2], c[3]);
+}
+// first draw of a stream: u0 = word 0, u1 = word 1; words 2 and 3 are parked in the thread's shared-memory slots for steps 1, 2
+__device__ __forceinline__ void cloud_rnd(const CloudParams &P, uint32_t (*spare)[CB], uint32_t pixel, uint32_t sample, uint32_t stream,
                                           float &u0, float &u1) {
-    uint32_t c[4] = {pixel, sample, step, stream};
-    ft_philox4x32_10(c, P.seed_lo, P.seed_hi);
-    u0 = __uint2float_rn(c[0]) * 2.3283064365386963e-10f;  // == (float)(c * 2^-32 in double)
-    u1 = __uint2float_rn(c[1]) * 2.3283064365386963e-10f;
+    const uint4 c = cloud_block(P.seed_lo, P.seed_hi, pixel, sample, 0u, stream);
+    u0 = cloud_u(c.x);
+    u1 = cloud_u(c.y);
+    spare[1][threadIdx.x] = c.z;
+    spare[2][threadIdx.x] = c.w;
+}
+// collision draw of tracking step k >= 1
+__device__ __forceinline__ float cloud_track_u(const CloudParams &P, uint32_t (*spare)[CB], uint32_t pixel, uint32_t sample, uint32_t k,
+                                               uint32_t stream) {
+    const uint32_t j = k + 1u;
+    if ((j & 3u) == 0u) {
+        const uint4 c = cloud_block(P.seed_lo, P.seed_hi, pixel, sample, j >> 2, stream);
+        spare[0][threadIdx.x] = c.y;
+        spare[1][threadIdx.x] = c.z;
+        spare[2][threadIdx.x] = c.w;
+        return cloud_u(c.x);
+    }
+    return cloud_u(spare[(j & 3u) - 1u][threadIdx.x]);
 }
 
 // pixel of lane `lane` in local tile `tile`; false when it lies outside the frame (padding)
@@ -133,6 +163,7 @@ constexpr int FLOPS_SAMPLE_RAY = 29;  // jittered camera ray (Camera.uniformPixe
 template <bool CHAIN, bool COUNT>
 __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_constant__ DevScene S, const __grid_constant__ CloudParams P) {
     __shared__ NoiseTab tab;
+    __shared__ uint32_t spare[3][CB];  // the unused words of each thread's current Philox block (cloud_track_u)
     for (int i = threadIdx.x; i < 256; i += CB) tab.perm[i] = P.perm[i];
     for (int i = threadIdx.x; i < 768; i += CB) tab.grad[i] = P.gradients[i];
     __syncthreads();
@@ -144,9 +175,9 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
     const V3 cam = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
     const V3 bg = V3{S.bg[0], S.bg[1], S.bg[2]};
     Acc acc{0ull, 0ull};
-    uint32_t best_dummy = 0u, hit_best = 0u;  // eval_chain's arg-min note: kept at a hit, it names the material's leaf (FT_CHAIN_MAT)
+    uint32_t hit_best = 0u;  // eval_chain's arg-min note: kept at a hit, it names the material's leaf (FT_CHAIN_MAT)
     // Distance at the common origin of all camera rays, once per warp
-    const float d0 = CHAIN ? eval_chain<COUNT>(S, cam, acc, best_dummy) : eval_form<COUNT>(S, S.root_word, cam, acc);
+    const float d0 = CHAIN ? eval_chain_call<COUNT>(S, cam, acc) : eval_form_call<COUNT>(S, S.root_word, cam, acc);
 
     int phase = C_FETCH;
     bool have_tile = false, active = false, cloud_mode = false;
@@ -187,9 +218,18 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             continue;
         }
         // ------------------------------------------------------------------ per-lane refill: the lane's next sample
-        if (phase == C_FETCH && s < spp_eff) {
+        // (a finished lane waits until FT_CLOUD_REFILL_MIN lanes want their next sample, or nobody is busy: the set-up below --
+        // Philox, three IEEE divisions of the normalisation -- ran with two lanes active on average when every lane started its
+        // next sample the moment it finished the last, a tenth of the kernel's warp instructions)
+        const bool want = phase == C_FETCH && s < spp_eff;
+#if FT_CLOUD_REFILL_MIN > 1
+        const unsigned wm = __ballot_sync(FULL, want), busy = __ballot_sync(FULL, phase != C_FETCH);
+        if (want && (__popc(wm) >= FT_CLOUD_REFILL_MIN || busy == 0u)) {
+#else
+        if (want) {
+#endif
             float u0, u1;
-            cloud_rnd(P, pixel, (uint32_t)s, 0u, 0u, u0, u1);  // sub-pixel jitter
+            cloud_rnd(P, spare, pixel, (uint32_t)s, 0u, u0, u1);  // sub-pixel jitter
             const float pu = ((float)x + u0) / P.max_size, pv = ((float)y + u1) / P.max_size;
             const V3 fwd = V3{P.cam.forward[0], P.cam.forward[1], P.cam.forward[2]};
             const V3 rs = V3{P.cam.right_scaled[0], P.cam.right_scaled[1], P.cam.right_scaled[2]};
@@ -298,10 +338,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                         phase = C_SHADOW;
                     }
                 } else {
-                    if (k > 0u) {
-                        float u1;
-                        cloud_rnd(P, pixel, (uint32_t)s, k, stream + (phase == C_LTRACK ? 1u + (uint32_t)light : 0u), ucur, u1);
-                    }
+                    if (k > 0u) ucur = cloud_track_u(P, spare, pixel, (uint32_t)s, k, stream + (phase == C_LTRACK ? 1u + (uint32_t)light : 0u));
                     add_flops<COUNT>(acc, FLOPS_DENSITY);
                     if (ucur < cloud_density(tab, P, p, dist) * P.step) {
                         if (phase == C_TRACK) {  // real collision: single scattering at p
@@ -338,7 +375,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                 mat = __ldg(S.objects + leaf_obj).z;
                 if (__float_as_uint(ld4(S.materials + mat).w) == (uint32_t)FT_MATERIAL_CLOUD) {
                     stream = 1u + seg * nstreams;
-                    cloud_rnd(P, pixel, (uint32_t)s, 0u, stream, ucur, xi0);
+                    cloud_rnd(P, spare, pixel, (uint32_t)s, stream, ucur, xi0);
                     k = 0u;
                     phase = C_TRACK;
                 } else {  // the reference's shading, SdfScene.fs:12-28
@@ -374,7 +411,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                             cint = xyz(lrgb) / d2;
                         }
                         n_secondary++;
-                        cloud_rnd(P, pixel, (uint32_t)s, 0u, stream + 1u + (uint32_t)light, ucur, xi0);
+                        cloud_rnd(P, spare, pixel, (uint32_t)s, stream + 1u + (uint32_t)light, ucur, xi0);
                         k = 0u;
                         phase = C_LTRACK;
                         finish = false;

@@ -33,11 +33,20 @@ namespace ft_spectral {
 
 constexpr int SB = 128;  // threads per CTA
 constexpr unsigned FULL = 0xffffffffu;
+#ifndef FT_SPEC_REFILL_MIN
+#define FT_SPEC_REFILL_MIN 32  // idle lanes of a path-wave warp that trigger a refill (32: whole chunks in lockstep).  Measured on
+                               // B200 (config 3): 1, 8, 16, 24 are all 5-8 % slower than 32 -- the chunk cursor costs registers in a
+                               // kernel that already spills, and refilled lanes drift apart
+#endif
+#ifndef FT_PROBE_INLINE
+#define FT_PROBE_INLINE 0  // 1: the once-per-warp probe of the camera position is a second inlined copy of the evaluator
+#endif
 #ifndef FT_SPEC_MINB
-#define FT_SPEC_MINB 8  // <= 64 registers.  Measured (config 3, 4K): 4 CTAs/SM 139.8 ms, 6: 114.9, 8: 108.1, 10: 115.6
+#define FT_SPEC_MINB 7  // <= 72 registers.  Measured (config 3, 4K; round 2, sub-grid + batched material stage): 6 CTAs/SM 60.2 ms, 7: 58.1, 8: 59.2
 #endif
 
 enum : int {
+    SP_PARK = -1,   // path waves: a glass hit waiting for the warp's batched material stage (see the fetch block)
     SP_FETCH = 0,
     SP_MARCH = 1,   // primary ray or continuation path
     SP_SHADOW = 2,  // the reference's shadow ray (SdfLight.fs:10-20 / 26-41)
@@ -173,14 +182,24 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
     constexpr int NB = PRIMARY ? 6 : 1;
 
     Acc acc{0ull, 0ull};
-    uint32_t best_dummy = 0u, hit_best = 0u;  // eval_chain's arg-min note: kept at a hit, it names the material's leaf (FT_CHAIN_MAT)
+    uint32_t hit_best = 0u;  // eval_chain's arg-min note: kept at a hit, it names the material's leaf (FT_CHAIN_MAT)
     float d0 = 0.f;
     if (PRIMARY) {  // Distance at the common origin of all primary rays, once per warp
         const V3 c = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
+        #if FT_PROBE_INLINE
+        uint32_t best_dummy = 0u;
         d0 = CHAIN ? eval_chain<COUNT>(S, c, acc, best_dummy) : eval_form<COUNT>(S, S.root_word, c, acc);
+#else
+        d0 = CHAIN ? eval_chain_call<COUNT>(S, c, acc) : eval_form_call<COUNT>(S, S.root_word, c, acc);
+#endif
     }
 
     int phase = SP_FETCH;
+#if FT_SPEC_REFILL_MIN < 32
+    long long chunk_next = 0;  // the warp's current chunk (uniform)
+    int chunk_left = 0;
+    bool exhausted = false;
+#endif
     V3 o{0, 0, 0}, d{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, cint{0, 0, 0}, ho{0, 0, 0}, hd{0, 0, 0};
     float len = 0.f, hlen = 0.f, lcos = 0.f, lcb[NB];
     float sign = 1.0f;
@@ -192,8 +211,26 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
     for (int b = 0; b < NB; b++) lcb[b] = 0.f;
 
     for (;;) {
+#if FT_SPEC_REFILL_MIN >= 32
         // ------------------------------------------------------------------ a new chunk once the whole warp is idle
-        if (__all_sync(FULL, phase == SP_FETCH)) {
+        if (__all_sync(FULL, phase <= SP_FETCH)) {
+            // Path waves: the material stage of the chunk's glass hits runs here, for all of them at once.  Done in each lane's
+            // own transition it ran a dozen times per chunk with a few lanes each (Fresnel + Philox + the queue append are ~250
+            // instructions: a quarter of the wave's warp instructions at 3-6 active lanes); the lanes would have idled anyway.
+            if (!PRIMARY && __any_sync(FULL, phase == SP_PARK)) {
+                const bool parked = phase == SP_PARK;
+                Continuation cont{V3{0, 0, 0}, V3{0, 0, 0}, 0.f, false};
+                if (parked) {
+                    cont = glass_interact(xyz(ld4(S.materials + mat)), wavelength_nu((int)kk, P.nl), P.seed_lo, P.seed_hi, pixel, kk,
+                                          (uint32_t)P.wave, ho, hd, hlen, eps, n, inside);
+                    add_flops<COUNT>(acc, FLOPS_GLASS);
+                }
+                const unsigned idx = queue_slot(P, parked, cont.into_glass, lane);
+                if (parked) {
+                    store_path(P.out_q, idx, cont, pixel, slot, kk);
+                    phase = SP_FETCH;
+                }
+            }
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.work_counter, 32ull);
             base = __shfl_sync(FULL, base, 0);
@@ -244,6 +281,87 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
             }
             continue;
         }
+#else
+        // ------------------------------------------------------------------ refill
+        // Wave 0 takes a new 4 x 8 pixel tile once the whole warp is idle (coherent primary rays: lockstep pays, see the hot path).
+        // Path waves refill as soon as FT_SPEC_REFILL_MIN lanes are idle: the segments of one chunk differ several-fold in length
+        // (grazing paths crawl along the glass surface), and consecutive queue entries are the other wavelengths of the same
+        // pixels, so a refilled lane stays close to its neighbours.
+        {
+            unsigned idle = __ballot_sync(FULL, phase == SP_FETCH);
+            constexpr int REFILL = PRIMARY ? 32 : FT_SPEC_REFILL_MIN;
+            if (idle == FULL || (__popc(idle) >= REFILL && !(exhausted && chunk_left == 0))) {
+                while (idle) {
+                    if (chunk_left == 0) {
+                        if (exhausted) break;
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(P.work_counter, 32ull);
+                        base = __shfl_sync(FULL, base, 0);
+                        if ((long long)base >= total) {
+                            exhausted = true;
+                            break;
+                        }
+                        chunk_next = (long long)base;
+                        chunk_left = 32;
+                    }
+                    const int want = __popc(idle), take = want < chunk_left ? want : chunk_left;
+                    const int r = __popc(idle & ((1u << lane) - 1u));
+                    const long long i = chunk_next + r;
+                    if (phase == SP_FETCH && r < take && i < total && (PRIMARY || i >= front_pad || i < (long long)n_front)) {
+                        if (PRIMARY) {  // 4 (x) by 8 (y) pixel tiles, like Image.render's machine (take == 32: r == lane)
+                            const int tiles_y = (P.height + 7) / 8;
+                            const bool by_tile = P.T.strip_width == 0;  // tiles dealt round-robin over the ranks instead of column strips
+                            const long long tile = by_tile ? (i >> 5) * P.T.world + P.T.rank : (i >> 5);
+                            const int tx = (int)(tile / tiles_y), ty = (int)(tile - (long long)tx * tiles_y);
+                            const int xl = tx * 4 + (r >> 3), y = ty * 8 + (r & 7);  // xl: column of the rank's compact strip space
+                            const int x = by_tile ? xl : P.T.image_column(xl);
+                            if ((by_tile || xl < P.T.local_cols) && x < P.width && y < P.height) {
+                                pixel = (uint32_t)((long long)x * P.height + y);
+                                o = V3{P.cam.position[0], P.cam.position[1], P.cam.position[2]};
+                                d = pixel_direction(P.cam, x, y, P.max_size);
+                                len = P.length;
+                                steps = 0;
+                                if (len > 0.0f && d0 >= eps) {  // first iteration of the march with the shared Distance
+                                    o = o + d * d0;
+                                    len = len - d0;
+                                    steps = 1;
+                                }
+                                sign = 1.0f;
+                                armed = true;
+                                inside = 0;
+                                phase = SP_MARCH;
+                                add_flops<COUNT>(acc, FLOPS_PRIMARY_RAY);
+                            }
+                        } else {
+                            const long long qi = i < front_pad ? i : (long long)P.q_cap - 1 - (i - front_pad);
+                            const float4 a = __ldg(P.in_q + 3 * qi), b = __ldg(P.in_q + 3 * qi + 1), c = __ldg(P.in_q + 3 * qi + 2);
+                            o = V3{a.x, a.y, a.z};
+                            d = V3{a.w, b.x, b.y};
+                            len = b.z;
+                            pixel = __float_as_uint(b.w);
+                            slot = __float_as_uint(c.x);
+                            kk = __float_as_uint(c.y);
+                            band = band_of(wavelength_nu((int)kk, P.nl));
+                            sign = 1.0f;
+                            inside = 0;
+                            armed = false;  // continuation rays arm (and learn their medium) once |Distance| >= epsilon
+                            steps = 0;
+                            n_paths++;
+                            phase = SP_MARCH;
+                        }
+                    }
+                    chunk_next += take;
+                    chunk_left -= take;
+                    idle = __ballot_sync(FULL, phase == SP_FETCH);  // padding items leave their lane idle: it draws again ...
+                    if (PRIMARY && idle != FULL) break;             // ... but a warp of wave 0 never mixes two tiles
+                }
+                if (idle == FULL) {
+                    if (exhausted) break;  // no work left anywhere
+                    continue;
+                }
+            }
+        }
+#endif
         // ------------------------------------------------------------------ march pre-check
         int event = 0;  // 1 march miss, 2 march hit, 3 shadow ray unoccluded, 4 shadow ray occluded, 5 normal done
         if (phase == SP_MARCH || phase == SP_SHADOW) {
@@ -351,6 +469,12 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                         push = true;  // the material stage takes it from the hit queue
                     } else if (P.wave >= P.max_bounces) {
                         P.slots[slot] = 0.0f;  // interaction budget spent
+#if FT_SPEC_REFILL_MIN >= 32
+                    } else {
+                        phase = SP_PARK;  // the material stage runs for the whole chunk at once (fetch block)
+                    }
+                    if (phase != SP_PARK) phase = SP_FETCH;
+#else
                     } else {
                         cont = glass_interact(xyz(m), wavelength_nu((int)kk, P.nl), P.seed_lo, P.seed_hi, pixel, kk,
                                               (uint32_t)P.wave, ho, hd, hlen, eps, n, inside);
@@ -358,6 +482,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                         push = true;
                     }
                     phase = SP_FETCH;
+#endif
                 } else {
                     const V3 bg = V3{S.bg[0], S.bg[1], S.bg[2]};  // SdfScene.fs:12
 #pragma unroll

@@ -642,6 +642,17 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, u
     return v;
 }
 
+// out-of-line copy of the chain evaluator for callers outside the hot loop (the once-per-warp probe of the camera position in
+// the extension kernels).  (Measured and rejected on B200: out-of-line copies for the cold call sites INSIDE the loop -- the
+// fallback scan, the chain operations' operands, the material arg-min -- to shrink the instruction footprint: no gain on the
+// hot path (config 2 0.831 = 0.831 ms, config 1 0.669 vs 0.641 ms), and the extension kernels lost 8-30 %: live registers
+// are spilled around every call.)
+template <bool COUNT>
+__device__ __noinline__ float eval_chain_call(const DevScene &S, V3 p, Acc &acc) {
+    uint32_t best = 0u;
+    return eval_chain<COUNT>(S, p, acc, best);
+}
+
 // out-of-line copy for the rare callers (composite children inside the material arg-min)
 template <bool COUNT>
 __device__ __noinline__ float eval_form_call(const DevScene &S, uint32_t root, V3 p, Acc &acc) {

@@ -1526,11 +1526,27 @@ static float cloud_density(const ft_cloud_params *cp, v3 p, float D) {
     float edge = clamp01f(-D / cp->fade);
     return (cp->density * shape) * edge;
 }
-static void cloud_rnd(const cjob *j, uint32_t pixel, uint32_t sample, uint32_t step, uint32_t stream, float u[2]) {
-    uint32_t c[4] = {pixel, sample, step, stream};
+/* Random numbers of the extension: block b of stream `stream` of (pixel, sample) is
+ * Philox4x32-10(counter = {pixel, sample, b, stream}, key = seed), four 32-bit words.  Stream 0 / block 0 holds the
+ * sub-pixel jitter (words 0, 1).  A tracking stream uses block 0 word 0 for the collision draw of step 0 and word 1 for
+ * the offset xi0 of the first step; the collision draw of step k >= 1 is word (k + 1) & 3 of block (k + 1) >> 2, so
+ * that one Philox evaluation serves four tracking steps. */
+static float cloud_u(uint32_t word) { return (float)((double)word * (1.0 / 4294967296.0)); }
+static void cloud_block(const cjob *j, uint32_t pixel, uint32_t sample, uint32_t block, uint32_t stream, uint32_t c[4]) {
+    c[0] = pixel; c[1] = sample; c[2] = block; c[3] = stream;
     philox4x32_10(c, (uint32_t)j->seed, (uint32_t)(j->seed >> 32));
-    u[0] = (float)((double)c[0] * (1.0 / 4294967296.0));
-    u[1] = (float)((double)c[1] * (1.0 / 4294967296.0));
+}
+static void cloud_rnd(const cjob *j, uint32_t pixel, uint32_t sample, uint32_t step, uint32_t stream, float u[2]) {
+    uint32_t c[4];
+    cloud_block(j, pixel, sample, step, stream, c);
+    u[0] = cloud_u(c[0]);
+    u[1] = cloud_u(c[1]);
+}
+/* collision draw of tracking step k >= 1; `blk` holds the stream's current block (block 0 after the stream's first draw) */
+static float cloud_track_u(const cjob *j, uint32_t pixel, uint32_t sample, uint32_t k, uint32_t stream, uint32_t blk[4]) {
+    const uint32_t jj = k + 1u;
+    if ((jj & 3u) == 0u) cloud_block(j, pixel, sample, jj >> 2, stream, blk);
+    return cloud_u(blk[jj & 3u]);
 }
 /* the reference's shadow ray of light lt from `origin` (SdfLight.fs:10-20 / 26-41): 1 when unoccluded */
 static int shadow_unoccluded(const fto_scene *s, const olight *lt, v3 origin, float eps) {
@@ -1552,8 +1568,10 @@ static int light_track(const cjob *j, cstat *st, const olight *lt, v3 p, v3 ldir
                        uint32_t stream) {
     const ft_cloud_params *cp = j->cp;
     float u[2];
-    cloud_rnd(j, pixel, sample, 0u, stream, u);
-    const float xi0 = u[1];
+    uint32_t blk[4];
+    cloud_block(j, pixel, sample, 0u, stream, blk);
+    u[0] = cloud_u(blk[0]);
+    const float xi0 = cloud_u(blk[1]);
     st->secondary++;
     for (uint32_t k = 0;; k++) {
         float t = ((float)k + xi0) * cp->step;
@@ -1563,7 +1581,7 @@ static int light_track(const cjob *j, cstat *st, const olight *lt, v3 p, v3 ldir
         float D = form_distance(j->s->root->form, q);
         st->track_steps++;
         if (D >= j->eps) { st->secondary++; return shadow_unoccluded(j->s, lt, q, j->eps); }
-        if (k > 0) cloud_rnd(j, pixel, sample, k, stream, u);
+        if (k > 0) u[0] = cloud_track_u(j, pixel, sample, k, stream, blk);
         if (u[0] < cloud_density(cp, q, D) * cp->step) return 0;
     }
 }
@@ -1610,8 +1628,10 @@ static v3 cloud_sample(const cjob *j, cstat *st, int x, int y, uint32_t sample) 
         }
         /* cloud: fixed-step tracking along the camera ray from the hit point */
         const uint32_t stream = 1u + seg * nstreams;
-        cloud_rnd(j, pixel, sample, 0u, stream, u);
-        const float xi0 = u[1];
+        uint32_t blk[4];
+        cloud_block(j, pixel, sample, 0u, stream, blk);
+        u[0] = cloud_u(blk[0]);
+        const float xi0 = cloud_u(blk[1]);
         int exited = 0;
         for (uint32_t k = 0;; k++) {
             float t = ((float)k + xi0) * cp->step;
@@ -1625,7 +1645,7 @@ static v3 cloud_sample(const cjob *j, cstat *st, int x, int y, uint32_t sample) 
                 exited = 1;
                 break;
             }
-            if (k > 0) cloud_rnd(j, pixel, sample, k, stream, u);
+            if (k > 0) u[0] = cloud_track_u(j, pixel, sample, k, stream, blk);
             if (u[0] < cloud_density(cp, p, D) * cp->step) { /* real collision: single scattering */
                 st->scattered++;
                 v3 lc = s->background;
