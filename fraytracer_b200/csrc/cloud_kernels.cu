@@ -30,8 +30,9 @@ namespace ft_cloud {
 
 constexpr int CB = 128;
 #ifndef FT_CLOUD_REFILL_MIN
-#define FT_CLOUD_REFILL_MIN 16  // lanes that must want their next sample before any of them starts it (1: at once).  Measured on B200
-                                // (config 4, one box): 1: 263.6 ms, 4: 240.3, 8: 229.4, 16: 220.3
+#define FT_CLOUD_REFILL_MIN 32  // lanes that must want their next sample before any of them starts it (1: at once; 32: the warp's
+                                // lanes start their samples together).  Measured on B200 (config 4): 1: 264.2 ms, 4: 240.3, 8: 229.4,
+                                // 16: 220.8, 24: 216.1, 32: 181.1 -- samples of neighbouring pixels started together march in step
 #endif
 #ifndef FT_CLOUD_MINB
 #define FT_CLOUD_MINB 4  // <= 128 registers.  Measured (config 4, 16 spp): 2 or 3 CTAs/SM 94 ms, 4: 81.4, 6: 84.9, 8: 87.5
