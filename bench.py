@@ -715,6 +715,12 @@ def main():
     ap.add_argument("--gather", default=None, choices=["p2p", "nccl"],
                     help="N > 1: how the framebuffer is gathered (default p2p: peer stores fused into the render kernel)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: whatever libraries print to fd 1 on the way (NCCL's version banner under
+    # torchrun) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     if args.workload in ("config3", "config4"):
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "config3 / config4 are builder-defined extensions: the "

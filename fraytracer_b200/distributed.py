@@ -14,6 +14,7 @@ One process per GPU; torch.distributed is only the plumbing around the C ABI (`f
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 from . import _abi as A
 
@@ -66,6 +67,37 @@ class _DeviceArray:
 
     def __init__(self, ptr: int, shape):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _interleave_numa(buf, nbytes: int) -> bool:
+    """Spread the pages of the shared host framebuffer over all NUMA nodes (mbind MPOL_INTERLEAVE on the tmpfs mapping: a
+    shared policy, valid for every process that maps it).  With N GPUs behind two sockets writing one frame, first-touch
+    placement would put every page on the node of rank 0 and send half of the GPUs' stores across the socket interconnect
+    into one node's memory controllers.  Best effort: False (and first-touch placement) when the kernel refuses.
+    FT_HOST_INTERLEAVE=0 disables it."""
+    import ctypes
+    import glob
+
+    if os.environ.get("FT_HOST_INTERLEAVE", "1") == "0":
+        return False
+    nodes = sorted(int(p.rsplit("node", 1)[1]) for p in glob.glob("/sys/devices/system/node/node[0-9]*"))
+    if len(nodes) < 2:
+        return False
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(buf))
+        page = os.sysconf("SC_PAGE_SIZE")
+        start = addr & ~(page - 1)
+        length = ((addr + nbytes + page - 1) & ~(page - 1)) - start
+        mask = (ctypes.c_ulong * 16)()
+        for n in nodes:
+            mask[n // 64] |= 1 << (n % 64)
+        MPOL_INTERLEAVE, SYS_mbind = 3, 237  # x86_64
+        rc = libc.syscall(SYS_mbind, ctypes.c_void_p(start), ctypes.c_ulong(length), ctypes.c_int(MPOL_INTERLEAVE), mask,
+                          ctypes.c_ulong(16 * 64), ctypes.c_uint(0))
+        return rc == 0
+    except Exception:  # noqa: BLE001
+        return False
 
 
 class DistributedRenderer:
@@ -197,6 +229,7 @@ class DistributedRenderer:
         if self.rank == 0:
             self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
             name[0] = self._shm.name
+            _interleave_numa(self._shm.buf, nbytes)  # before the first touch (the page-locking below)
         if self.world > 1:
             self.dist.broadcast_object_list(name, src=0, group=self.group)
             if self.rank != 0:
