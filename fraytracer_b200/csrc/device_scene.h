@@ -119,6 +119,10 @@ struct DevScene {
     int32_t sub_ny, sub_nz; // fine cells along y and z
     float sub_scale;        // (float)(1 << sub_shift)
     float sub_lo[3], sub_hi[3];  // -halo and count + halo per axis, as floats
+    // "Fast region" in the same cell coordinates: the covered region clipped to the escape box (when there is one).  Inside it
+    // the evaluator needs no further coverage test and the ray machine no escape pre-check (trace_device.cuh in_fast_region);
+    // empty (lo = +inf) without a sub-grid.  Scheduling only: every position outside it takes the complete tests.
+    float fast_lo[3], fast_hi[3];
     int32_t sub_debug;      // bit 0: distrust every certificate (every evaluation also runs the sequential scan; tests)
                             // bit 1: COUNT kernels compare the certified result with the scan and count mismatches
 };

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <new>
 #include <string>
@@ -758,6 +759,19 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
     if (const char *d = getenv("FT_HINT_SPLIT")) s->hint_split_pct = std::min(std::max(atoi(d), 1), 1000);
     if (const char *d = getenv("FT_SUB_DEBUG")) s->dev.sub_debug = atoi(d);  // tests: 1 = distrust every certificate
     if (getenv("FT_NO_ESCAPE")) s->dev.esc_valid = 0;  // experiments only
+    for (int k = 0; k < 3; k++) {  // the fast region (device_scene.h): covered region of the sub-grid, clipped to the escape box
+        s->dev.fast_lo[k] = std::numeric_limits<float>::infinity();
+        s->dev.fast_hi[k] = -std::numeric_limits<float>::infinity();
+        if (!s->dev.sub_valid || getenv("FT_NO_FAST_REGION")) continue;
+        float lo = s->dev.sub_lo[k], hi = s->dev.sub_hi[k];
+        if (s->dev.esc_valid) {
+            const float *g1 = &s->dev.chain_g1.x, *g2 = &s->dev.chain_g2.x;
+            lo = std::max(lo, (s->dev.esc_lo[k] - g1[k]) * g2[k]);
+            hi = std::min(hi, (s->dev.esc_hi[k] - g1[k]) * g2[k]);
+        }
+        s->dev.fast_lo[k] = lo;
+        s->dev.fast_hi[k] = hi;
+    }
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->hint_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");

@@ -231,6 +231,25 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                     phase = SP_FETCH;
                 }
             }
+            // Wave 0: the tile's glass hits enter the hit queue together, in tile order -- the material stage and the path waves
+            // take 32 consecutive entries per warp, and appended hit by hit (as each lane finished its normal probes) the queue
+            // interleaved the pixels of all the tiles in flight: a path-wave chunk held two unrelated pixels and waited for the
+            // longer of their segments
+            if (PRIMARY && __any_sync(FULL, phase == SP_PARK)) {
+                const bool parked = phase == SP_PARK;
+                const unsigned pm = __ballot_sync(FULL, parked);
+                const int leader = __ffs(pm) - 1;
+                unsigned qbase = 0;
+                if (lane == leader) qbase = atomicAdd(P.hit_count, (unsigned)__popc(pm));
+                qbase = __shfl_sync(FULL, qbase, leader);
+                if (parked) {
+                    const unsigned idx = qbase + (unsigned)__popc(pm & ((1u << lane) - 1u));
+                    P.hit_q[3ull * idx + 0] = float4{ho.x, ho.y, ho.z, hlen};
+                    P.hit_q[3ull * idx + 1] = float4{hd.x, hd.y, hd.z, __uint_as_float(pixel)};
+                    P.hit_q[3ull * idx + 2] = float4{n.x, n.y, n.z, __int_as_float(mat)};
+                    phase = SP_FETCH;
+                }
+            }
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.work_counter, 32ull);
             base = __shfl_sync(FULL, base, 0);
@@ -465,16 +484,20 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 mat = __ldg(S.objects + leaf_obj).z;
                 const float4 m = ld4(S.materials + mat);
                 if (__float_as_uint(m.w) == (uint32_t)FT_MATERIAL_GLASS) {
+#if FT_SPEC_REFILL_MIN >= 32
                     if (PRIMARY) {
-                        push = true;  // the material stage takes it from the hit queue
+                        phase = SP_PARK;  // the tile's glass hits enter the hit queue together (fetch block)
                     } else if (P.wave >= P.max_bounces) {
                         P.slots[slot] = 0.0f;  // interaction budget spent
-#if FT_SPEC_REFILL_MIN >= 32
                     } else {
                         phase = SP_PARK;  // the material stage runs for the whole chunk at once (fetch block)
                     }
                     if (phase != SP_PARK) phase = SP_FETCH;
 #else
+                    if (PRIMARY) {
+                        push = true;  // the material stage takes it from the hit queue
+                    } else if (P.wave >= P.max_bounces) {
+                        P.slots[slot] = 0.0f;  // interaction budget spent
                     } else {
                         cont = glass_interact(xyz(m), wavelength_nu((int)kk, P.nl), P.seed_lo, P.seed_hi, pixel, kk,
                                               (uint32_t)P.wave, ho, hd, hlen, eps, n, inside);

@@ -488,8 +488,19 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     return true;
 }
 
+// The cell coordinate of p in U's spatial lookup, c = (p - aabbMin) * cellSizeInv (SdfBoundary.fs:276, header from the constant
+// bank), and whether it lies in the "fast region" -- the sub-grid's covered region clipped to the escape box (DevScene::fast_lo).
+// One box test serves two decisions there: the evaluator goes straight to the sub-grid, and the ray machine skips the escape
+// pre-check (a position inside the escape box cannot pass it).
+__device__ __forceinline__ V3 chain_coord(const DevScene &S, V3 p) { return (p - xyz(S.chain_g1)) * xyz(S.chain_g2); }
+__device__ __forceinline__ bool in_fast_region(const DevScene &S, V3 c) {
+    return c.x >= S.fast_lo[0] && c.y >= S.fast_lo[1] && c.z >= S.fast_lo[2] && c.x < S.fast_hi[0] && c.y < S.fast_hi[1] &&
+           c.z < S.fast_hi[2];
+}
+
+// `c` = chain_coord(S, p), `fast` = in_fast_region(S, c)
 template <bool COUNT>
-__device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, uint32_t &best_lo) {
+__device__ __forceinline__ float eval_chain_c(const DevScene &S, V3 p, V3 c, bool fast, Acc &acc, uint32_t &best_lo) {
     uint32_t i;
     float dtc;
     add_flops<COUNT>(acc, FLOPS_CELL_LOOKUP);
@@ -497,10 +508,9 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, u
     bool certified = false;
     {
         // SdfBoundary.fs:276-282 with U's header from the constant bank (see grid_cell_from)
-        const float4 g1 = S.chain_g1, g2 = S.chain_g2, g3 = S.chain_g3;
-        const V3 c = (p - xyz(g1)) * xyz(g2);
-        if (S.sub_valid && c.x >= S.sub_lo[0] && c.y >= S.sub_lo[1] && c.z >= S.sub_lo[2] && c.x < S.sub_hi[0] &&
-            c.y < S.sub_hi[1] && c.z < S.sub_hi[2]) {
+        const float4 g1 = S.chain_g1, g3 = S.chain_g3;
+        if (fast || (S.sub_valid && c.x >= S.sub_lo[0] && c.y >= S.sub_lo[1] && c.z >= S.sub_lo[2] && c.x < S.sub_hi[0] &&
+                     c.y < S.sub_hi[1] && c.z < S.sub_hi[2])) {
             uint32_t best = 0u;
             float ms = 0.f;
             certified = sub_lookup<COUNT>(S, p, __float2int_rd(c.x * S.sub_scale) + S.sub_off,
@@ -640,6 +650,12 @@ __device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, u
         }
     }
     return v;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ float eval_chain(const DevScene &S, V3 p, Acc &acc, uint32_t &best_lo) {
+    const V3 c = chain_coord(S, p);
+    return eval_chain_c<COUNT>(S, p, c, in_fast_region(S, c), acc, best_lo);
 }
 
 // out-of-line copy of the chain evaluator for callers outside the hot loop (the once-per-warp probe of the camera position in

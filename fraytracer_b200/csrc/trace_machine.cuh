@@ -403,16 +403,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         // ------------------------------------------------------------------ march pre-check (SdfForm.fs:94)
         // a ray whose Length is exhausted (or that hit the watchdog) ends as a miss without another evaluation
         int event = 0;  // 1 primary miss, 2 primary hit, 3 shadow finished (miss), 4 shadow finished (hit), 5 normal done
-        if (phase == PH_PRIMARY || phase == PH_SHADOW) {
-            if (len <= 0.0f || steps >= S.step_cap) {
-                if (!(len <= 0.0f)) atomicAdd(wstats + 2, 1u);
-                event = phase == PH_PRIMARY ? 1 : 3;
-            } else if (ESCAPE && S.esc_valid && outside_box(S.esc_lo, S.esc_hi, o) && ray_escapes(S, o, d, FT_EPS)) {
-                atomicAdd(wstats + 3, 1u);
-                event = phase == PH_PRIMARY ? 1 : 3;
-            }
-        }
-        // ------------------------------------------------------------------ the one distance evaluation
+        // the evaluation point
         V3 p = o;
         if (Job::kProbe && phase == PH_PROBE) {
             p = job.probe_point();
@@ -423,6 +414,19 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
             else if (phase == PH_N1) p.y = q.y + h;
             else if (phase == PH_N2) p.z = q.z + h;
         }
+        // chain scenes: one box test on the cell coordinate decides both "no escape pre-check" and "straight to the sub-grid"
+        const V3 cc = CHAIN ? chain_coord(S, p) : V3{0.f, 0.f, 0.f};
+        const bool fast = CHAIN && in_fast_region(S, cc);
+        if (phase == PH_PRIMARY || phase == PH_SHADOW) {
+            if (len <= 0.0f || steps >= S.step_cap) {
+                if (!(len <= 0.0f)) atomicAdd(wstats + 2, 1u);
+                event = phase == PH_PRIMARY ? 1 : 3;
+            } else if (ESCAPE && S.esc_valid && !fast && outside_box(S.esc_lo, S.esc_hi, o) && ray_escapes(S, o, d, FT_EPS)) {
+                atomicAdd(wstats + 3, 1u);
+                event = phase == PH_PRIMARY ? 1 : 3;
+            }
+        }
+        // ------------------------------------------------------------------ the one distance evaluation
         // Scheduling only (no arithmetic depends on it): positions outside the largest lookup's box scan whole
         // candidate lists (50-140 entries), positions inside it a handful.  The warp runs the two classes in
         // separate iterations so that one long scan does not hold 31 short ones hostage.
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
 #endif
             const unsigned long long f0 = acc.flops;
             uint32_t best_lo = 0u;
-            const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
+            const float dist = CHAIN ? eval_chain_c<COUNT>(S, p, cc, fast, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
             if (COUNT) {
                 acc.evals++;
                 if (is_long) {

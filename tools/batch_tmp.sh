@@ -1,3 +1,2 @@
-for v in "" r8m7 r16m7 r24m7 r16m6 r8m6; do
-  echo "config3 [$v]"; FT_LIB=${v:+build/lib_$v.so} python bench.py --workload config3 --no-cpu --steps 4 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['roofline']['frac'])"
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/kexp.py "" "FT_NO_FAST_REGION=1" "FT_LIB=build/lib_head.so" > gpurun_out/r3a_kexp.txt 2>&1; cut -c1-150 gpurun_out/r3a_kexp.txt
