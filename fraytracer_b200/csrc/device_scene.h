@@ -106,7 +106,9 @@ struct DevScene {
     // cell coordinate, SdfBoundary.fs:276), the fine index along an axis is  g = floor(c * sub_scale) + sub_off  (the product is
     // exact: sub_scale is a power of two), valid for sub_lo <= c < sub_hi; the reference's cell is clamp(floor(c)) =
     // clamp((g - sub_off) >> sub_shift), so a fine cell maps to ONE reference cell, halo included (border cells).
-    // sub_hdr[(gx * sub_ny + gy) * sub_nz + gz] = {(first << 8) | count, nearest candidate}; sub_idx[first ...] holds candidates
+    // sub_hdr[(gx * sub_ny + gy) * sub_nz + gz] = {(first << 8) | count, (q << 24) | nearest candidate}, q = a lower bound of
+    // dist(p, reference cell centre) over the fine cell in quanta of 1 / (256 sub_dtc_inv) (certificate (1) of sub_lookup);
+    // sub_idx[first ...] holds candidates
     // 1 .. count-1: ABSOLUTE indices into entries[] -- those candidates of the reference cell's own list that can be the nearest
     // one for some position inside the fine cell (all others are provably farther than the nearest by a margin), nearest first.
     // Positions inside the covered region evaluate only these (eval_chain); the result is certified equal to the reference's
@@ -118,6 +120,7 @@ struct DevScene {
     int32_t sub_off;        // sub_halo << sub_shift
     int32_t sub_ny, sub_nz; // fine cells along y and z
     float sub_scale;        // (float)(1 << sub_shift)
+    float sub_dtc_inv;      // 1 / (256 quanta): fma(x, sub_dtc_inv, 1) <= as_float(0x3f800000 | q << 15)  <=>  x <= q quanta
     float sub_lo[3], sub_hi[3];  // -halo and count + halo per axis, as floats
     // "Fast region" in the same cell coordinates: the covered region clipped to the escape box (when there is one).  Inside it
     // the evaluator needs no further coverage test and the ray machine no escape pre-check (trace_device.cuh in_fast_region);

@@ -712,7 +712,8 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
     if (getenv("FT_NO_CHAIN")) s->dev.chain_valid = 0;  // experiments / tests of the generic interpreter
     // nearest-candidate sub-grid of the chain union's lookup (device_scene.h): built on the device from the uploaded scene
     s->dev.sub_valid = 0;
-    if (s->dev.chain_valid && !getenv("FT_NO_SUBGRID")) {
+    // (its headers address candidate records with 24 bits: scenes with 2^24 or more records -- half a gigabyte of them -- keep the scan)
+    if (s->dev.chain_valid && !getenv("FT_NO_SUBGRID") && h.fat_entries.size() / 2 < ((size_t)1 << 24)) {
         uint32_t cell_base;
         std::memcpy(&cell_base, &s->dev.chain_g1.w, sizeof(cell_base));
         for (const ftc::GridHost &g : h.grids) {
@@ -742,6 +743,7 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
                 s->dev.sub_ny = s->sub.ny;
                 s->dev.sub_nz = s->sub.nz;
                 s->dev.sub_scale = (float)s->sub.res;
+                s->dev.sub_dtc_inv = 1.0f / (256.0f * s->sub.dtc_unit);
                 for (int k = 0; k < 3; k++) {
                     s->dev.sub_lo[k] = -(float)s->sub.halo;
                     s->dev.sub_hi[k] = (float)(g.count[k] + s->sub.halo);

@@ -20,7 +20,7 @@ struct SubGrid {
     uint32_t *idx = nullptr;
     int res = 0, shift = 0, halo = 0, ny = 0, nz = 0;
     long long n_subcells = 0, n_entries = 0, bytes = 0;
-    float threshold = 0.f, build_ms = 0.f;
+    float threshold = 0.f, build_ms = 0.f, dtc_unit = 0.f;
 };
 // `S` must already hold the uploaded nodes / cells / entries.  Returns cudaSuccess with out->hdr == nullptr when the lookup is
 // too large to encode (the kernels then always run the reference's scan).

@@ -33,6 +33,7 @@ struct SubParams {
     int nx, ny, nz;          // fine cells per axis: (count + 2 halo) S
     uint32_t cell_base;      // first cell of U in cells[]
     float thr;               // 2 hd + tol
+    float dtc_unit;          // quantum of the header's lower bound of dist(p, cell centre) (half a cell diagonal / 255)
     unsigned n_sub;          // nx ny nz
 };
 
@@ -48,6 +49,25 @@ __device__ __forceinline__ V3 sub_centre(const SubParams &P, unsigned t, uint32_
     const float inv = 1.0f / (float)P.S;
     return V3{P.amin[0] + (((float)fx + 0.5f) * inv) * P.cell[0], P.amin[1] + (((float)fy + 0.5f) * inv) * P.cell[1],
               P.amin[2] + (((float)fz + 0.5f) * inv) * P.cell[2]};
+}
+
+// A lower bound, in quanta of P.dtc_unit (0 .. 255, rounded down and then lowered by one more quantum: the margin of
+// sub_lookup's certificate (1)), of dist(p, centre of the reference cell) over all positions p the kernels can assign to fine
+// cell t.  The fine cell is inflated by 1e-3 of its size for the rounding of the cell coordinate it is derived from.
+__device__ __forceinline__ unsigned sub_dtc_quanta(const SubParams &P, unsigned t) {
+    const int gz = (int)(t % P.nz), gy = (int)((t / P.nz) % P.ny), gx = (int)(t / (P.nz * P.ny));
+    const int off = P.halo << P.shift;
+    const int f[3] = {gx - off, gy - off, gz - off}, cnt[3] = {P.cx, P.cy, P.cz};
+    double s2 = 0.0;
+    for (int k = 0; k < 3; k++) {
+        const int i = min(max(f[k] >> P.shift, 0), cnt[k] - 1);
+        const double centre = ((double)i + 0.5) * (double)P.S;  // in fine-cell units from aabbMin
+        double gap = fabs(((double)f[k] + 0.5) - centre) - 0.5 - 1e-3;
+        gap = gap > 0.0 ? gap * ((double)P.cell[k] / (double)P.S) : 0.0;
+        s2 += gap * gap;
+    }
+    const double q = floor(sqrt(s2) / (double)P.dtc_unit) - 1.0;
+    return q <= 0.0 ? 0u : (q >= 255.0 ? 255u : (unsigned)q);
 }
 
 // pass 1: nearest candidate distance at the sub-cell centre and the number of candidates within the threshold
@@ -114,7 +134,8 @@ __global__ void __launch_bounds__(128) sub_fill_kernel(const __grid_constant__ D
     // the count pass and this pass see the same distances, so m - 1 == count[t] whenever the list is encodable; a list the
     // count pass refused (more than 255 candidates) stays empty
     const bool ok = m > 0u && m - 1u == count[t];
-    hdr[t] = ok ? make_uint2((off << 8) | m, out[0]) : make_uint2(0u, 0u);
+    // header: {(first << 8) | count, (dtc quanta << 24) | nearest candidate}; entries[] indices are < 2^24 (checked by the caller)
+    hdr[t] = ok ? make_uint2((off << 8) | m, (sub_dtc_quanta(P, t) << 24) | out[0]) : make_uint2(0u, 0u);
     for (uint32_t j = 1; ok && j < m; j++) idx_out[off + j - 1u] = out[j];
 }
 
@@ -171,6 +192,8 @@ cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out
         P.nz = (job.count[2] + 2 * halo) * res;
         P.cell_base = job.cell_base;
         P.thr = (float)(2.0 * std::sqrt(hd2) + tol);
+        P.dtc_unit = (float)(0.5 * std::sqrt((double)job.cell[0] * job.cell[0] + (double)job.cell[1] * job.cell[1] +
+                                             (double)job.cell[2] * job.cell[2]) / 255.0);
         const long long n_sub = n_cells * res * res * res;
         if (n_sub >= (1ll << 31)) { if (res > 1) continue; cleanup(); return cudaSuccess; }
         P.n_sub = (unsigned)n_sub;
@@ -211,6 +234,7 @@ cudaError_t build_subgrid(const DevScene &S, const SubGridJob &job, SubGrid *out
         out->n_entries = (long long)total + n_sub;  // the nearest candidate of every sub-cell lives in its header
         out->bytes = (long long)sizeof(uint2) * n_sub + (long long)sizeof(uint32_t) * std::max(1u, total);
         out->threshold = P.thr;
+        out->dtc_unit = P.dtc_unit;
         cudaEventElapsedTime(&out->build_ms, e0, e1);
         cleanup();
         return cudaSuccess;

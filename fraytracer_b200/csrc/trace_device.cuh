@@ -437,7 +437,7 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     const uint32_t *lp = S.sub_idx + (hdr.x >> 8);  // candidates 1 .. n-1
     float M = __int_as_float(0x7f800000);
     uint32_t best = 0xffffffffu;
-    uint32_t idx = hdr.y;
+    uint32_t idx = hdr.y & 0xffffffu;
     for (uint32_t k = 0;;) {
         const Entry e = ld_entry(S, idx);
         const bool more = ++k < n;
@@ -464,7 +464,11 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     add_flops<COUNT>(acc, 12);
     const float x = eb.lb() - M;
     bool ok = true;
-    if (x > 0.0f) {  // (1)  M >= fl(lb - dtc): certainly true when |p - centre|^2 > x^2 (1 + 2^-10); else compare exactly
+    // (1)  M >= fl(lb - dtc).  Certainly true when x = fl(lb - M) <= dq, dq = the header's lower bound of dtc over the whole fine
+    // cell (rounded down to its 8-bit quantum and lowered by one more, which dwarfs the roundings of x, dtc and the
+    // difference): lb - dtc <= lb - dq <= M.  The comparison runs on 1 + x / (256 quanta) against the float whose top mantissa
+    // bits are q (no integer-to-float conversion).  Otherwise: certainly true when |p - centre|^2 > x^2 (1 + 2^-10); else exact.
+    if (__fmaf_rn(x, S.sub_dtc_inv, 1.0f) > __uint_as_float(0x3f800000u | ((hdr.y >> 24) << 15))) {
         // the reference's cell of this fine cell: clamp(floor(c)) per axis (SdfBoundary.fs:276-282)
         const int mx = __float_as_int(S.chain_g3.x), my = __float_as_int(S.chain_g3.y), mz = __float_as_int(S.chain_g3.z);
         const int ix = min(max((gx - S.sub_off) >> S.sub_shift, 0), mx), iy = min(max((gy - S.sub_off) >> S.sub_shift, 0), my),

@@ -1,2 +1,2 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/kexp.py "" "FT_NO_FAST_REGION=1" "FT_LIB=build/lib_head.so" > gpurun_out/r3a_kexp.txt 2>&1; cut -c1-150 gpurun_out/r3a_kexp.txt
+python tools/kexp.py "" "FT_LIB=build/lib_head.so" > gpurun_out/r3b_kexp.txt 2>&1; cut -c1-150 gpurun_out/r3b_kexp.txt
