@@ -48,6 +48,9 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #ifndef FT_WITH_CONE
 #define FT_WITH_CONE 0
 #endif
+#ifndef FT_SUB_PREFETCH
+#define FT_SUB_PREFETCH 0  // sub_lookup loads the index of candidate k + 1 before it evaluates candidate k
+#endif
 #ifndef FT_INLINE_PRIM
 #define FT_INLINE_PRIM 0  // 1: primitives met by the candidate scan are evaluated inside the scan loop
 #endif
@@ -438,9 +441,15 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     float M = __int_as_float(0x7f800000);
     uint32_t best = 0xffffffffu;
     uint32_t idx = hdr.y & 0xffffffu;
+#if FT_SUB_PREFETCH
+    uint32_t nxt = n > 1u ? __ldg(lp) : 0u;  // the index of candidate k + 1 is in flight while candidate k is evaluated
+#endif
     for (uint32_t k = 0;;) {
         const Entry e = ld_entry(S, idx);
         const bool more = ++k < n;
+#if FT_SUB_PREFETCH
+        const uint32_t nn = k + 1u < n ? __ldg(lp + k) : 0u;
+#endif
         add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
         if (!certain_fail_up(M, e.bound(), e.b.w, p)) {
             float d;
@@ -456,7 +465,12 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
             }
         }
         if (!more) break;
+#if FT_SUB_PREFETCH
+        idx = nxt;
+        nxt = nn;
+#else
         idx = __ldg(lp + k - 1u);
+#endif
     }
     if (best == 0xffffffffu) return false;  // nothing comparable (NaN positions): the scan decides
     // certificates on the arg-min

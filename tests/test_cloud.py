@@ -193,3 +193,21 @@ def test_gpu_config4_full_size_columns_bit_exact():
     cols = np.arange(0, X, stride)
     assert np.array_equal(bits(img[cols]), bits(ref[cols]))
     tracer.close()
+
+
+@pytest.mark.gpu
+def test_gpu_instrumented_variant_counts_work_and_changes_nothing():
+    """ft_scene_set_debug bit 3: the COUNT kernel (bench.py's roofline numerator) returns the same image and counters and
+    fills eval_flops; a tracking step costs at least its density evaluation (95 operations) plus a Distance evaluation."""
+    cp = CloudParams()
+    tracer = ft.SceneTracer(_puff_scene(), device=0)
+    img, st = tracer.render_cloud(_camera(), ImageSize(96, 72), 0.01, 30.0, cp, 8, 19)
+    tracer.set_debug(8)
+    img_c, st_c = tracer.render_cloud(_camera(), ImageSize(96, 72), 0.01, 30.0, cp, 8, 19)
+    tracer.set_debug(0)
+    tracer.close()
+    assert np.array_equal(bits(img), bits(img_c))
+    assert st["eval_flops"] == 0
+    for k in ("primary_rays", "shadow_rays", "march_steps", "reserved"):
+        assert st[k] == st_c[k], k
+    assert st_c["eval_flops"] > 100 * st_c["march_steps"]

@@ -193,3 +193,22 @@ def test_gpu_config3_full_size_columns_bit_exact():
     black, st0 = tracer.render_spectral(w.camera, w.size, w.epsilon, w.length, 16, 0, 19)
     assert int((np.abs(black).max(axis=2) == 0.0).sum()) == st["reserved"] == st0["reserved"]
     tracer.close()
+
+
+@pytest.mark.gpu
+def test_gpu_instrumented_variant_counts_work_and_changes_nothing():
+    """ft_scene_set_debug bit 3: the COUNT kernels (bench.py's roofline numerator) return the same image bit for bit and fill
+    eval_flops / march_steps; the plain kernels leave them at zero."""
+    w = scenes.spectral_glass_scene(width=160, height=90)
+    tracer = ft.SceneTracer(w.scene, device=0)
+    img, st = tracer.render_spectral(_camera(), ImageSize(160, 90), 0.01, 30.0, 16, 8, 19)
+    tracer.set_debug(8)
+    img_c, st_c = tracer.render_spectral(_camera(), ImageSize(160, 90), 0.01, 30.0, 16, 8, 19)
+    tracer.set_debug(0)
+    tracer.close()
+    assert np.array_equal(bits(img), bits(img_c))
+    assert st["eval_flops"] == 0 and st["march_steps"] == 0
+    rays = st_c["primary_rays"] + st_c["shadow_rays"]
+    assert st_c["shadow_rays"] == st["shadow_rays"] and st_c["reserved"] == st["reserved"]
+    assert st_c["march_steps"] > rays  # several Distance evaluations per ray ...
+    assert 50 * st_c["march_steps"] < st_c["eval_flops"] < 5000 * st_c["march_steps"]  # ... each tens to hundreds of flops
