@@ -487,6 +487,20 @@ def bench_b200(args):
                               strip_width=sw, rank=rank, world=world, want_stats=True)
     my_rays = st["primary_rays"] + st["shadow_rays"]
     my_flops = st["eval_flops"]
+    # the same strips through the reference's own sequential candidate scan (no sub-grid): what the reference's algorithm
+    # performs for this frame, with this implementation's sorted early exit and escape proof -- round 1's roofline numerator
+    scan_flops = None
+    if rank == 0:
+        os.environ["FT_NO_SUBGRID"] = "1"
+        try:
+            scan_tracer = ft.SceneTracer(w.scene, device=local_rank)
+            st_scan = scan_tracer.render_device(w.camera, w.size, w.epsilon, w.length, buf.data_ptr(),
+                                                stream=torch.cuda.current_stream().cuda_stream, flags=flags | A.FT_FLAG_COUNTERS,
+                                                strip_width=sw, rank=rank, world=world, want_stats=True)
+            scan_flops = st_scan["eval_flops"]
+            scan_tracer.close()
+        finally:
+            del os.environ["FT_NO_SUBGRID"]
     total_rays = allreduce(float(my_rays), dist.ReduceOp.SUM if world > 1 else None)
     capped = allreduce(float(st["capped_rays"]), dist.ReduceOp.SUM if world > 1 else None)
 
@@ -650,6 +664,14 @@ def bench_b200(args):
                     "rays_per_launch": my_rays, "distance_evaluations_in_marches": st["march_steps"],
                     "march_steps_per_ray": st["march_steps"] / max(1, my_rays),
                     "flops_per_ray": my_flops / max(1, my_rays), "rays_ended_by_escape_proof": st["escaped_rays"],
+                    # for comparison across rounds: the operations the reference's sequential scan performs on the same
+                    # strips (instrumented kernel with the sub-grid off) over the same launch time
+                    "equal_work": None if not scan_flops else {
+                        "flops_per_launch": scan_flops, "achieved": scan_flops / (kern_ms * 1e-3) / 1e12,
+                        "frac": scan_flops / (kern_ms * 1e-3) / 1e12 / tf.value if tf.value else None,
+                        "note": "NOT the roofline figure: `achieved` counts what this implementation executes; this is the "
+                                "work of the reference's candidate scan for the same frame, most of which the certified "
+                                "sub-grid path skips"},
                     "peak_source": "measured live: dependent-free FFMA stream on all SMs, FMA = 2 flops "
                                    "(MEASURED_PEAKS.json has no FP32 entry); strict mode issues no FMA, so its "
                                    "ceiling is half of this",

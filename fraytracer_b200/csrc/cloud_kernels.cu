@@ -259,9 +259,6 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             if (len <= 0.0f || steps >= S.step_cap) {
                 if (!(len <= 0.0f)) n_capped++;
                 event = phase == C_MARCH ? 1 : 3;
-            } else if (S.esc_valid && outside_box(S.esc_lo, S.esc_hi, o) && ray_escapes(S, o, d, eps)) {
-                n_escaped++;
-                event = phase == C_MARCH ? 1 : 3;
             }
         } else if (phase >= C_N0 && phase <= C_N3) {
             const float h = eps * 0.125f;
@@ -279,10 +276,18 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             else if (k >= (uint32_t)FT_CLOUD_MAX_TRACK_STEPS) event = 8;
             p = ps + d * t;
         }
+        // chain scenes: one box test on the cell coordinate decides "no escape pre-check" and "straight to the sub-grid"
+        const V3 cc = CHAIN ? chain_coord(S, p) : V3{0.f, 0.f, 0.f};
+        const bool fast = CHAIN && in_fast_region(S, cc);
+        if ((phase == C_MARCH || phase == C_SHADOW) && event == 0 && S.esc_valid && !fast && outside_box(S.esc_lo, S.esc_hi, o) &&
+            ray_escapes(S, o, d, eps)) {
+            n_escaped++;
+            event = phase == C_MARCH ? 1 : 3;
+        }
         // ------------------------------------------------------------------ the one distance evaluation
         if (phase > C_FETCH && event == 0) {
             uint32_t best_lo = 0u;
-            const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
+            const float dist = CHAIN ? eval_chain_c<COUNT>(S, p, cc, fast, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
             if (phase <= C_SHADOW) {
                 steps++;
                 add_flops<COUNT>(acc, FLOPS_MOVE + 1);

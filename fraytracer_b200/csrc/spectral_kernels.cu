@@ -383,18 +383,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
 #endif
         // ------------------------------------------------------------------ march pre-check
         int event = 0;  // 1 march miss, 2 march hit, 3 shadow ray unoccluded, 4 shadow ray occluded, 5 normal done
-        if (phase == SP_MARCH || phase == SP_SHADOW) {
-            if (len <= 0.0f || steps >= S.step_cap) {
-                if (!(len <= 0.0f)) n_capped++;
-                event = phase == SP_MARCH ? 1 : 3;
-            } else if (S.esc_valid && (phase == SP_SHADOW || !armed || sign > 0.0f) && outside_box(S.esc_lo, S.esc_hi, o) &&
-                       ray_escapes(S, o, d, eps)) {
-                n_escaped++;  // Distance >= distance to the escape box > epsilon along the whole half-line: no hit ahead
-                event = phase == SP_MARCH ? 1 : 3;
-            }
-        }
-        // ------------------------------------------------------------------ the one distance evaluation
-        V3 p = o;
+        V3 p = o;  // the evaluation point
         if (phase >= SP_N0) {
             const float h = eps * 0.125f;
             p = q;
@@ -402,9 +391,23 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
             else if (phase == SP_N1) p.y = q.y + h;
             else if (phase == SP_N2) p.z = q.z + h;
         }
+        // chain scenes: one box test on the cell coordinate decides "no escape pre-check" and "straight to the sub-grid"
+        const V3 cc = CHAIN ? chain_coord(S, p) : V3{0.f, 0.f, 0.f};
+        const bool fast = CHAIN && in_fast_region(S, cc);
+        if (phase == SP_MARCH || phase == SP_SHADOW) {
+            if (len <= 0.0f || steps >= S.step_cap) {
+                if (!(len <= 0.0f)) n_capped++;
+                event = phase == SP_MARCH ? 1 : 3;
+            } else if (S.esc_valid && !fast && (phase == SP_SHADOW || !armed || sign > 0.0f) && outside_box(S.esc_lo, S.esc_hi, o) &&
+                       ray_escapes(S, o, d, eps)) {
+                n_escaped++;  // Distance >= distance to the escape box > epsilon along the whole half-line: no hit ahead
+                event = phase == SP_MARCH ? 1 : 3;
+            }
+        }
+        // ------------------------------------------------------------------ the one distance evaluation
         if (phase > SP_FETCH && event == 0) {
             uint32_t best_lo = 0u;
-            const float dist = CHAIN ? eval_chain<COUNT>(S, p, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
+            const float dist = CHAIN ? eval_chain_c<COUNT>(S, p, cc, fast, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
             if (COUNT && phase <= SP_SHADOW) {
                 acc.steps++;
                 add_flops<COUNT>(acc, FLOPS_MOVE + 2);
