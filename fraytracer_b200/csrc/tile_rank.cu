@@ -16,7 +16,9 @@
 //    tools/micro/pcie_store.cu: 4x8 tiles stored in scattered order reach 26-29 GB/s, in natural order 47 GB/s, the copy engine
 //    56 GB/s).  One ascending radix sort of the keys gives the order.  Measured end to end through ft_render (B200, median of
 //    40 frames, config 2 at 1080p / config 5 at 4K): natural order 1.11 / 2.99 ms, plain LPT 1.03 / 3.70, split 0.5 1.11 / 3.68,
-//    split 1 0.97 / 3.22, split 1.5 0.99 / 3.05 (the default), split 2 1.01 / 3.02, split 4 1.05 / 3.11.
+//    split 1 0.97 / 3.22, split 1.5 0.99 / 3.05 (the default), split 2 1.01 / 3.02, split 4 1.05 / 3.11.  The launch itself
+//    takes 0.914 ms with host stores in this order against 0.79 ms into device memory (LPT); ending the launch on its cheapest
+//    tiles (a window for the non-tops that shrinks with their cost) changes nothing (0.913-0.921 ms): what is left is the link.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
