@@ -48,9 +48,6 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #ifndef FT_WITH_CONE
 #define FT_WITH_CONE 0
 #endif
-#ifndef FT_SUB_PREFETCH
-#define FT_SUB_PREFETCH 0  // sub_lookup loads the index of candidate k + 1 before it evaluates candidate k
-#endif
 #ifndef FT_INLINE_PRIM
 #define FT_INLINE_PRIM 0  // 1: primitives met by the candidate scan are evaluated inside the scan loop
 #endif
@@ -428,6 +425,16 @@ __device__ __forceinline__ bool certain_fail_up(float M, float4 b0, float rup, V
     return sf > __fmaf_rn(u, u, 1e-30f);
 }
 
+// The cell coordinate of p in U's spatial lookup, c = (p - aabbMin) * cellSizeInv (SdfBoundary.fs:276, header from the constant
+// bank), and whether it lies in the "fast region" -- the sub-grid's covered region clipped to the escape box (DevScene::fast_lo).
+// One box test serves two decisions there: the evaluator goes straight to the sub-grid, and the ray machine skips the escape
+// pre-check (a position inside the escape box cannot pass it).
+__device__ __forceinline__ V3 chain_coord(const DevScene &S, V3 p) { return (p - xyz(S.chain_g1)) * xyz(S.chain_g2); }
+__device__ __forceinline__ bool in_fast_region(const DevScene &S, V3 c) {
+    return c.x >= S.fast_lo[0] && c.y >= S.fast_lo[1] && c.z >= S.fast_lo[2] && c.x < S.fast_hi[0] && c.y < S.fast_hi[1] &&
+           c.z < S.fast_hi[2];
+}
+
 // `g` = the fine-cell coordinates of p (see DevScene): the caller has checked that p lies in the covered region
 template <bool COUNT>
 __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int gy, int gz, float &m_out, uint32_t &best_out,
@@ -441,15 +448,9 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     float M = __int_as_float(0x7f800000);
     uint32_t best = 0xffffffffu;
     uint32_t idx = hdr.y & 0xffffffu;
-#if FT_SUB_PREFETCH
-    uint32_t nxt = n > 1u ? __ldg(lp) : 0u;  // the index of candidate k + 1 is in flight while candidate k is evaluated
-#endif
     for (uint32_t k = 0;;) {
         const Entry e = ld_entry(S, idx);
         const bool more = ++k < n;
-#if FT_SUB_PREFETCH
-        const uint32_t nn = k + 1u < n ? __ldg(lp + k) : 0u;
-#endif
         add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
         if (!certain_fail_up(M, e.bound(), e.b.w, p)) {
             float d;
@@ -465,12 +466,7 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
             }
         }
         if (!more) break;
-#if FT_SUB_PREFETCH
-        idx = nxt;
-        nxt = nn;
-#else
-        idx = __ldg(lp + k - 1u);
-#endif
+        idx = __ldg(lp + k - 1u);  // (prefetching it one candidate ahead costs a register: measured 0.792 -> 0.821 ms)
     }
     if (best == 0xffffffffu) return false;  // nothing comparable (NaN positions): the scan decides
     // certificates on the arg-min
@@ -483,10 +479,11 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     // difference): lb - dtc <= lb - dq <= M.  The comparison runs on 1 + x / (256 quanta) against the float whose top mantissa
     // bits are q (no integer-to-float conversion).  Otherwise: certainly true when |p - centre|^2 > x^2 (1 + 2^-10); else exact.
     if (__fmaf_rn(x, S.sub_dtc_inv, 1.0f) > __uint_as_float(0x3f800000u | ((hdr.y >> 24) << 15))) {
-        // the reference's cell of this fine cell: clamp(floor(c)) per axis (SdfBoundary.fs:276-282)
+        // the reference's cell, clamp(floor(c)) per axis (SdfBoundary.fs:276-282), from the position again rather than from the
+        // fine-cell coordinates: those need not stay live across the candidate loop (three registers where the kernel spills)
+        const V3 c = chain_coord(S, p);
         const int mx = __float_as_int(S.chain_g3.x), my = __float_as_int(S.chain_g3.y), mz = __float_as_int(S.chain_g3.z);
-        const int ix = min(max((gx - S.sub_off) >> S.sub_shift, 0), mx), iy = min(max((gy - S.sub_off) >> S.sub_shift, 0), my),
-                  iz = min(max((gz - S.sub_off) >> S.sub_shift, 0), mz);
+        const int ix = cell_index(c.x, mx), iy = cell_index(c.y, my), iz = cell_index(c.z, mz);
         const float4 cell = ld4(S.cells + (__float_as_uint(S.chain_g1.w) +
                                            (uint32_t)(ix * __float_as_int(S.chain_g3.w) + iy * (mz + 1) + iz)));
         const V3 dc = p - xyz(cell);
@@ -504,16 +501,6 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     m_out = M;
     best_out = best;
     return true;
-}
-
-// The cell coordinate of p in U's spatial lookup, c = (p - aabbMin) * cellSizeInv (SdfBoundary.fs:276, header from the constant
-// bank), and whether it lies in the "fast region" -- the sub-grid's covered region clipped to the escape box (DevScene::fast_lo).
-// One box test serves two decisions there: the evaluator goes straight to the sub-grid, and the ray machine skips the escape
-// pre-check (a position inside the escape box cannot pass it).
-__device__ __forceinline__ V3 chain_coord(const DevScene &S, V3 p) { return (p - xyz(S.chain_g1)) * xyz(S.chain_g2); }
-__device__ __forceinline__ bool in_fast_region(const DevScene &S, V3 c) {
-    return c.x >= S.fast_lo[0] && c.y >= S.fast_lo[1] && c.z >= S.fast_lo[2] && c.x < S.fast_hi[0] && c.y < S.fast_hi[1] &&
-           c.z < S.fast_hi[2];
 }
 
 // `c` = chain_coord(S, p), `fast` = in_fast_region(S, c)

@@ -506,3 +506,37 @@ def test_tile_order_hints_change_nothing_but_the_schedule():
         for d in dst:
             assert np.array_equal(bits(d.cpu().numpy()), bits(ref["rgb"])), frame
     A.check(tracer.lib.ft_host_free(host))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make", [scenes.default_scene, scenes.spheres_capsules_scene])
+def test_hinted_frames_equal_the_first_frame_at_full_size(make):
+    """BASELINE frame sizes (1000x1000, 1920x1080): every later frame of a shape -- drawn in ranked tile order, a permutation that
+    tile_rank.cu derives on the device -- equals the first frame (natural order) bit for bit, leaf indices included, for a device
+    destination (longest-processing-time-first) and for a mapped host destination (timed merge)."""
+    import ctypes as C
+
+    import torch
+
+    w = make()
+    X, Y = w.size.X, w.size.Y
+    tracer = ft.SceneTracer(w.scene, device=0)
+    host = C.c_void_p()
+    A.check(tracer.lib.ft_host_alloc(C.byref(host), X * Y * 12))
+    mapped = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(X, Y, 3))
+    dev = torch.empty((X, Y, 3), dtype=torch.float32, device="cuda:0")
+    first_dev = first_host = None
+    for frame in range(5):
+        dev.fill_(-1.0)
+        tracer.render_device(w.camera, w.size, w.epsilon, w.length, dev.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        mapped.fill(-1.0)
+        tracer.render(w.camera, w.size, w.epsilon, w.length, out=mapped)
+        if frame == 0:
+            first_dev, first_host = dev.cpu().numpy().copy(), mapped.copy()
+            assert np.array_equal(bits(first_dev), bits(first_host))
+        else:
+            assert np.array_equal(bits(dev.cpu().numpy()), bits(first_dev)), frame
+            assert np.array_equal(bits(mapped), bits(first_host)), frame
+    A.check(tracer.lib.ft_host_free(host))
+    tracer.close()
