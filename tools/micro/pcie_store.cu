@@ -160,6 +160,25 @@ int main(int argc, char **argv) {
     Ctx c{hdev, W, H, nullptr, 0, counter, 0, prop.multiProcessorCount * 9, s, dev, bytes};
     time_it("cudaMemcpyAsync D2H (copy engine)", bytes, 5, launch_memcpy, &c, s);
     time_it("linear 512 B per warp, host", bytes, 5, launch_linear, &c, s);
+    if (argc > 3 && !strcmp(argv[3], "quick")) {
+        // several GPUs at once (one process each, CUDA_VISIBLE_DEVICES): what the host takes in from all of them together.
+        // Two seconds of each, so that the processes overlap whatever their start skew.
+        for (int pass = 0; pass < 2; pass++) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            const int reps = (int)(2.0 / (bytes / 45e9)) + 1;
+            CK(cudaEventRecord(a, s));
+            for (int r = 0; r < reps; r++) (pass ? launch_linear : launch_memcpy)(&c);
+            CK(cudaEventRecord(b, s));
+            CK(cudaEventSynchronize(b));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            printf("sustained %-30s %8.1f GB/s over %.2f s\n", pass ? "linear stores (SMs)" : "cudaMemcpyAsync D2H", (double)bytes * reps / ms / 1e6,
+                   ms / 1e3);
+        }
+        return 0;
+    }
     // shuffled tile orders
     auto make_order = [&](int TW, int TH, int kind) {
         const unsigned n = (unsigned)(W / TW) * (H / TH);
