@@ -185,8 +185,11 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
     int x = 0, y = 0, s = 0, spp_eff = 0, item_group = 0;  // spp_eff: one past the last sample of this work item
     long long item_tile = 0;
     uint32_t pixel = 0, seg = 0, stream = 0, k = 0;
-    V3 sum{0, 0, 0}, o{0, 0, 0}, d{0, 0, 0}, cd{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, ho{0, 0, 0}, ps{0, 0, 0}, lc{0, 0, 0}, cint{0, 0, 0};
-    float len = 0.f, hlen = 0.f, lcos = 0.f, xi0 = 0.f, ucur = 0.f, maxdist = 0.f;
+    // (o, d, len) stay the un-moved hit ray while the normal is probed and while the camera ray is tracked through the medium
+    // (neither touches them; d is the sample's camera direction until a shadow ray or a light track ends the sample), and a
+    // light's intensity is formed again from its record when its visibility is decided: no copies are carried
+    V3 sum{0, 0, 0}, o{0, 0, 0}, d{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, ps{0, 0, 0}, lc{0, 0, 0};
+    float len = 0.f, xi0 = 0.f, ucur = 0.f, maxdist = 0.f;
     int steps = 0, light = 0, mat = 0;
     unsigned n_hits = 0, n_secondary = 0, n_capped = 0, n_escaped = 0, n_scattered = 0;
     unsigned long long n_track = 0;
@@ -235,9 +238,8 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             const V3 fwd = V3{P.cam.forward[0], P.cam.forward[1], P.cam.forward[2]};
             const V3 rs = V3{P.cam.right_scaled[0], P.cam.right_scaled[1], P.cam.right_scaled[2]};
             const V3 us = V3{P.cam.up_scaled[0], P.cam.up_scaled[1], P.cam.up_scaled[2]};
-            cd = normalize((fwd + rs * (pu - 0.5f)) + us * (pv - 0.5f));
+            d = normalize((fwd + rs * (pu - 0.5f)) + us * (pv - 0.5f));
             o = cam;
-            d = cd;
             len = P.length;
             steps = 0;
             if (len > 0.0f && d0 >= eps) {  // first iteration of the march with the shared Distance
@@ -268,8 +270,8 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             else if (phase == C_N2) p.z = q.z + h;
         } else if (phase == C_TRACK) {
             t = ((float)k + xi0) * P.step;
-            if (hlen - t <= 0.0f || k >= (uint32_t)FT_CLOUD_MAX_TRACK_STEPS) event = 6;
-            p = ho + cd * t;
+            if (len - t <= 0.0f || k >= (uint32_t)FT_CLOUD_MAX_TRACK_STEPS) event = 6;
+            p = o + d * t;
         } else if (phase == C_LTRACK) {
             t = ((float)k + xi0) * P.step;
             if (t >= maxdist) event = 7;
@@ -322,8 +324,7 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                         } else {
                             n_secondary++;
                             o = p;
-                            d = cd;
-                            len = hlen - t;
+                            len = len - t;
                             steps = 0;
                             phase = C_MARCH;
                         }
@@ -369,15 +370,13 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             V3 L = bg;
             if (event == 1 || event == 6) {  // SdfScene.fs:10
                 finish = true;
-            } else if (event == 2) {  // hit: the un-moved hit ray stays in ho / hlen, probe the normal
-                ho = o;
-                hlen = len;
+            } else if (event == 2) {  // hit: the un-moved hit ray stays in (o, d, len), probe the normal
                 q = o + d * (-eps);
                 n_hits++;
                 phase = C_N0;
             } else if (event == 5) {
-                const int leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, ho, hit_best)
-                                                                                  : material_leaf<COUNT>(S, ho, acc);
+                const int leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, o, hit_best)
+                                                                                  : material_leaf<COUNT>(S, o, acc);
                 mat = __ldg(S.objects + leaf_obj).z;
                 if (__float_as_uint(ld4(S.materials + mat).w) == (uint32_t)FT_MATERIAL_CLOUD) {
                     stream = 1u + seg * nstreams;
@@ -393,7 +392,16 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
             } else if (event == 9) {
                 next_light = true;
             } else {  // a light is decided: 3 / 7 it contributes, 4 / 8 it does not
-                if (event == 3 || event == 7) lc = cloud_mode ? lc + cint : lc + cint * lcos;
+                if (event == 3 || event == 7) {  // the light's intensity (and cosine) again from its record: same inputs, same operations
+                    const float4 lv = ld4(S.lights + 2 * light), lrgb = ld4(S.lights + 2 * light + 1);
+                    const bool directional = __float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL;
+                    if (cloud_mode) {
+                        lc = lc + (directional ? xyz(lrgb) : xyz(lrgb) / length2(xyz(lv) - ps));
+                    } else {
+                        const float lcos = dot(n, directional ? xyz(lv) : normalize(xyz(lv) - q));
+                        lc = lc + (directional ? xyz(lrgb) : xyz(lrgb) / length2(xyz(lv) - q)) * lcos;
+                    }
+                }
                 add_flops<COUNT>(acc, 6);
                 light++;
                 next_light = true;
@@ -405,7 +413,6 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                     const bool directional = __float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL;
                     add_flops<COUNT>(acc, directional ? FLOPS_LIGHT : FLOPS_LIGHT + FLOPS_POINT_LIGHT);
                     if (cloud_mode) {  // isotropic scattering: every light, visibility by tracking
-                        cint = xyz(lrgb);
                         maxdist = __int_as_float(0x7f800000);
                         if (directional) {
                             d = xyz(lv);
@@ -414,7 +421,6 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                             const float d2 = length2(diff);
                             maxdist = sqrtf(d2);
                             d = diff / maxdist;
-                            cint = xyz(lrgb) / d2;
                         }
                         n_secondary++;
                         cloud_rnd(P, spare, pixel, (uint32_t)s, stream + 1u + (uint32_t)light, ucur, xi0);
@@ -424,19 +430,17 @@ __global__ void __launch_bounds__(CB, FT_CLOUD_MINB) cloud_kernel(const __grid_c
                         break;
                     }
                     const V3 ldir = directional ? xyz(lv) : normalize(xyz(lv) - q);  // SdfScene.fs:13-19
-                    lcos = dot(n, ldir);
+                    const float lcos = dot(n, ldir);
                     if (lcos > 0.0f) {
                         o = q;
                         if (directional) {
                             d = xyz(lv);
                             len = 1000.0f;
-                            cint = xyz(lrgb);
                         } else {
                             const V3 diff = xyz(lv) - q;
                             const float d2 = length2(diff);
                             len = sqrtf(d2);
                             d = diff / d2;
-                            cint = xyz(lrgb) / d2;
                         }
                         steps = 0;
                         n_secondary++;

@@ -200,8 +200,10 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
     int chunk_left = 0;
     bool exhausted = false;
 #endif
-    V3 o{0, 0, 0}, d{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, cint{0, 0, 0}, ho{0, 0, 0}, hd{0, 0, 0};
-    float len = 0.f, hlen = 0.f, lcos = 0.f, lcb[NB];
+    // (o, d, len) stay the un-moved hit ray from the hit until the material is known: the normal probes evaluate around q and
+    // leave them alone, so no copy of the hit ray is kept
+    V3 o{0, 0, 0}, d{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0};
+    float len = 0.f, lcb[NB];
     float sign = 1.0f;
     bool armed = true;
     int steps = 0, light = 0, inside = 0, band = 0, mat = 0;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 Continuation cont{V3{0, 0, 0}, V3{0, 0, 0}, 0.f, false};
                 if (parked) {
                     cont = glass_interact(xyz(ld4(S.materials + mat)), wavelength_nu((int)kk, P.nl), P.seed_lo, P.seed_hi, pixel, kk,
-                                          (uint32_t)P.wave, ho, hd, hlen, eps, n, inside);
+                                          (uint32_t)P.wave, o, d, len, eps, n, inside);
                     add_flops<COUNT>(acc, FLOPS_GLASS);
                 }
                 const unsigned idx = queue_slot(P, parked, cont.into_glass, lane);
@@ -244,8 +246,8 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 qbase = __shfl_sync(FULL, qbase, leader);
                 if (parked) {
                     const unsigned idx = qbase + (unsigned)__popc(pm & ((1u << lane) - 1u));
-                    P.hit_q[3ull * idx + 0] = float4{ho.x, ho.y, ho.z, hlen};
-                    P.hit_q[3ull * idx + 1] = float4{hd.x, hd.y, hd.z, __uint_as_float(pixel)};
+                    P.hit_q[3ull * idx + 0] = float4{o.x, o.y, o.z, len};
+                    P.hit_q[3ull * idx + 1] = float4{d.x, d.y, d.z, __uint_as_float(pixel)};
                     P.hit_q[3ull * idx + 2] = float4{n.x, n.y, n.z, __int_as_float(mat)};
                     phase = SP_FETCH;
                 }
@@ -474,16 +476,13 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 }
                 phase = SP_FETCH;
             } else if (event == 2) {  // hit: keep the un-moved hit ray, probe the normal
-                ho = o;
-                hd = d;
-                hlen = len;
                 inside = sign < 0.0f;
                 q = o + d * (-eps);
                 n_hits++;
                 phase = SP_N0;
             } else if (event == 5) {  // normal done: Material arg-min at the un-moved hit origin (SdfObject.fs:75-77)
-                const int leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, ho, hit_best)
-                                                                                  : material_leaf<COUNT>(S, ho, acc);
+                const int leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, o, hit_best)
+                                                                                  : material_leaf<COUNT>(S, o, acc);
                 mat = __ldg(S.objects + leaf_obj).z;
                 const float4 m = ld4(S.materials + mat);
                 if (__float_as_uint(m.w) == (uint32_t)FT_MATERIAL_GLASS) {
@@ -503,7 +502,7 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                         P.slots[slot] = 0.0f;  // interaction budget spent
                     } else {
                         cont = glass_interact(xyz(m), wavelength_nu((int)kk, P.nl), P.seed_lo, P.seed_hi, pixel, kk,
-                                              (uint32_t)P.wave, ho, hd, hlen, eps, n, inside);
+                                              (uint32_t)P.wave, o, d, len, eps, n, inside);
                         add_flops<COUNT>(acc, FLOPS_GLASS);
                         push = true;
                     }
@@ -518,6 +517,17 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 }
             } else {  // shadow ray finished
                 if (event == 3) {
+                    // the light's intensity and cosine are formed again from its record (same inputs, same operations as when
+                    // the shadow ray was set up) instead of being carried in four registers through the shadow march
+                    const float4 lv = ld4(S.lights + 2 * light), lrgb = ld4(S.lights + 2 * light + 1);
+                    V3 cint = xyz(lrgb);
+                    float lcos;
+                    if (__float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL) {
+                        lcos = dot(n, xyz(lv));
+                    } else {
+                        lcos = dot(n, normalize(xyz(lv) - q));
+                        cint = xyz(lrgb) / length2(xyz(lv) - q);
+                    }
 #pragma unroll
                     for (int b = 0; b < NB; b++) lcb[b] = lcb[b] + spec(cint, PRIMARY ? b : band) * lcos;
                     add_flops<COUNT>(acc, NB * (FLOPS_SPEC + 2));
@@ -531,14 +541,14 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                     const float4 lv = ld4(S.lights + 2 * light), lrgb = ld4(S.lights + 2 * light + 1);
                     const bool directional = __float_as_int(lv.w) == FT_LIGHT_DIRECTIONAL;
                     const V3 ldir = directional ? xyz(lv) : normalize(xyz(lv) - q);
-                    lcos = dot(n, ldir);
+                    const float lcos = dot(n, ldir);
                     add_flops<COUNT>(acc, FLOPS_LIGHT);
                     if (lcos > 0.0f) {
                         o = q;
+                        V3 cint = xyz(lrgb);
                         if (directional) {
                             d = xyz(lv);
                             len = 1000.0f;
-                            cint = xyz(lrgb);
                         } else {
                             const V3 diff = xyz(lv) - q;
                             const float d2 = length2(diff);
@@ -586,8 +596,8 @@ __global__ void __launch_bounds__(SB, FT_SPEC_MINB) spectral_trace_kernel(const 
                 base = __shfl_sync(FULL, base, leader);
                 if (push) {
                     const unsigned idx = base + (unsigned)__popc(pm & ((1u << lane) - 1u));
-                    P.hit_q[3ull * idx + 0] = float4{ho.x, ho.y, ho.z, hlen};
-                    P.hit_q[3ull * idx + 1] = float4{hd.x, hd.y, hd.z, __uint_as_float(pixel)};
+                    P.hit_q[3ull * idx + 0] = float4{o.x, o.y, o.z, len};
+                    P.hit_q[3ull * idx + 1] = float4{d.x, d.y, d.z, __uint_as_float(pixel)};
                     P.hit_q[3ull * idx + 2] = float4{n.x, n.y, n.z, __int_as_float(mat)};
                 }
             }
