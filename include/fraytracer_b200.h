@@ -294,7 +294,14 @@ FT_API int ft_scene_grid_read(const ft_scene *scene, int32_t grid, float *cell_c
  * are page-locked and device-mapped (ft_host_register on the pinned FColor[,],
  * or ft_host_alloc) the kernel stores every finished pixel straight into them
  * -- one launch, no staging buffer, no device->host copy; otherwise the frame
- * is rendered in two column bands whose copies overlap the rendering.        */
+ * is rendered in two column bands whose copies overlap the rendering.
+ * Scheduling memory: the handle remembers, per frame shape (size, strip
+ * partition, kind of destination), what every 4x8-pixel tile cost, and from the
+ * third frame of a shape on the tiles are drawn in an order ranked from those
+ * costs (most expensive first).  Pixels do not depend on it; it applies to
+ * ft_render, ft_render_device, ft_render_strips_device and
+ * ft_render_gather_device alike (FT_NO_TILE_HINT in the environment, or bit 2
+ * of ft_scene_set_debug, turns it off).                                       */
 FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
                      float epsilon, float length, uint32_t flags, float *out_rgb, int32_t *out_leaf,
                      ft_render_stats *stats);
