@@ -13,7 +13,10 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 which = os.environ.get("FT_EXP_WORKLOAD", "config2")
 w = bench.workload(which, world, which == "config5")
 tr = ft.SceneTracer(w.scene, device=local)
-r = DistributedRenderer(tr, w.size, gather="p2p")
+sw = int(os.environ.get("FT_EXP_STRIP", "0"))
+if sw < 0:  # one contiguous slab per rank
+    sw = -(-(-(-w.size.X // world)) // 4) * 4
+r = DistributedRenderer(tr, w.size, strip_width=sw or None, gather="p2p")
 r.host_frame()
 ts = []
 for it in range(16):
@@ -25,7 +28,7 @@ t = torch.tensor(sorted(ts[4:])[len(ts[4:]) // 2], dtype=torch.float64, device="
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     X, Y = w.size.X, w.size.Y
-    print(json.dumps({"n_gpus": world, "workload": w.name, "image": f"{X}x{Y}", "e2e_ms_median": 1e3 * float(t),
+    print(json.dumps({"n_gpus": world, "strip_width": r.strip_width, "workload": w.name, "image": f"{X}x{Y}", "e2e_ms_median": 1e3 * float(t),
                       "GB_per_s": X * Y * 12 / float(t) / 1e9,
                       "env": {k: v for k, v in os.environ.items() if k.startswith("FT_") and k != "FT_EXP_WORKLOAD"}}), flush=True)
 r.close(); tr.close()
