@@ -26,8 +26,8 @@ struct RenderParams {
     int xl_begin;        // first compact column (in the rank's strip space) this launch renders; out_rgb starts there
     float epsilon, length, max_size;
     // Scheduling hints (ft_api.cu TileHint; never used in arithmetic): `order` = the launch's tiles, most expensive first, as
-    // measured by the previous launch of the same shape on this scene (null: natural order); `cost` receives every tile's
-    // iteration count for the next launch (null: not recorded).
+    // measured by the previous launch of the same shape on this scene (null: natural order); `cost` receives the time
+    // the warp spent on every tile (SM clock, units of 64 cycles, saturating) for the later launches (null: not recorded).
     const unsigned *order;
     unsigned short *cost;
     int order_mode;      // 0: order[] as it is (most expensive first); 1: expensive and cheap units alternate (order[0], order[n-1],

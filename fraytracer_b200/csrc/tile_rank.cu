@@ -3,8 +3,8 @@
 //
 // A persistent grid hands out 4x8-pixel tiles from one counter; a tile is a serial chain of up to hundreds of Distance
 // evaluations and a warp gets only about a dozen tiles per frame, so in natural order the launch ends when the last long tile
-// does (ncu: sm__cycles_active.avg 82 % of elapsed on config 2).  Every launch records each tile's cost (loop iterations of the
-// warp that traced it); this file turns the costs of one frame into the order of a later frame of the same shape:
+// does (ncu: sm__cycles_active.avg 82 % of elapsed on config 2).  Every launch records each tile's cost (the SM clock time
+// its warp spent on it); this file turns the costs of one frame into the order of a later frame of the same shape:
 //
 //  * FT_RANK_LPT   -- device destinations: longest processing time first (a stable descending radix sort of the costs).
 //  * FT_RANK_TIMED -- destinations behind PCIe (mapped host memory): the launch is then also bound by the rate at which

@@ -140,8 +140,8 @@ struct RenderJobT {
     static constexpr bool kTileCost = true;
     __device__ __forceinline__ long long map_chunk(long long base) const { return hinted_chunk(P, base, n_items); }
     __device__ __forceinline__ long long draw_total() const { return hinted_total(P, n_items); }
-    __device__ __forceinline__ void note_cost(long long base, unsigned iters) const {
-        if (P.cost && base < n_items) P.cost[base >> 5] = (unsigned short)(iters < 65535u ? iters : 65535u);
+    __device__ __forceinline__ void note_cost(long long base, unsigned cost) const {
+        if (P.cost && base < n_items) P.cost[base >> 5] = (unsigned short)(cost < 65535u ? cost : 65535u);
     }
     static constexpr bool kTileStore = TILE;  // launch_render picks it for destinations behind PCIe (mapped host memory)
     __device__ __forceinline__ int *out_leaf_ptr() const { return out_leaf; }
@@ -222,8 +222,8 @@ struct GatherJob {
     static constexpr bool kTileCost = true;
     __device__ __forceinline__ long long map_chunk(long long base) const { return hinted_chunk(P, base, n_items); }
     __device__ __forceinline__ long long draw_total() const { return hinted_total(P, n_items); }
-    __device__ __forceinline__ void note_cost(long long base, unsigned iters) const {
-        if (P.cost && base < n_items) P.cost[base >> 5] = (unsigned short)(iters < 65535u ? iters : 65535u);
+    __device__ __forceinline__ void note_cost(long long base, unsigned cost) const {
+        if (P.cost && base < n_items) P.cost[base >> 5] = (unsigned short)(cost < 65535u ? cost : 65535u);
     }
     // see RenderJob::store_tile; the tile's four columns are consecutive image columns when the strip width is a multiple of 4
     static constexpr bool kTileStore = true;
@@ -336,7 +336,9 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     __shared__ __align__(16) float sh_tile[TILE_STORE ? MB / 32 : 1][TILE_STORE ? 96 : 4];
     float *const wtile = sh_tile[TILE_STORE ? (threadIdx.x >> 5) : 0];
     long long tile_base = -1;  // the chunk in flight (uniform): staged pixels, cost record
-    unsigned iters = 0u;       // loop iterations spent on it
+    unsigned tile_t0 = 0u;     // SM clock when it was drawn: its cost is the time the warp spent on it, in units of 64 cycles
+                               // (a loop-iteration counter was kept first: one more value incremented -- and spilled -- in every
+                               // iteration of the march loop; the clock is read twice per tile)
     bool has_pix = false;
     __shared__ unsigned sh_stats[MB / 32][4];
     unsigned *const wstats = sh_stats[threadIdx.x >> 5];
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                         __syncwarp();
                         has_pix = false;
                     }
-                    if (Job::kTileCost && lane == 0) job.note_cost(tile_base, iters);
+                    if (Job::kTileCost && lane == 0) job.note_cost(tile_base, ((unsigned)clock() - tile_t0) >> 6);
                     tile_base = -1;
                 }
                 while (idle) {
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                         chunk_next = job.map_chunk((long long)base);
                         chunk_left = FT_CHUNK;
                         if (TILE_STORE || Job::kTileCost) tile_base = chunk_next;
-                        iters = 0u;
+                        if (Job::kTileCost) tile_t0 = (unsigned)clock();
                     }
                     const int want = __popc(idle), take = want < chunk_left ? want : chunk_left;
                     const int r = __popc(idle & ((1u << lane) - 1u));
@@ -399,7 +401,6 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                 }
             }
         }
-        iters++;
         // ------------------------------------------------------------------ march pre-check (SdfForm.fs:94)
         // a ray whose Length is exhausted (or that hit the watchdog) ends as a miss without another evaluation
         int event = 0;  // 1 primary miss, 2 primary hit, 3 shadow finished (miss), 4 shadow finished (hit), 5 normal done
