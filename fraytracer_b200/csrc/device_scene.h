@@ -114,6 +114,7 @@ struct DevScene {
     // Positions inside the covered region evaluate only these (eval_chain); the result is certified equal to the reference's
     // sequential scan, otherwise the scan itself runs.  sub_valid == 0: no sub-grid (the scan always runs).
     const uint2 *sub_hdr;
+    const uint2 *sub_hdr_biased;  // sub_hdr + ((sub_off * sub_ny + sub_off) * sub_nz + sub_off): indexed by floor(c * sub_scale) directly
     const uint32_t *sub_idx;
     int32_t sub_valid;
     int32_t sub_shift;      // log2(sub-cells per cell and axis): 0 .. 3
@@ -126,8 +127,9 @@ struct DevScene {
     // the evaluator needs no further coverage test and the ray machine no escape pre-check (trace_device.cuh in_fast_region);
     // empty (lo = +inf) without a sub-grid.  Scheduling only: every position outside it takes the complete tests.
     float fast_lo[3], fast_hi[3];
-    int32_t sub_debug;      // bit 0: distrust every certificate (every evaluation also runs the sequential scan; tests)
-                            // bit 1: COUNT kernels compare the certified result with the scan and count mismatches
+    int32_t sub_debug;      // bit 0: distrust every certificate -- every evaluation runs the reference's sequential scan (tests).
+                            // Applied on the host (ft_scene_set_debug detaches the sub-grid: sub_valid = 0, empty fast region),
+                            // so the kernels carry no test for it
 };
 enum : uint32_t {
     FT_OP_INTERSECT = 1,  // if v < dist(C,p)+R then v = Max(v, D(p))      SdfForm.fs:62-63

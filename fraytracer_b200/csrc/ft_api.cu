@@ -115,6 +115,18 @@ struct ft_scene {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long *d_stats = nullptr, *h_stats = nullptr;
+    // sub_debug bit 0 ("distrust every certificate", tests): the sub-grid is detached from the kernel parameters, so every
+    // evaluation runs the reference's sequential scan; the built state is kept to re-attach it
+    int32_t sub_valid_built = 0;
+    float fast_lo_built[3] = {0.f, 0.f, 0.f}, fast_hi_built[3] = {0.f, 0.f, 0.f};
+    void apply_sub_debug() {
+        const bool detach = (dev.sub_debug & 1) != 0;
+        dev.sub_valid = detach ? 0 : sub_valid_built;
+        for (int k = 0; k < 3; k++) {
+            dev.fast_lo[k] = detach ? std::numeric_limits<float>::infinity() : fast_lo_built[k];
+            dev.fast_hi[k] = detach ? -std::numeric_limits<float>::infinity() : fast_hi_built[k];
+        }
+    }
     // ring of work counters for the persistent kernels: every launch zeroes and uses the next one, so that
     // launches in flight on different streams never share a counter
     unsigned long long *d_counters = nullptr;
@@ -737,6 +749,10 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
             }
             if (s->sub.hdr) {
                 s->dev.sub_hdr = s->sub.hdr;
+                {
+                    const long long off = (long long)s->sub.halo << s->sub.shift;
+                    s->dev.sub_hdr_biased = s->sub.hdr + ((off * s->sub.ny + off) * s->sub.nz + off);
+                }
                 s->dev.sub_idx = s->sub.idx;
                 s->dev.sub_shift = s->sub.shift;
                 s->dev.sub_off = s->sub.halo << s->sub.shift;
@@ -774,6 +790,12 @@ FT_API int ft_scene_create(const ft_scene_desc *desc, int device, ft_scene **out
         s->dev.fast_lo[k] = lo;
         s->dev.fast_hi[k] = hi;
     }
+    s->sub_valid_built = s->dev.sub_valid;
+    for (int k = 0; k < 3; k++) {
+        s->fast_lo_built[k] = s->dev.fast_lo[k];
+        s->fast_hi_built[k] = s->dev.fast_hi[k];
+    }
+    s->apply_sub_debug();
     if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->hint_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
@@ -835,6 +857,7 @@ FT_API int ft_scene_set_debug(ft_scene *scene, int32_t sub_debug) {
     if (!scene) return fail(FT_ERR_INVALID_ARGUMENT, "null argument");
     std::lock_guard<std::mutex> lock(scene->mu);
     scene->dev.sub_debug = sub_debug & 3;
+    scene->apply_sub_debug();
     scene->hints_enabled = (sub_debug & 4) == 0 && getenv("FT_NO_TILE_HINT") == nullptr;  // bit 2: natural tile order, no hints
     scene->ext_count = (sub_debug & 8) != 0;  // bit 3: the extension entry points run their instrumented kernels (eval_flops, march_steps)
     return FT_OK;

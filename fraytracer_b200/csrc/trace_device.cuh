@@ -48,6 +48,19 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #ifndef FT_WITH_CONE
 #define FT_WITH_CONE 0
 #endif
+// sub_lookup, round 2 (each measured on B200, config 2):
+#ifndef FT_SUB_BIASED
+#define FT_SUB_BIASED 1  // the halo offset of the three fine-cell coordinates is folded into the header pointer on the host
+#endif
+#ifndef FT_SUB_IDX_WALK
+#define FT_SUB_IDX_WALK 1  // the candidate list is walked by a 32-bit position (two instructions and a register less per candidate)
+#endif
+#ifndef FT_SUB_TIE_FALLBACK
+#define FT_SUB_TIE_FALLBACK 1  // exact ties between candidates go to the sequential scan instead of being resolved by index
+#endif
+#ifndef FT_SUB_DEBUG_IN_KERNEL
+#define FT_SUB_DEBUG_IN_KERNEL 0  // 1: the kernel itself tests DevScene::sub_debug after every certified evaluation
+#endif
 #ifndef FT_INLINE_PRIM
 #define FT_INLINE_PRIM 0  // 1: primitives met by the candidate scan are evaluated inside the scan loop
 #endif
@@ -440,17 +453,31 @@ template <bool COUNT>
 __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int gy, int gz, float &m_out, uint32_t &best_out,
                                            Acc &acc) {
     // header: {(first << 8) | count, the nearest candidate}: the first record's load depends on one load only
+#if FT_SUB_BIASED
+    // `g` without the halo offset: the header pointer is biased by it on the host (DevScene::sub_hdr_biased)
+    const uint2 hdr = __ldg(S.sub_hdr_biased + ((gx * S.sub_ny + gy) * S.sub_nz + gz));
+#else
     const uint2 hdr = __ldg(S.sub_hdr + (uint32_t)((gx * S.sub_ny + gy) * S.sub_nz + gz));
+#endif
     const uint32_t n = hdr.x & 255u;
     if (n == 0u) return false;  // no list for this sub-cell (too long to encode): the scan runs
     add_flops<COUNT>(acc, 9);
-    const uint32_t *lp = S.sub_idx + (hdr.x >> 8);  // candidates 1 .. n-1
     float M = __int_as_float(0x7f800000);
     uint32_t best = 0xffffffffu;
     uint32_t idx = hdr.y & 0xffffffu;
+#if FT_SUB_IDX_WALK
+    // candidates 1 .. n-1 by position in sub_idx (a 32-bit cursor and its end instead of a 64-bit pointer and a counter)
+    uint32_t pos = hdr.x >> 8;
+    const uint32_t end = pos + n - 1u;
+    for (;;) {
+#else
+    const uint32_t *lp = S.sub_idx + (hdr.x >> 8);  // candidates 1 .. n-1
     for (uint32_t k = 0;;) {
+#endif
         const Entry e = ld_entry(S, idx);
+#if !FT_SUB_IDX_WALK
         const bool more = ++k < n;
+#endif
         add_flops<COUNT>(acc, FLOPS_BOUND_TEST);
         if (!certain_fail_up(M, e.bound(), e.b.w, p)) {
             float d;
@@ -460,13 +487,35 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
                 d = prim_distance<COUNT>(S, e.word(), e.bound(), p, acc);
             }
             add_flops<COUNT>(acc, FLOPS_MINMAX);
+#if FT_SUB_TIE_FALLBACK
+            // an exact tie at the running minimum (the arg-min would be the smaller index) invalidates `best` until a strictly
+            // smaller Distance turns up: a tie that survives leaves the evaluation to the scan
+            if (d <= M) {
+                best = d < M ? idx : 0xffffffffu;
+                M = d;
+            }
+#else
             if (d < M || (d == M && idx < best)) {
                 M = d;
                 best = idx;
             }
+#endif
         }
+#if FT_SUB_IDX_WALK
+        if (pos == end) break;
+        // (the address is formed in inline PTX: the compiler otherwise turns the cursor back into a 64-bit pointer and a counter)
+        asm("{\n\t"
+            ".reg .u64 a;\n\t"
+            "mad.wide.u32 a, %1, 4, %2;\n\t"
+            "ld.global.nc.u32 %0, [a];\n\t"
+            "}"
+            : "=r"(idx)
+            : "r"(pos), "l"(S.sub_idx));
+        pos++;
+#else
         if (!more) break;
         idx = __ldg(lp + k - 1u);  // (prefetching it one candidate ahead costs a register: measured 0.792 -> 0.821 ms)
+#endif
     }
     if (best == 0xffffffffu) return false;  // nothing comparable (NaN positions): the scan decides
     // certificates on the arg-min
@@ -497,7 +546,11 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
         const float y = M + b0.w;
         if (!(y > 0.0f && sf < (y * y) * 0.9999847412109375f)) ok = ok && (M >= sqrtf(dot(dl, dl)) - b0.w);
     }
+#if FT_SUB_DEBUG_IN_KERNEL
     if (!ok || (S.sub_debug & 1)) return false;
+#else
+    if (!ok) return false;  // ("distrust every certificate", sub_debug bit 0, is applied by the host: it detaches the sub-grid)
+#endif
     m_out = M;
     best_out = best;
     return true;
@@ -518,9 +571,14 @@ __device__ __forceinline__ float eval_chain_c(const DevScene &S, V3 p, V3 c, boo
                      c.y < S.sub_hi[1] && c.z < S.sub_hi[2])) {
             uint32_t best = 0u;
             float ms = 0.f;
+#if FT_SUB_BIASED
+            certified = sub_lookup<COUNT>(S, p, __float2int_rd(c.x * S.sub_scale), __float2int_rd(c.y * S.sub_scale),
+                                          __float2int_rd(c.z * S.sub_scale), ms, best, acc);
+#else
             certified = sub_lookup<COUNT>(S, p, __float2int_rd(c.x * S.sub_scale) + S.sub_off,
                                           __float2int_rd(c.y * S.sub_scale) + S.sub_off,
                                           __float2int_rd(c.z * S.sub_scale) + S.sub_off, ms, best, acc);
+#endif
             if (certified) {
                 m = ms;
 #if FT_CHAIN_MAT

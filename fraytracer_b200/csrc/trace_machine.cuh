@@ -40,6 +40,31 @@ constexpr int MB = 128;             // threads per CTA
 #define FT_REFILL_MIN 32  // idle lanes that trigger a refill (see the refill block of machine_kernel)
 #endif
 constexpr int FT_CHUNK = 32;        // work items per global-counter grab (one tile of 4x8 pixels)
+#ifndef FT_LAZY_WSTATS
+#define FT_LAZY_WSTATS 1  // the address of the warp's event counters is formed inside the rare branch that bumps one (volatile asm
+                          // reading %tid.x cannot be hoisted): ptxas otherwise rematerialises it -- S2R, S2R, SHF, LEA, LOP3, IADD3 --
+                          // at the head of the march pre-check of EVERY iteration (1.6 % of the warp instructions, ncu r03z)
+#endif
+
+// one of the warp's four event counters (hits, shadow rays, capped rays, rays ended by the escape proof) in shared memory
+__device__ __forceinline__ void warp_event(unsigned *wstats, unsigned sh_base, int k) {
+#if FT_LAZY_WSTATS
+    (void)wstats;
+    asm volatile(
+        "{\n\t"
+        ".reg .u32 t;\n\t"
+        "mov.u32 t, %%tid.x;\n\t"
+        "shr.u32 t, t, 5;\n\t"
+        "shl.b32 t, t, 4;\n\t"
+        "add.u32 t, t, %0;\n\t"
+        "red.shared.add.u32 [t], 1;\n\t"
+        "}" ::"r"(sh_base + 4u * (unsigned)k)
+        : "memory");
+#else
+    (void)sh_base;
+    atomicAdd(wstats + k, 1u);
+#endif
+}
 
 enum : int {
     PH_DONE = -1,
@@ -342,6 +367,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     bool has_pix = false;
     __shared__ unsigned sh_stats[MB / 32][4];
     unsigned *const wstats = sh_stats[threadIdx.x >> 5];
+    const unsigned sh_stats_base = (unsigned)__cvta_generic_to_shared(&sh_stats[0][0]);
     if (lane < 4) wstats[lane] = 0u;
     __syncwarp();
     Acc acc{0ull, 0ull};
@@ -420,10 +446,10 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         const bool fast = CHAIN && in_fast_region(S, cc);
         if (phase == PH_PRIMARY || phase == PH_SHADOW) {
             if (len <= 0.0f || steps >= S.step_cap) {
-                if (!(len <= 0.0f)) atomicAdd(wstats + 2, 1u);
+                if (!(len <= 0.0f)) warp_event(wstats, sh_stats_base, 2);
                 event = phase == PH_PRIMARY ? 1 : 3;
             } else if (ESCAPE && S.esc_valid && !fast && outside_box(S.esc_lo, S.esc_hi, o) && ray_escapes(S, o, d, FT_EPS)) {
-                atomicAdd(wstats + 3, 1u);
+                warp_event(wstats, sh_stats_base, 3);
                 event = phase == PH_PRIMARY ? 1 : 3;
             }
         }
@@ -491,7 +517,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                 finish = true;
             } else if (event == 2) {  // primary hit: SdfObject.fs:70-73
                 primary_steps = steps;
-                atomicAdd(wstats + 0, 1u);
+                warp_event(wstats, sh_stats_base, 0);
                 q = o + d * (-FT_EPS);  // Ray.get (-epsilon): the normal's probe point and result.Ray's origin
                 phase = PH_N0;
             } else if (event == 5) {
@@ -542,7 +568,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                             add_flops<COUNT>(acc, FLOPS_POINT_LIGHT);
                         }
                         steps = 0;
-                        atomicAdd(wstats + 1, 1u);
+                        warp_event(wstats, sh_stats_base, 1);
                         phase = PH_SHADOW;
                         finish = false;
                         break;

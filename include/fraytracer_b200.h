@@ -269,8 +269,9 @@ FT_API int ft_scene_set_step_cap(ft_scene *scene, int32_t max_steps);
 
 FT_API int ft_scene_subgrid_info(const ft_scene *scene, ft_subgrid_info *out);
 /* test / measurement hook: bit 0 of `sub_debug` makes the device path distrust
- * every sub-grid certificate, so that every Distance evaluation also runs the
- * reference's sequential candidate scan (SdfForm.fs:27-33); bit 2 draws tiles in
+ * every sub-grid certificate: the sub-grid is detached from the kernel parameters
+ * and every Distance evaluation of this handle runs the reference's sequential
+ * candidate scan (SdfForm.fs:27-33) until the bit is cleared; bit 2 draws tiles in
  * natural order (no scheduling hints); results must not change.  Bit 3 makes the
  * extension entry points (ft_render_spectral, ft_render_cloud) run their
  * instrumented kernels: ft_render_stats.eval_flops / march_steps are filled     */

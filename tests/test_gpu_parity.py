@@ -436,8 +436,9 @@ def test_extension_strip_rendering_equals_whole_frame():
                                   lambda: scenes.mixed_scene(width=256, height=144)])
 def test_subgrid_certified_path_equals_sequential_scan(make, monkeypatch):
     """The nearest-candidate sub-grid (DESIGN.md "sub-grid") against the reference's sequential candidate scan
-    (SdfForm.fs:27-33) on the same device: (a) sub-grid off, (b) sub-grid on, (c) sub-grid on with every certificate
-    distrusted, so that every evaluation runs the sub-grid path AND the scan -- frames, leaf ids, per-ray step counts and
+    (SdfForm.fs:27-33) on the same device: (a) sub-grid off, (b) sub-grid on, (c) sub-grid built but detached by
+    ft_scene_set_debug bit 0 ("distrust every certificate": the host clears sub_valid and the fast region in the kernel
+    parameters, so every evaluation of the same handle runs the scan) -- frames, leaf ids, per-ray step counts and
     Distance values must be identical bit for bit; (b) must also equal the oracle."""
     w = make()
     X, Y = w.size.X, w.size.Y
