@@ -127,6 +127,10 @@ struct DevScene {
     // the evaluator needs no further coverage test and the ray machine no escape pre-check (trace_device.cuh in_fast_region);
     // empty (lo = +inf) without a sub-grid.  Scheduling only: every position outside it takes the complete tests.
     float fast_lo[3], fast_hi[3];
+    // the same in fine-cell units (times sub_scale), and cellSizeInv * sub_scale: the ray machine's per-iteration box test and
+    // the fine-cell index work on  f = (p - aabbMin) * chain_g2s  directly (trace_device.cuh chain_coord)
+    float fast_lo_s[3], fast_hi_s[3];
+    float4 chain_g2s;
     int32_t sub_debug;      // bit 0: distrust every certificate -- every evaluation runs the reference's sequential scan (tests).
                             // Applied on the host (ft_scene_set_debug detaches the sub-grid: sub_valid = 0, empty fast region),
                             // so the kernels carry no test for it

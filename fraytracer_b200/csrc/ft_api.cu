@@ -126,6 +126,13 @@ struct ft_scene {
             dev.fast_lo[k] = detach ? std::numeric_limits<float>::infinity() : fast_lo_built[k];
             dev.fast_hi[k] = detach ? -std::numeric_limits<float>::infinity() : fast_hi_built[k];
         }
+        // fine-cell units (DevScene::chain_g2s): exact scalings by a power of two
+        const float scale = dev.sub_valid ? dev.sub_scale : 1.0f;
+        dev.chain_g2s = float4{dev.chain_g2.x * scale, dev.chain_g2.y * scale, dev.chain_g2.z * scale, 0.f};
+        for (int k = 0; k < 3; k++) {
+            dev.fast_lo_s[k] = dev.fast_lo[k] * scale;
+            dev.fast_hi_s[k] = dev.fast_hi[k] * scale;
+        }
     }
     // ring of work counters for the persistent kernels: every launch zeroes and uses the next one, so that
     // launches in flight on different streams never share a counter

@@ -58,6 +58,12 @@ constexpr int FLOPS_PRIMARY_RAY = 25; // Camera.uniformPixelToRay
 #ifndef FT_SUB_TIE_FALLBACK
 #define FT_SUB_TIE_FALLBACK 1  // exact ties between candidates go to the sequential scan instead of being resolved by index
 #endif
+#ifndef FT_SUB_PRESCALED
+#define FT_SUB_PRESCALED 1  // the ray machine hands the evaluator the fine-cell coordinate (see chain_coord)
+#endif
+#ifndef FT_SUB_EARLY_RETURN
+#define FT_SUB_EARLY_RETURN 1  // a failed certificate leaves sub_lookup at once (no boolean carried in a register to the end)
+#endif
 #ifndef FT_SUB_DEBUG_IN_KERNEL
 #define FT_SUB_DEBUG_IN_KERNEL 0  // 1: the kernel itself tests DevScene::sub_debug after every certified evaluation
 #endif
@@ -442,11 +448,25 @@ __device__ __forceinline__ bool certain_fail_up(float M, float4 b0, float rup, V
 // bank), and whether it lies in the "fast region" -- the sub-grid's covered region clipped to the escape box (DevScene::fast_lo).
 // One box test serves two decisions there: the evaluator goes straight to the sub-grid, and the ray machine skips the escape
 // pre-check (a position inside the escape box cannot pass it).
-__device__ __forceinline__ V3 chain_coord(const DevScene &S, V3 p) { return (p - xyz(S.chain_g1)) * xyz(S.chain_g2); }
+// FT_SUB_PRESCALED: the coordinate handed from the ray machine to the evaluator is the FINE-cell coordinate
+// f = (p - aabbMin) * (cellSizeInv * sub_scale) = c * sub_scale bit for bit (sub_scale is a power of two: scaling commutes with
+// the rounding of the product, underflow aside -- and a product that underflows lies within 1e-37 of the box's min face, where
+// either neighbouring fine cell draws from the same reference cell with a margin of millimetres), so the fast path needs
+// neither c nor the multiplication by sub_scale; the fast region is kept in the same units.  The cold paths form c themselves.
+__device__ __forceinline__ V3 cell_coord(const DevScene &S, V3 p) { return (p - xyz(S.chain_g1)) * xyz(S.chain_g2); }
+#if FT_SUB_PRESCALED
+__device__ __forceinline__ V3 chain_coord(const DevScene &S, V3 p) { return (p - xyz(S.chain_g1)) * xyz(S.chain_g2s); }
+__device__ __forceinline__ bool in_fast_region(const DevScene &S, V3 f) {
+    return f.x >= S.fast_lo_s[0] && f.y >= S.fast_lo_s[1] && f.z >= S.fast_lo_s[2] && f.x < S.fast_hi_s[0] &&
+           f.y < S.fast_hi_s[1] && f.z < S.fast_hi_s[2];
+}
+#else
+__device__ __forceinline__ V3 chain_coord(const DevScene &S, V3 p) { return cell_coord(S, p); }
 __device__ __forceinline__ bool in_fast_region(const DevScene &S, V3 c) {
     return c.x >= S.fast_lo[0] && c.y >= S.fast_lo[1] && c.z >= S.fast_lo[2] && c.x < S.fast_hi[0] && c.y < S.fast_hi[1] &&
            c.z < S.fast_hi[2];
 }
+#endif
 
 // `g` = the fine-cell coordinates of p (see DevScene): the caller has checked that p lies in the covered region
 template <bool COUNT>
@@ -522,7 +542,9 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     const Entry eb = ld_entry(S, best);
     add_flops<COUNT>(acc, 12);
     const float x = eb.lb() - M;
+#if !FT_SUB_EARLY_RETURN
     bool ok = true;
+#endif
     // (1)  M >= fl(lb - dtc).  Certainly true when x = fl(lb - M) <= dq, dq = the header's lower bound of dtc over the whole fine
     // cell (rounded down to its 8-bit quantum and lowered by one more, which dwarfs the roundings of x, dtc and the
     // difference): lb - dtc <= lb - dq <= M.  The comparison runs on 1 + x / (256 quanta) against the float whose top mantissa
@@ -530,35 +552,48 @@ __device__ __forceinline__ bool sub_lookup(const DevScene &S, V3 p, int gx, int 
     if (__fmaf_rn(x, S.sub_dtc_inv, 1.0f) > __uint_as_float(0x3f800000u | ((hdr.y >> 24) << 15))) {
         // the reference's cell, clamp(floor(c)) per axis (SdfBoundary.fs:276-282), from the position again rather than from the
         // fine-cell coordinates: those need not stay live across the candidate loop (three registers where the kernel spills)
-        const V3 c = chain_coord(S, p);
+        const V3 c = cell_coord(S, p);
         const int mx = __float_as_int(S.chain_g3.x), my = __float_as_int(S.chain_g3.y), mz = __float_as_int(S.chain_g3.z);
         const int ix = cell_index(c.x, mx), iy = cell_index(c.y, my), iz = cell_index(c.z, mz);
         const float4 cell = ld4(S.cells + (__float_as_uint(S.chain_g1.w) +
                                            (uint32_t)(ix * __float_as_int(S.chain_g3.w) + iy * (mz + 1) + iz)));
         const V3 dc = p - xyz(cell);
         const float dtc2 = __fmaf_rn(dc.z, dc.z, __fmaf_rn(dc.y, dc.y, dc.x * dc.x));
+#if FT_SUB_EARLY_RETURN
+        if (!(dtc2 > (x * x) * 1.0009765625f) && !(M >= eb.lb() - distance(p, xyz(cell)))) return false;
+#else
         if (!(dtc2 > (x * x) * 1.0009765625f)) ok = M >= eb.lb() - distance(p, xyz(cell));
+#endif
     }
     if (FT_WORD_KIND(eb.word()) != FT_K_SPHERE) {  // (2)  M >= bd: certainly true when s < (M + R)^2 (1 - 2^-16), M + R > 0
         const float4 b0 = eb.bound();
         const V3 dl = xyz(b0) - p;
         const float sf = __fmaf_rn(dl.z, dl.z, __fmaf_rn(dl.y, dl.y, dl.x * dl.x));
         const float y = M + b0.w;
+#if FT_SUB_EARLY_RETURN
+        if (!(y > 0.0f && sf < (y * y) * 0.9999847412109375f) && !(M >= sqrtf(dot(dl, dl)) - b0.w)) return false;
+#else
         if (!(y > 0.0f && sf < (y * y) * 0.9999847412109375f)) ok = ok && (M >= sqrtf(dot(dl, dl)) - b0.w);
+#endif
     }
+    // ("distrust every certificate", sub_debug bit 0, is applied by the host: it detaches the sub-grid)
+#if FT_SUB_EARLY_RETURN
 #if FT_SUB_DEBUG_IN_KERNEL
+    if (S.sub_debug & 1) return false;
+#endif
+#elif FT_SUB_DEBUG_IN_KERNEL
     if (!ok || (S.sub_debug & 1)) return false;
 #else
-    if (!ok) return false;  // ("distrust every certificate", sub_debug bit 0, is applied by the host: it detaches the sub-grid)
+    if (!ok) return false;
 #endif
     m_out = M;
     best_out = best;
     return true;
 }
 
-// `c` = chain_coord(S, p), `fast` = in_fast_region(S, c)
+// `cf` = chain_coord(S, p), `fast` = in_fast_region(S, cf)
 template <bool COUNT>
-__device__ __forceinline__ float eval_chain_c(const DevScene &S, V3 p, V3 c, bool fast, Acc &acc, uint32_t &best_lo) {
+__device__ __forceinline__ float eval_chain_c(const DevScene &S, V3 p, V3 cf, bool fast, Acc &acc, uint32_t &best_lo) {
     uint32_t i;
     float dtc;
     add_flops<COUNT>(acc, FLOPS_CELL_LOOKUP);
@@ -567,6 +602,20 @@ __device__ __forceinline__ float eval_chain_c(const DevScene &S, V3 p, V3 c, boo
     {
         // SdfBoundary.fs:276-282 with U's header from the constant bank (see grid_cell_from)
         const float4 g1 = S.chain_g1, g3 = S.chain_g3;
+#if FT_SUB_PRESCALED
+        bool covered = fast;
+        if (!fast) {
+            const V3 c = cell_coord(S, p);  // the reference's cell coordinate: formed only off the fast path
+            covered = S.sub_valid && c.x >= S.sub_lo[0] && c.y >= S.sub_lo[1] && c.z >= S.sub_lo[2] && c.x < S.sub_hi[0] &&
+                      c.y < S.sub_hi[1] && c.z < S.sub_hi[2];
+        }
+        if (covered) {
+            uint32_t best = 0u;
+            float ms = 0.f;
+            static_assert(FT_SUB_BIASED, "FT_SUB_PRESCALED needs the biased header pointer");
+            certified = sub_lookup<COUNT>(S, p, __float2int_rd(cf.x), __float2int_rd(cf.y), __float2int_rd(cf.z), ms, best, acc);
+#else
+        const V3 c = cf;
         if (fast || (S.sub_valid && c.x >= S.sub_lo[0] && c.y >= S.sub_lo[1] && c.z >= S.sub_lo[2] && c.x < S.sub_hi[0] &&
                      c.y < S.sub_hi[1] && c.z < S.sub_hi[2])) {
             uint32_t best = 0u;
@@ -579,6 +628,7 @@ __device__ __forceinline__ float eval_chain_c(const DevScene &S, V3 p, V3 c, boo
                                           __float2int_rd(c.y * S.sub_scale) + S.sub_off,
                                           __float2int_rd(c.z * S.sub_scale) + S.sub_off, ms, best, acc);
 #endif
+#endif
             if (certified) {
                 m = ms;
 #if FT_CHAIN_MAT
@@ -587,6 +637,9 @@ __device__ __forceinline__ float eval_chain_c(const DevScene &S, V3 p, V3 c, boo
             }
         }
         if (!certified) {
+#if FT_SUB_PRESCALED
+            const V3 c = cell_coord(S, p);
+#endif
             const int mx = __float_as_int(g3.x), my = __float_as_int(g3.y), mz = __float_as_int(g3.z);
             const int ix = cell_index(c.x, mx), iy = cell_index(c.y, my), iz = cell_index(c.z, mz);
             const uint32_t ci = __float_as_uint(g1.w) + (uint32_t)(ix * __float_as_int(g3.w) + iy * (mz + 1) + iz);

@@ -345,10 +345,17 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     int phase = Job::kProbe ? PH_PROBE : PH_FETCH;
     float d0 = 0.f;
     typename Job::slot_t slot = 0;
-    V3 o{0, 0, 0}, d{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, lc{0, 0, 0};
+    // `o` is ALWAYS the next evaluation point: the marching ray's origin, a normal probe point (the hit's leaf object is
+    // resolved when the hit is detected, so the un-moved hit origin is not needed afterwards), or the job's probe point.
+    // (A separate evaluation point `p` -- a copy of `o` or of a probe point, chosen at the head of every iteration -- cost
+    // eleven instructions per iteration and three more live registers across the evaluator.)
+    V3 o = Job::kProbe ? job.probe_point() : V3{0, 0, 0};
+    V3 d{0, 0, 0}, q{0, 0, 0}, n{0, 0, 0}, lc{0, 0, 0};
     float len = 0.f, eps_lane = 1.f;  // per-ray Epsilon (RaysJob); render jobs use the uniform one
 #define FT_EPS (Job::kUniformEps ? job.uniform_eps() : eps_lane)
     int steps = 0, primary_steps = 0, light = 0, leaf_obj = 0;
+    // (measured and rejected: the leaf object, 27 bits, and the light counter, 5 bits, packed into one register between
+    // iterations -- config 2 0.717 -> 0.727 ms, config 5 4K 2.473 -> 2.500; ptxas spills the same hot values either way)
     unsigned shadow_mask = 0;
     // the warp's current chunk (uniform)
     long long chunk_next = 0;
@@ -430,17 +437,9 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         // ------------------------------------------------------------------ march pre-check (SdfForm.fs:94)
         // a ray whose Length is exhausted (or that hit the watchdog) ends as a miss without another evaluation
         int event = 0;  // 1 primary miss, 2 primary hit, 3 shadow finished (miss), 4 shadow finished (hit), 5 normal done
-        // the evaluation point
-        V3 p = o;
-        if (Job::kProbe && phase == PH_PROBE) {
-            p = job.probe_point();
-        } else if (phase >= PH_N0) {
-            const float h = FT_EPS * 0.125f;  // SdfForm.fs:115
-            p = q;
-            if (phase == PH_N0) p.x = q.x + h;
-            else if (phase == PH_N1) p.y = q.y + h;
-            else if (phase == PH_N2) p.z = q.z + h;
-        }
+        uint32_t best_lo_hit = 0u;  // event 2: the arg-min candidate of the evaluation that detected the hit
+        // the evaluation point is `o` in every phase (see the lane state)
+        const V3 p = o;
         // chain scenes: one box test on the cell coordinate decides both "no escape pre-check" and "straight to the sub-grid"
         const V3 cc = CHAIN ? chain_coord(S, p) : V3{0.f, 0.f, 0.f};
         const bool fast = CHAIN && in_fast_region(S, cc);
@@ -468,7 +467,7 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
         if (wants) {
 #endif
             const unsigned long long f0 = acc.flops;
-            uint32_t best_lo = 0u;
+            uint32_t best_lo = 0u;  // the arg-min candidate of this evaluation (chain scenes)
             const float dist = CHAIN ? eval_chain_c<COUNT>(S, p, cc, fast, acc, best_lo) : eval_form<COUNT>(S, S.root_word, p, acc);
             if (COUNT) {
                 acc.evals++;
@@ -477,12 +476,12 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
                     acc.long_evals++;
                 }
             }
+            best_lo_hit = best_lo;
             if (phase <= PH_SHADOW) {  // SdfForm.fs:97-104
                 steps++;
                 if (COUNT) acc.steps++;
                 if (dist < FT_EPS) {
-                    event = phase == PH_PRIMARY ? 2 : 4;
-                    if (FT_CHAIN_MAT && CHAIN && phase == PH_PRIMARY) leaf_obj = (int)best_lo;  // the hit evaluation's arg-min candidate (event 5)
+                    event = phase == PH_PRIMARY ? 2 : 4;  // (a primary hit resolves its leaf object from `best_lo` below)
                 } else {
                     o = o + d * dist;  // Ray.move
                     len = len - dist;
@@ -491,14 +490,19 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
             } else if (Job::kProbe && phase == PH_PROBE) {
                 d0 = dist;
                 phase = PH_FETCH;
-            } else if (phase == PH_N0) {
+            } else if (phase == PH_N0) {  // the probe points of SdfForm.fs:107-112: q + h e_x, q + h e_y, q + h e_z, q
                 n.x = dist;
+                o.x = q.x;
+                o.y = q.y + FT_EPS * 0.125f;
                 phase = PH_N1;
             } else if (phase == PH_N1) {
                 n.y = dist;
+                o.y = q.y;
+                o.z = q.z + FT_EPS * 0.125f;
                 phase = PH_N2;
             } else if (phase == PH_N2) {
                 n.z = dist;
+                o.z = q.z;
                 phase = PH_N3;
             } else {
                 n = normalize(n - V3{dist, dist, dist});  // SdfForm.fs:107-112
@@ -518,12 +522,16 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
             } else if (event == 2) {  // primary hit: SdfObject.fs:70-73
                 primary_steps = steps;
                 warp_event(wstats, sh_stats_base, 0);
+                // Material.Color at the un-moved hit origin `o` (SdfObject.fs:75-77): the leaf object is resolved here, before
+                // the normal (the reference takes the normal first, SdfObject.fs:70-77; both are pure functions of the hit), from
+                // the arg-min candidate of the evaluation that detected the hit or by the arg-min scan
+                leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, o, best_lo_hit)
+                                                                         : material_leaf<COUNT>(S, o, acc);
                 q = o + d * (-FT_EPS);  // Ray.get (-epsilon): the normal's probe point and result.Ray's origin
+                o = q;
+                o.x = q.x + FT_EPS * 0.125f;  // h = epsilon / 8, SdfForm.fs:115
                 phase = PH_N0;
             } else if (event == 5) {
-                // Material.Color at the un-moved hit origin `o` (SdfObject.fs:75-77)
-                leaf_obj = (FT_CHAIN_MAT && CHAIN && S.chain_mat_valid) ? chain_leaf_from_best(S, o, (uint32_t)leaf_obj)
-                                                        : material_leaf<COUNT>(S, o, acc);
                 lc = V3{S.bg[0], S.bg[1], S.bg[2]};  // SdfScene.fs:12
                 shadow_mask = 0;
                 light = 0;
