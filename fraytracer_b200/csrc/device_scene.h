@@ -41,7 +41,7 @@ struct int4 { int x, y, z, w; };
 #endif
 
 enum : uint32_t {
-    FT_K_SPHERE = 1,
+    FT_K_SPHERE = 0,  // 0: "is a sphere" is one unsigned comparison of the word
     FT_K_CAPSULE = 2,
     FT_K_TORUS = 3,
     FT_K_TRIANGLE = 4,

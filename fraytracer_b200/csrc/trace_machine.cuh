@@ -193,6 +193,12 @@ struct RenderJobT {
 typedef RenderJobT<false> RenderJob;      // device-memory destination: plain per-pixel stores (2-3 % faster on the device)
 typedef RenderJobT<true> RenderTileJob;   // mapped host memory: whole tiles as 128-bit stores
 
+// (Measured and rejected, round 2: staging finished tiles in an L2-resident device frame and letting the warp that completes the
+// last tile of a group of four vertically adjacent tiles copy the group's 384-byte column runs to the host frame in one go --
+// one atomic per tile, no waiting.  The PCIe microbenchmark favours long runs (96-byte runs in scattered order 26-29 GB/s, 384-byte
+// runs 48-50 GB/s), yet ft_render got slower, config 2 0.870 -> 1.000 ms, config 5 at 4K 2.99 -> 3.08 ms: a tile's pixels then leave
+// only when the slowest of four tiles is done, and the fence per tile waits behind the warp's own host stores.)
+
 // Image.render of this rank's column strips, fused with the framebuffer gather: every finished
 // pixel is stored at its final x-major position in the framebuffer of EVERY destination -- the rank's own and its
 // peers', mapped through CUDA IPC, so the stores travel over NVLink / NVSwitch while the rest of the tile is still

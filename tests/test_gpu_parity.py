@@ -510,6 +510,29 @@ def test_tile_order_hints_change_nothing_but_the_schedule():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("size", [(64, 72), (128, 32), (8, 8), (4, 8), (400, 248), (62, 72), (64, 70)])
+def test_zero_copy_frames_equal_the_oracle(size):
+    """ft_render into a mapped host frame (RenderTileJob: whole tiles leave as 128-bit stores): frames made of complete 4 x 8 tiles
+    (column heights of 9, 4, 1 and 31 tiles; a single tile) and frames with partial tiles at either edge.  Every frame of a
+    sequence (natural order, then ranked orders) must equal the oracle bit for bit, with no pixel left unwritten."""
+    import ctypes as C
+
+    X, Y = size
+    w = scenes.spheres_capsules_scene(width=X, height=Y)
+    tracer = ft.SceneTracer(w.scene, device=0)
+    ref = O.OracleScene(tracer.description).render(w.camera, X, Y, w.epsilon, w.length)
+    host = C.c_void_p()
+    A.check(tracer.lib.ft_host_alloc(C.byref(host), X * Y * 12))
+    mapped = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(X, Y, 3))
+    for frame in range(5):
+        mapped.fill(np.nan)
+        tracer.render(w.camera, w.size, w.epsilon, w.length, out=mapped)
+        assert np.array_equal(bits(mapped), bits(ref["rgb"])), frame
+    A.check(tracer.lib.ft_host_free(host))
+    tracer.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("make", [scenes.default_scene, scenes.spheres_capsules_scene])
 def test_hinted_frames_equal_the_first_frame_at_full_size(make):
     """BASELINE frame sizes (1000x1000, 1920x1080): every later frame of a shape -- drawn in ranked tile order, a permutation that
