@@ -155,6 +155,8 @@ struct ft_scene {
     bool ext_count = false;  // ft_scene_set_debug bit 3
     // destinations behind PCIe (mapped host memory): FT_RANK_TIMED by default (tile_rank.cu); 0 = plain LPT, 1 = LPT read from
     // both ends alternately (RenderParams::order_mode) -- experiments
+    // (re-measured after the round's kernel work, ft_render config 2 / config 5 at 4K, ms: split 110 0.905 / 3.32, 150 0.876 / 2.96..3.14,
+    // 200 0.881 / 2.90, 300 0.899 / 2.77; shift 1 0.866..0.889 / 2.88..3.2, shift 2 0.931 / 2.82: nothing beats the defaults on both)
     int hint_pcie_mode = FT_RANK_TIMED, hint_pcie_shift = 0, hint_split_pct = 150;
     std::mutex mu;
 

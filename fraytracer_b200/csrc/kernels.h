@@ -34,9 +34,10 @@ struct RenderParams {
                          // order[1], order[n-2] ...) -- for destinations behind PCIe, where the cheap tiles' stores must not all
                          // arrive at the end of the launch
     int order_shift;     // order[] ranks units of (1 << order_shift) consecutive tiles (vertical neighbours: tile ids run along y).
-                         // 0 for device destinations; 2 behind PCIe, where neighbouring 96-byte column runs must be written at about
-                         // the same time to leave the GPU as full lines (measured, tools/micro/pcie_store.cu: 4x8 tiles in
-                         // scattered order 29 GB/s, in natural order 47 GB/s, 4x32 units in scattered order 46-48 GB/s)
+                         // 0 in every shipped path.  (Units were meant for destinations behind PCIe, where neighbouring 96-byte
+                         // column runs leave the GPU as full lines when they are written at about the same time -- tools/micro/
+                         // pcie_store.cu: 4x8 tiles in scattered order 29 GB/s, in natural order 47 GB/s, 4x32 units in scattered
+                         // order 46-48 GB/s -- but in ft_render the timed merge of single tiles measured best, ft_api.cu.)
 };
 
 // Which pixels a rank renders and where they go (multi-GPU): column strips dealt round-robin

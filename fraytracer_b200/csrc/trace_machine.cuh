@@ -371,6 +371,9 @@ __global__ void __launch_bounds__(MB, FT_MINB) machine_kernel(const __grid_const
     // event counters live in shared memory (one row per warp, RED.shared on the rare transition paths)
     // FT_TILE_STORE: finished pixels wait in the warp's shared-memory row until the whole tile leaves at once (store_tile)
     constexpr bool TILE_STORE = FT_TILE_STORE && Job::kTileStore && FT_REFILL_MIN >= 32;
+    // (Measured and rejected: dropping the lane's `slot` -- in whole-tile lockstep it can be formed again from the tile id when the
+    // pixel is stored.  ptxas keeps ONE loop-carried value in the evaluator's result register and spills it around the body in
+    // every iteration (STL at the head, LDL.LU at the end); without `slot` it picks another, and config 2 went 0.705 -> 0.716 ms.)
     __shared__ __align__(16) float sh_tile[TILE_STORE ? MB / 32 : 1][TILE_STORE ? 96 : 4];
     float *const wtile = sh_tile[TILE_STORE ? (threadIdx.x >> 5) : 0];
     long long tile_base = -1;  // the chunk in flight (uniform): staged pixels, cost record
