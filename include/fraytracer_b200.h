@@ -314,7 +314,10 @@ FT_API int ft_render(ft_scene *scene, const ft_camera *camera, int32_t width, in
  * in out_rgb ([local_strip][strip_width][height][3]) so that N ranks can
  * all-gather equal-sized buffers; world == 1 gives the plain FColor[X,Y].
  * stats (optional, host) is filled only when FT_FLAG_COUNTERS forces a
- * synchronisation.                                                           */
+ * synchronisation.  A scene handle owns ONE block of device counters: a call
+ * that passes `stats` must not overlap other launches of the same handle on
+ * other streams (their counts would mix); calls with stats == NULL hand the
+ * kernel no counter block and may overlap freely.                            */
 FT_API int ft_render_device(ft_scene *scene, const ft_camera *camera, int32_t width, int32_t height,
                             float epsilon, float length, uint32_t flags, int32_t strip_width,
                             int32_t rank, int32_t world, float *d_out_rgb, int32_t *d_out_leaf,
