@@ -7,6 +7,7 @@ behaviour of .NET's System.Random, (b) distances/boundaries derived by hand from
 """
 import json
 import math
+import struct
 import os
 
 import numpy as np
@@ -249,6 +250,14 @@ def test_lens_and_camera_quirks():
     cam = O.camera_look_at((0, 0, -10), (0, 0, 0), (0, 1, 0), nps)
     assert list(cam.forward) == [0, 0, 1]
     assert list(cam.right_scaled) == [nps, 0, 0] and list(cam.up_scaled) == [0, nps, 0]
+    # FSharp.Core 5.0.1 evaluates `sin` of a float32 in double and rounds once; a later FSharp.Core calling MathF.Sin would give
+    # the same NearPlaneSize at the reference's own field of view: the correctly rounded float32 sine of 30 is 0xbf7cefa4 either way
+    # (the double-precision sine lies far from the midpoints between neighbouring float32 values, so the float32 result does not
+    # depend on how the last bits of a correctly rounded or nearly correctly rounded sine fall)
+    assert struct.unpack("<I", struct.pack("<f", nps))[0] == 0xBF7CEFA4
+    lo, hi = struct.unpack("<f", struct.pack("<I", 0xBF7CEFA3))[0], struct.unpack("<f", struct.pack("<I", 0xBF7CEFA5))[0]
+    exact = math.sin(30.0)
+    assert abs(nps - exact) < 0.25 * abs(lo - nps) and abs(nps - exact) < 0.25 * abs(hi - nps)
 
 
 def test_trace_single_sphere_by_hand():
